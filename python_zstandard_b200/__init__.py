@@ -1,0 +1,60 @@
+"""python_zstandard_b200 -- B200-native backend for python-zstandard's batch path.
+
+Exposes the reference's names for that path (zstandard/__init__.pyi:312-320, 423-438 and the
+buffer types) so a caller can ``import python_zstandard_b200 as zstandard``:
+
+    ZstdCompressor(...).multi_compress_to_buffer / .compress
+    ZstdDecompressor(...).multi_decompress_to_buffer / .decompress
+    BufferWithSegments, BufferSegments, BufferSegment, BufferWithSegmentsCollection
+    ZstdCompressionDict, ZstdError, frame helpers and constants
+
+All codec work runs as CUDA kernels in ``libzb200.so`` (C ABI: include/zb200.h).
+"""
+from .errors import ZstdError  # noqa: F401
+from .buffers import (BufferSegment, BufferSegments, BufferWithSegments,  # noqa: F401
+                      BufferWithSegmentsCollection)
+from .dictionary import (ZstdCompressionDict, DICT_TYPE_AUTO, DICT_TYPE_RAWCONTENT,  # noqa: F401
+                         DICT_TYPE_FULLDICT)
+from .decompressor import ZstdDecompressor, FORMAT_ZSTD1, FORMAT_ZSTD1_MAGICLESS  # noqa: F401
+
+__version__ = "0.25.0+b200"
+backend = "b200"
+backend_features = {"buffer_types", "multi_decompress_to_buffer"}
+
+ZSTD_VERSION = (1, 5, 7)
+FRAME_HEADER = b"\x28\xb5\x2f\xfd"
+MAGIC_NUMBER = 0xFD2FB528
+BLOCKSIZE_MAX = 131072
+BLOCKSIZE_LOG_MAX = 17
+CONTENTSIZE_UNKNOWN = (1 << 64) - 1
+CONTENTSIZE_ERROR = (1 << 64) - 2
+MAX_COMPRESSION_LEVEL = 22
+WINDOWLOG_MIN = 10
+WINDOWLOG_MAX = 31
+
+
+def frame_content_size(data):
+    """zstandard.frame_content_size (c-ext/backend_c.c:43-72)."""
+    import ctypes as C
+    from . import _native
+    b = bytes(memoryview(data))
+    info = _native.FrameInfo()
+    _native.lib().zb200_frame_info(b, len(b), C.byref(info))
+    if info.status:
+        raise ZstdError("error when determining content size")
+    if info.content_size == CONTENTSIZE_UNKNOWN:
+        return -1
+    return info.content_size
+
+
+def frame_header_size(data):
+    """zstandard.frame_header_size (c-ext/backend_c.c:74-102)."""
+    import ctypes as C
+    from . import _native
+    b = bytes(memoryview(data))
+    info = _native.FrameInfo()
+    _native.lib().zb200_frame_info(b, len(b), C.byref(info))
+    if info.status:
+        raise ZstdError("could not determine frame header size: %s"
+                        % _native.lib().zb200_error_string(info.status).decode())
+    return info.header_size

@@ -1,0 +1,466 @@
+// zb_api.cu -- the C ABI of libzb200.so (include/zb200.h): contexts, memory pools, the host
+// orchestration that replaces decompress_from_framesources (c-ext/decompressor.c:1186-1455).
+//
+// The reference partitions the batch over a pthread pool (POOL_add, c-ext/decompressor.c:1290-1320);
+// here the partition is the CUDA grid and the "workers" are warps.  What stays on the host is only
+// what the reference also does on its calling thread: argument marshalling, output ownership and
+// first-error selection.
+#include "zb_common.cuh"
+#include "../../include/zb200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+extern "C" {
+void zb_launch_default_tables(cudaStream_t st);
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, cudaStream_t st);
+void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
+                     u32* status, cudaStream_t st);
+void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
+                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u8* lane_scratch, u32 n_warps, u32* work_counter,
+                       ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st);
+void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
+                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st);
+void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,
+                      u32* first_error, cudaStream_t st);
+void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;          // grow-only with slack
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBlock { void* p; size_t cap; bool busy; };
+
+}  // namespace
+
+struct zb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int sm_count = 148;
+    // device arenas (grow-only)
+    DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs;
+    u32 entropy_warps = 0;
+    // pinned pool
+    std::mutex mu;
+    std::vector<PinnedBlock> pinned;
+    // profiling
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    struct Span { int k; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    float k_ms[ZB200_K_COUNT] = {0}; u32 k_launch[ZB200_K_COUNT] = {0};
+    u64 last_scratch = 0;
+    int live_results = 0;
+};
+
+struct zb200_ddict {
+    zb200_ctx* ctx; void* d_raw = nullptr; ZbDictDigest* d_digest = nullptr; ZbDictDev dev; size_t size = 0;
+};
+
+struct zb200_result {
+    zb200_ctx* ctx; void* data = nullptr; bool data_on_device = false; bool data_pinned_pool = false;
+    u64 size = 0; size_t n = 0;
+    std::vector<zb200_segment> segs;
+    bool has_error = false; size_t err_item = 0; int err_code = 0; u64 err_got = 0, err_expected = 0;
+};
+
+namespace {
+
+int fail(zb200_ctx* c, const char* what, cudaError_t e)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+    if (c) c->last_error = buf;
+    return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, #call, e_); } while (0)
+
+cudaEvent_t get_event(zb200_ctx* c)
+{
+    if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+    return c->ev_pool[c->ev_used++];
+}
+struct KSpan {
+    zb200_ctx* c; int k; cudaEvent_t a = nullptr;
+    KSpan(zb200_ctx* c_, int k_) : c(c_), k(k_) { if (c->prof) { a = get_event(c); cudaEventRecord(a, c->stream); } c->k_launch[k]++; }
+    ~KSpan() { if (c->prof) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({k, a, b}); } }
+};
+void fold_spans(zb200_ctx* c)
+{
+    for (auto& s : c->spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->k_ms[s.k] += ms; }
+    c->spans.clear(); c->ev_used = 0;
+}
+
+void* pinned_get(zb200_ctx* c, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    PinnedBlock* best = nullptr;
+    for (auto& b : c->pinned) if (!b.busy && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+    if (best) { best->busy = true; return best->p; }
+    // drop idle blocks that are too small before growing
+    for (size_t i = 0; i < c->pinned.size();) {
+        if (!c->pinned[i].busy) { cudaFreeHost(c->pinned[i].p); c->pinned.erase(c->pinned.begin() + (long)i); } else i++;
+    }
+    void* p = nullptr; size_t cap = bytes + bytes / 16 + 4096;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    c->pinned.push_back({p, cap, true});
+    return p;
+}
+void pinned_put(zb200_ctx* c, void* p)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    for (auto& b : c->pinned) if (b.p == p) { b.busy = false; return; }
+}
+bool is_pinned_pool(zb200_ctx* c, const void* p)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    for (auto& b : c->pinned) if ((const char*)p >= (const char*)b.p && (const char*)p < (const char*)b.p + b.cap) return true;
+    return false;
+}
+
+ZbDictDev no_dict() { ZbDictDev d; memset(&d, 0, sizeof d); return d; }
+
+}  // namespace
+
+extern "C" {
+
+int zb200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int zb200_ctx_create(int device, zb200_ctx** out)
+{
+    *out = nullptr;
+    int n = zb200_device_count();
+    if (n <= 0 || device < 0 || device >= n) return -2;          // no CUDA device: there is no CPU path
+    zb200_ctx* ctx = new zb200_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return -1;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    zb_launch_default_tables(ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -1; }
+    *out = ctx;
+    return 0;
+}
+
+void zb200_ctx_destroy(zb200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
+                     &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs};
+    for (auto* b : all) b->release();
+    for (auto& b : ctx->pinned) cudaFreeHost(b.p);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* zb200_ctx_last_error(const zb200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+void* zb200_ctx_stream(zb200_ctx* ctx) { return (void*)ctx->stream; }
+int zb200_ctx_synchronize(zb200_ctx* ctx) { cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+const char* zb200_error_string(int code)
+{
+    // strings of ERR_getErrorString (zstd/zstd.c, error_private.c) so messages match the reference's
+    switch (code) {
+    case 0: return "No error detected";
+    case 1: return "Error (generic)";
+    case 10: return "Unknown frame descriptor";
+    case 12: return "Version not supported";
+    case 14: return "Unsupported frame parameter";
+    case 16: return "Frame requires too much memory for decoding";
+    case 20: return "Data corruption detected";
+    case 22: return "Restored data doesn't match checksum";
+    case 24: return "Header of Literals' block doesn't respect format specification";
+    case 30: return "Dictionary is corrupted";
+    case 32: return "Dictionary mismatch";
+    case 40: return "Unsupported parameter";
+    case 42: return "Parameter is out of bound";
+    case 44: return "tableLog requires too much memory : unsupported";
+    case 46: return "Unsupported max Symbol Value : too large";
+    case 48: return "Specified maxSymbolValue is too small";
+    case 64: return "Allocation error : not enough memory";
+    case 70: return "Destination buffer is too small";
+    case 72: return "Src size is incorrect";
+    case 74: return "Operation on NULL destination buffer";
+    case ZB200_E_UNKNOWN_SIZE: return "could not determine decompressed size";
+    case ZB200_E_SIZE_MISMATCH: return "decompressed size mismatch";
+    default: return "Unspecified error code";
+    }
+}
+
+void* zb200_host_alloc(zb200_ctx* ctx, size_t bytes) { cudaSetDevice(ctx->device); return pinned_get(ctx, bytes ? bytes : 1); }
+void  zb200_host_free(zb200_ctx* ctx, void* p) { pinned_put(ctx, p); }
+void* zb200_device_alloc(zb200_ctx* ctx, size_t bytes)
+{
+    cudaSetDevice(ctx->device); void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void zb200_device_free(zb200_ctx* ctx, void* p) { cudaSetDevice(ctx->device); cudaFree(p); }
+int zb200_memcpy_h2d(zb200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return 0;
+}
+int zb200_memcpy_d2h(zb200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return 0;
+}
+
+// ---------------------------------------------------------------- dictionaries
+int zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddict** out)
+{
+    *out = nullptr;
+    if (!ctx || !dict || size == 0 || size > 0x7FFFFFFFu) return fail(ctx, "zb200_ddict_create", cudaSuccess);
+    cudaSetDevice(ctx->device);
+    zb200_ddict* d = new zb200_ddict(); d->ctx = ctx; d->size = size;
+    cudaError_t e = cudaMalloc(&d->d_raw, size + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_digest, sizeof(ZbDictDigest));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d->d_raw, dict, size, cudaMemcpyHostToDevice, ctx->stream);
+    ZbDictDigest* h = nullptr;
+    if (e == cudaSuccess) {
+        zb_launch_digest_dict((const u8*)d->d_raw, (u32)size, d->d_digest, ctx->stream);
+        h = (ZbDictDigest*)malloc(sizeof(ZbDictDigest));
+        e = cudaMemcpyAsync(h, d->d_digest, sizeof(ZbDictDigest), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); zb200_ddict_free(d); return fail(ctx, "zb200_ddict_create", e); }
+    if (h->status != ZB_OK) { int code = (int)h->status; free(h); zb200_ddict_free(d); ctx->last_error = zb200_error_string(code); return -code; }
+    ZbDictDev& v = d->dev; memset(&v, 0, sizeof v);
+    v.content = (const u8*)d->d_raw + h->content_off; v.content_size = (u32)size - h->content_off;
+    v.dict_id = h->dict_id; v.has_entropy = h->has_entropy;
+    v.huf = d->d_digest->huf; v.huf_log = h->huf_log;
+    v.ll = d->d_digest->ll; v.of = d->d_digest->of; v.ml = d->d_digest->ml;
+    v.ll_log = h->ll_log; v.of_log = h->of_log; v.ml_log = h->ml_log;
+    v.rep[0] = h->rep[0]; v.rep[1] = h->rep[1]; v.rep[2] = h->rep[2];
+    free(h);
+    *out = d;
+    return 0;
+}
+void zb200_ddict_free(zb200_ddict* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    if (d->d_raw) cudaFree(d->d_raw);
+    if (d->d_digest) cudaFree(d->d_digest);
+    delete d;
+}
+uint32_t zb200_ddict_id(const zb200_ddict* d) { return d ? d->dev.dict_id : 0; }
+
+// ---------------------------------------------------------------- batch decompression
+// Device-side pipeline shared by the host and device entry points.  d_src/d_segs/d_dst_sizes are device
+// pointers.  On return the output is in ctx->dst (or caller_dst), segment table + status on the host.
+static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_segs, size_t n, const u64* d_dst_sizes,
+                          const zb200_ddict* dict, zb200_result* res, bool copy_back, bool exact_sizes)
+{
+    u32 const nf = (u32)n;
+    ZbDictDev dd = dict ? dict->dev : no_dict();
+    CK(ctx->info.ensure(n * sizeof(ZbFrameInfo)));
+    CK(ctx->place.ensure((n + 1) * sizeof(ZbFramePlace)));
+    CK(ctx->status.ensure(n * sizeof(u32)));
+    CK(ctx->out_sizes.ensure(n * sizeof(u64)));
+    CK(ctx->out_segs.ensure(n * sizeof(ZbSegment)));
+    CK(ctx->small.ensure(256));
+    u64* d_totals = ctx->small.as<u64>();                 // [0..3] totals
+    u32* d_counter = (u32*)(d_totals + 8);                // work counter
+    u32* d_first_err = d_counter + 1;
+    u32 init[2] = {0, 0xFFFFFFFFu};
+    CK(cudaMemcpyAsync(d_counter, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+
+    { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), ctx->stream); }
+    { KSpan s(ctx, ZB200_K_PLACE);
+      zb_launch_place(ctx->info.as<ZbFrameInfo>(), d_dst_sizes, nf, ctx->place.as<ZbFramePlace>(), d_totals,
+                      ctx->status.as<u32>(), ctx->stream); }
+    u64 totals[4];
+    CK(cudaMemcpyAsync(totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    // persistent entropy grid: enough warps to fill the machine, no more than the work
+    u32 warps = (u32)ctx->sm_count * 16;
+    u32 need_warps = (nf + 31) / 32;
+    if (warps > need_warps) warps = need_warps;
+    warps = (warps + 3) & ~3u;
+    CK(ctx->lane.ensure((size_t)warps * 32 * ZB_LANE_BYTES));
+    CK(ctx->blocks.ensure((totals[1] + 1) * sizeof(ZbBlock)));
+    CK(ctx->seqs.ensure((totals[2] + 1) * sizeof(ZbSeq)));
+    CK(ctx->lits.ensure(totals[3] + 64));
+    CK(ctx->dst.ensure(totals[0] + 64));
+    ctx->last_scratch = (totals[1] + 1) * sizeof(ZbBlock) + (totals[2] + 1) * sizeof(ZbSeq) + totals[3];
+
+    { KSpan s(ctx, ZB200_K_ENTROPY);
+      zb_launch_entropy(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
+                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->lane.as<u8>(), warps, d_counter, dd,
+                        ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->stream); }
+    { KSpan s(ctx, ZB200_K_EXECUTE);
+      zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
+                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), nf, dd, ctx->stream); }
+    { KSpan s(ctx, ZB200_K_FINISH);
+      zb_launch_finish(ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->status.as<u32>(), nf,
+                       ctx->out_segs.as<ZbSegment>(), d_first_err, ctx->stream); }
+
+    res->n = n; res->size = totals[0];
+    res->segs.resize(n);
+    u32 first_err = 0xFFFFFFFFu;
+    CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&first_err, d_first_err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (copy_back) {
+        res->data = pinned_get(ctx, totals[0] ? totals[0] : 1);
+        if (!res->data) return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation);
+        res->data_pinned_pool = true;
+        CK(cudaMemcpyAsync(res->data, ctx->dst.p, totals[0], cudaMemcpyDeviceToHost, ctx->stream));
+    } else { res->data = ctx->dst.p; res->data_on_device = true; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prof) fold_spans(ctx);
+    if (first_err != 0xFFFFFFFFu) {
+        u32 code = 0; u64 got = 0; ZbFramePlace pl;
+        cudaMemcpy(&code, ctx->status.as<u32>() + first_err, sizeof code, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&pl, ctx->place.as<ZbFramePlace>() + first_err, sizeof pl, cudaMemcpyDeviceToHost);
+        res->has_error = true; res->err_item = first_err; res->err_code = (int)code; res->err_got = got; res->err_expected = pl.dst_cap;
+    }
+    return 0;
+}
+
+static int decompress_common(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                             const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
+{
+    *out = nullptr;
+    if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_decompress_batch: bad arguments", cudaSuccess);
+    cudaSetDevice(ctx->device);
+    const u8* d_src; const ZbSegment* d_segs; const u64* d_dst_sizes = nullptr;
+    if (flags & ZB200_SRC_DEVICE) {
+        d_src = (const u8*)src_base; d_segs = (const ZbSegment*)segs; d_dst_sizes = dst_sizes;
+    } else {
+        // host input: one contiguous copy of the referenced span (the data a BufferWithSegments holds)
+        u64 lo = ~0ull, hi = 0;
+        for (size_t i = 0; i < n; i++) { if (segs[i].offset < lo) lo = segs[i].offset; if (segs[i].offset + segs[i].length > hi) hi = segs[i].offset + segs[i].length; }
+        if (hi < lo) { lo = hi = 0; }
+        CK(ctx->src.ensure(hi - lo + 64));
+        CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
+        CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+        if (lo == 0) CK(cudaMemcpyAsync(ctx->segs.p, segs, n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        else {
+            std::vector<zb200_segment> tmp(segs, segs + n);
+            for (auto& s : tmp) s.offset -= lo;
+            CK(cudaMemcpyAsync(ctx->segs.p, tmp.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
+        if (dst_sizes) {
+            CK(ctx->dst_sizes.ensure(n * sizeof(u64)));
+            CK(cudaMemcpyAsync(ctx->dst_sizes.p, dst_sizes, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+            d_dst_sizes = ctx->dst_sizes.as<u64>();
+        }
+    }
+    zb200_result* res = new zb200_result(); res->ctx = ctx;
+    int rc = run_decompress(ctx, d_src, d_segs, n, d_dst_sizes, dict, res, !(flags & ZB200_DST_DEVICE),
+                            !(flags & ZB200_SIZES_ARE_CAPACITY));
+    if (rc) { zb200_result_free(res); return rc; }
+    *out = res;
+    return 0;
+}
+
+int zb200_decompress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                           const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
+{
+    return decompress_common(ctx, src_base, segs, n, dst_sizes, dict, flags, out);
+}
+
+int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
+                                const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
+{
+    *out = nullptr;
+    if (!ctx || !srcs || !sizes || n == 0) return fail(ctx, "zb200_decompress_batch_ptrs: bad arguments", cudaSuccess);
+    cudaSetDevice(ctx->device);
+    // gather the independent buffers into pinned staging (this is the copy a list-of-bytes input costs anyway)
+    u64 total = 0; for (size_t i = 0; i < n; i++) total += sizes[i];
+    u8* stage = (u8*)pinned_get(ctx, total ? total : 1);
+    if (!stage) return fail(ctx, "pinned staging allocation", cudaErrorMemoryAllocation);
+    std::vector<zb200_segment> segs(n); u64 pos = 0;
+    for (size_t i = 0; i < n; i++) { memcpy(stage + pos, srcs[i], sizes[i]); segs[i].offset = pos; segs[i].length = sizes[i]; pos += sizes[i]; }
+    int rc = decompress_common(ctx, stage, segs.data(), n, dst_sizes, dict, flags & ~ZB200_SRC_DEVICE, out);
+    pinned_put(ctx, stage);
+    return rc;
+}
+
+const void* zb200_result_data(const zb200_result* r) { return r->data; }
+uint64_t zb200_result_size(const zb200_result* r) { return r->size; }
+size_t zb200_result_count(const zb200_result* r) { return r->n; }
+const zb200_segment* zb200_result_segments(const zb200_result* r) { return r->segs.data(); }
+int zb200_result_first_error(const zb200_result* r, size_t* item, int* code, uint64_t* got, uint64_t* expected)
+{
+    if (!r->has_error) return 0;
+    if (item) *item = r->err_item; if (code) *code = r->err_code; if (got) *got = r->err_got; if (expected) *expected = r->err_expected;
+    return 1;
+}
+void zb200_result_free(zb200_result* r)
+{
+    if (!r) return;
+    if (r->data && r->data_pinned_pool) pinned_put(r->ctx, r->data);
+    delete r;
+}
+
+// ---------------------------------------------------------------- frame inspection (host, header only)
+int zb200_frame_info(const void* vsrc, size_t n, zb200_frame_info_t* o)
+{
+    // restates ZSTD_getFrameHeader_advanced, zstd/zstd.c:43668-43778 (same rules as zb_parse_header on the device)
+    const u8* s = (const u8*)vsrc;
+    memset(o, 0, sizeof *o); o->content_size = ~0ull;
+    auto rd = [&](size_t p, int k) { u64 v = 0; for (int i = 0; i < k; i++) v |= (u64)s[p + i] << (8 * i); return v; };
+    if (n < 5) { o->status = (n >= 4 && rd(0, 4) != ZB_MAGIC && ((u32)rd(0, 4) & 0xFFFFFFF0u) != ZB_MAGIC_SKIP) ? ZB_E_PREFIX_UNKNOWN : ZB_E_SRCSIZE_WRONG; return 0; }
+    u32 magic = (u32)rd(0, 4);
+    if (magic != ZB_MAGIC) { o->status = ZB_E_PREFIX_UNKNOWN; return 0; }
+    u32 fhd = s[4], single = (fhd >> 5) & 1, did = fhd & 3, fcs = fhd >> 6;
+    u32 need = 5 + (single ? 0 : 1) + (did == 3 ? 4 : did) + (fcs == 0 ? (single ? 1 : 0) : (1u << fcs));
+    if (n < need) { o->status = ZB_E_SRCSIZE_WRONG; return 0; }
+    o->header_size = need;
+    if (fhd & 8) { o->status = ZB_E_FRAMEPARAM_UNSUPPORTED; return 0; }
+    o->has_checksum = (fhd >> 2) & 1;
+    size_t pos = 5;
+    if (!single) { u32 wl = s[pos++], wlog = (wl >> 3) + 10; if (wlog > 31) { o->status = ZB_E_WINDOW_TOO_LARGE; return 0; }
+                   o->window_size = 1ull << wlog; o->window_size += (o->window_size >> 3) * (wl & 7); }
+    if (did) { int k = did == 3 ? 4 : (int)did; o->dict_id = (u32)rd(pos, k); pos += (size_t)k; }
+    if (fcs == 0) { if (single) o->content_size = s[pos]; }
+    else if (fcs == 1) o->content_size = rd(pos, 2) + 256;
+    else if (fcs == 2) o->content_size = rd(pos, 4);
+    else o->content_size = rd(pos, 8);
+    if (single) o->window_size = o->content_size;
+    return 0;
+}
+
+// ---------------------------------------------------------------- profiling
+void zb200_profile_enable(zb200_ctx* ctx, int on) { ctx->prof = on != 0; }
+void zb200_profile_reset(zb200_ctx* ctx) { memset(ctx->k_ms, 0, sizeof ctx->k_ms); memset(ctx->k_launch, 0, sizeof ctx->k_launch); }
+int zb200_profile_read(zb200_ctx* ctx, float ms[ZB200_K_COUNT], uint32_t launches[ZB200_K_COUNT])
+{
+    memcpy(ms, ctx->k_ms, sizeof ctx->k_ms); memcpy(launches, ctx->k_launch, sizeof ctx->k_launch); return 0;
+}
+const char* zb200_kernel_name(int k)
+{
+    static const char* names[ZB200_K_COUNT] = {"zb_scan_frames", "zb_place_frames", "zb_entropy_decode", "zb_execute", "zb_finish"};
+    return (k >= 0 && k < ZB200_K_COUNT && names[k]) ? names[k] : "";
+}
+uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// zb_common.cuh -- shared device-side definitions of the B200 zstd batch codec.
+//
+// Format constants are RFC 8878's (the reference holds them at zstd/zstd.c:15596-15662
+// and :41266-41290); everything else here is this project's own design.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef uint8_t  u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ---- status codes: numeric values follow zstd_errors.h so host code can print
+// ---- the reference's own error strings (c-ext/decompressor.c:1328-1371)
+enum : u32 {
+    ZB_OK = 0,
+    ZB_E_GENERIC = 1,
+    ZB_E_PREFIX_UNKNOWN = 10,
+    ZB_E_FRAMEPARAM_UNSUPPORTED = 14,
+    ZB_E_WINDOW_TOO_LARGE = 16,
+    ZB_E_CORRUPTION = 20,
+    ZB_E_CHECKSUM_WRONG = 22,
+    ZB_E_LITERALS_HEADER_WRONG = 24,
+    ZB_E_DICT_CORRUPTED = 30,
+    ZB_E_DICT_WRONG = 32,
+    ZB_E_TABLELOG_TOO_LARGE = 44,
+    ZB_E_MAXSYMBOL_TOO_SMALL = 48,
+    ZB_E_DSTSIZE_TOO_SMALL = 70,
+    ZB_E_SRCSIZE_WRONG = 72,
+    // ours (python-zstandard worker errors, c-ext/decompressor.c:911-917)
+    ZB_E_UNKNOWN_SIZE = 200,
+    ZB_E_SIZE_MISMATCH = 201,
+};
+
+#define ZB_MAGIC       0xFD2FB528u
+#define ZB_MAGIC_DICT  0xEC30A437u
+#define ZB_MAGIC_SKIP  0x184D2A50u
+#define ZB_BLOCK_MAX   (128u << 10)
+#define ZB_CONTENT_UNKNOWN 0xFFFFFFFFFFFFFFFFull
+
+struct ZbSegment { u64 offset, length; };       // == BufferSegment, c-ext/python-zstandard.h:307-313
+
+// result of the frame scan (one per frame)
+struct ZbFrameInfo {
+    u64 content_size;     // from the header, ZB_CONTENT_UNKNOWN if absent
+    u32 n_blocks;
+    u32 n_seq_rec;        // sequence records needed: sum(nbSeq + 1) over compressed blocks
+    u32 n_lit;            // literal bytes that must be regenerated into scratch (Huffman coded)
+    u32 status;
+    u32 dict_id;
+    u32 flags;            // bit0: checksum present
+};
+
+// per-frame placement, produced by the offsets scan
+struct ZbFramePlace {
+    u64 dst_off;          // byte offset of the frame's output in dst
+    u64 dst_cap;          // bytes the frame may write
+    u64 blk_off;          // first ZbBlock of the frame
+    u64 seq_off;          // first sequence record
+    u64 lit_off;          // first literal scratch byte
+};
+
+enum : u32 { ZB_BLK_RAW = 0, ZB_BLK_RLE = 1, ZB_BLK_COMPRESSED = 2 };
+enum : u32 { ZB_LIT_RAW = 0, ZB_LIT_RLE = 1, ZB_LIT_SCRATCH = 2 };
+
+// one block of a frame, written by the entropy stage for the execute stage
+struct ZbBlock {
+    u64 out_pos;          // frame-relative start of the block's output
+    u64 src_pos;          // raw/rle block: payload position in src.  compressed: literal position
+                          //   (in src for ZB_LIT_RAW, in the literal scratch for ZB_LIT_SCRATCH)
+    u64 seq_pos;          // first sequence record (absolute index)
+    u32 kind;             // ZB_BLK_*
+    u32 regen;            // regenerated size of the block
+    u32 lit_kind;         // ZB_LIT_*  (ZB_LIT_RLE: byte value in lit_byte)
+    u32 n_lit;
+    u32 n_seq;
+    u32 lit_byte;
+};
+
+// sequence record: .x = literal start (block-relative index into the block's literals)
+//                  .y = output start of the sequence's literals (block-relative)
+//                  .z = match length, .w = match offset (real distance, repcodes resolved)
+// A sentinel record {.x = literals consumed, .y = output produced} ends every block.
+typedef uint4 ZbSeq;
+
+// FSE decode cell, same information as ZSTD_seqSymbol (zstd/zstd.c:41301-41306)
+struct __align__(8) ZbFseCell { u16 next; u8 nb; u8 add_bits; u32 base; };
+
+// digested dictionary, device resident (restates what ZSTD_loadDEntropy keeps, zstd/zstd.c:44673-44757)
+struct ZbDictDev {
+    const u8* content; u32 content_size; u32 dict_id;
+    const u16* huf; u32 huf_log; u32 has_entropy;
+    const ZbFseCell* ll; const ZbFseCell* of; const ZbFseCell* ml;
+    u32 ll_log, of_log, ml_log;
+    u32 rep[3];
+};
+
+// dictionary digest as the device kernel writes it
+struct ZbDictDigest {
+    u16 huf[4096]; ZbFseCell ll[512]; ZbFseCell ml[512]; ZbFseCell of[256]; ZbFseCell wt[64];
+    u32 huf_log, ll_log, of_log, ml_log; u32 rep[3]; u32 dict_id; u32 content_off; u32 status; u32 has_entropy; u32 pad;
+};
+
+// per-lane scratch layout of the entropy stage
+#define ZB_HUF_CELLS   4096
+#define ZB_LANE_HUF    0                                   // u16[4096]
+#define ZB_LANE_LL     (ZB_HUF_CELLS * 2)                  // ZbFseCell[512]
+#define ZB_LANE_ML     (ZB_LANE_LL + 512 * 8)              // ZbFseCell[512]
+#define ZB_LANE_OF     (ZB_LANE_ML + 512 * 8)              // ZbFseCell[256]
+#define ZB_LANE_WT     (ZB_LANE_OF + 256 * 8)              // ZbFseCell[64]  (Huffman-weight table)
+#define ZB_LANE_BYTES  (ZB_LANE_WT + 64 * 8)               // 18944
+
+__device__ __forceinline__ u32 zb_rd16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
+__device__ __forceinline__ u32 zb_rd24(const u8* p) { return zb_rd16(p) | ((u32)p[2] << 16); }
+__device__ __forceinline__ u32 zb_rd32(const u8* p) { return zb_rd16(p) | (zb_rd16(p + 2) << 16); }
+__device__ __forceinline__ u64 zb_rd64(const u8* p) { return (u64)zb_rd32(p) | ((u64)zb_rd32(p + 4) << 32); }
+__device__ __forceinline__ int zb_hibit(u32 v) { return 31 - __clz(v); }
+
+// ---------------------------------------------------------------------------
+// Backward bit reader over an arbitrary byte range, built on ALIGNED 32-bit loads.
+// `win` holds the next unread bits at its top; `left` counts unread stream bits and
+// goes negative when the stream is over-read (the reference's BIT_DStream_overflow,
+// zstd/zstd.c:2517-2556).  Reads below the stream start return the neighbouring
+// bytes (not zeros): harmless, because left < 0 then fails the block.
+// ---------------------------------------------------------------------------
+struct ZbBitR {
+    const u32* w; int widx; u64 win; int avail; int left;
+
+    __device__ __forceinline__ bool init(const u8* s, u32 n) {
+        if (n == 0) return false;
+        u32 last = s[n - 1];
+        if (last == 0) return false;
+        uintptr_t a = (uintptr_t)s & ~(uintptr_t)3;
+        w = (const u32*)a;
+        int skew = (int)((uintptr_t)s - a);
+        int hb = zb_hibit(last);
+        int P = (skew + (int)n - 1) * 8 + hb;      // bits from the aligned base up to the end mark
+        left = ((int)n - 1) * 8 + hb;
+        if (P == 0) { win = 0; avail = 0; widx = -1; return true; }
+        int wi = (P - 1) >> 5, k = P - wi * 32;    // k in 1..32 valid bits in the top word
+        win = (u64)w[wi] << (64 - k); avail = k; widx = wi - 1;
+        refill();
+        return true;
+    }
+    __device__ __forceinline__ void refill() {
+        if (avail <= 32 && widx >= 0) { win |= (u64)w[widx] << (32 - avail); avail += 32; widx--; }
+    }
+    __device__ __forceinline__ u32 peek(u32 nb) const { return (u32)((win >> 1) >> (63 - nb)); }
+    __device__ __forceinline__ void skip(u32 nb) { win <<= nb; avail -= (int)nb; left -= (int)nb; }
+    __device__ __forceinline__ u32 read(u32 nb) { u32 v = peek(nb); skip(nb); return v; }
+};

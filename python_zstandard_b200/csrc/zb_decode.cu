@@ -1,0 +1,848 @@
+// zb_decode.cu -- batch zstd decompression for sm_100a.
+//
+// Replaces the per-segment ZSTD_decompressStream call of the reference batch path
+// (c-ext/decompressor.c:1150 -> zstd/zstd.c:45307 -> ZSTD_decompressFrame :44174).
+//
+// Design: the work of a frame is split by the KIND of parallelism it has.
+//   K1 zb_scan_frames     one LANE per frame : header + block-chain walk -> sizes for placement
+//   K2 zb_place_frames    one CTA             : exclusive scans -> per-frame offsets
+//   K3 zb_entropy_decode  one LANE per frame : the bit-serial chains (Huffman literal streams,
+//                          FSE table builds, the 3-state FSE sequence stream, repcode history).
+//                          32 independent frames advance in lock-step per warp, so every issue
+//                          slot does 32 frames' worth of serial work.
+//   K4 zb_execute         one WARP per frame : the LZ copy-execute, lane per sequence with a
+//                          frontier test for match dependencies, coalesced copies for long runs.
+#include "zb_common.cuh"
+
+// ---------------------------------------------------------------------------
+// format constants (RFC 8878 3.1.1.3.2.1; reference zstd/zstd.c:15615-15659, :41266-41290)
+// ---------------------------------------------------------------------------
+__constant__ u8 c_LL_bits[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
+__constant__ u8 c_ML_bits[53] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,
+                                 1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16};
+__constant__ u32 c_LL_base[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,
+                                  0x80,0x100,0x200,0x400,0x800,0x1000,0x2000,0x4000,0x8000,0x10000};
+__constant__ u32 c_ML_base[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,
+                                  35,37,39,41,43,47,51,59,67,83,99,0x83,0x103,0x203,0x403,0x803,0x1003,0x2003,0x4003,0x8003,0x10003};
+__constant__ short c_LL_defnorm[36] = {4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1};
+__constant__ short c_ML_defnorm[53] = {1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,
+                                       1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1};
+__constant__ short c_OF_defnorm[29] = {1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1};
+
+enum { K_LL = 0, K_OF = 1, K_ML = 2 };
+
+// default tables, built once per context by zb_build_default_tables
+__device__ ZbFseCell g_defLL[64];
+__device__ ZbFseCell g_defOF[32];
+__device__ ZbFseCell g_defML[64];
+
+// ---------------------------------------------------------------------------
+// frame header (restates ZSTD_getFrameHeader_advanced, zstd/zstd.c:43668-43778)
+// ---------------------------------------------------------------------------
+struct ZbHdr { u64 content_size; u64 window; u32 dict_id; u32 hdr_size; u32 checksum; u32 status; };
+
+__device__ static void zb_parse_header(const u8* s, u64 n, ZbHdr& h)
+{
+    h.status = ZB_OK; h.content_size = ZB_CONTENT_UNKNOWN; h.window = 0; h.dict_id = 0; h.checksum = 0; h.hdr_size = 0;
+    if (n < 5) {
+        // too short for a header: still report a wrong magic as such (:43680-43697)
+        bool zstd_ok = true, skip_ok = true;
+        const u8 zm[4] = {0x28, 0xB5, 0x2F, 0xFD}, sm[4] = {0x50, 0x2A, 0x4D, 0x18};
+        for (u32 k = 0; k < n && k < 4; k++) {
+            if (s[k] != zm[k]) zstd_ok = false;
+            if (k == 0 ? ((s[0] & 0xF0) != sm[0]) : (s[k] != sm[k])) skip_ok = false;
+        }
+        h.status = (n && !zstd_ok && !skip_ok) ? ZB_E_PREFIX_UNKNOWN : ZB_E_SRCSIZE_WRONG;
+        return;
+    }
+    u32 magic = zb_rd32(s);
+    if (magic != ZB_MAGIC) { h.status = ZB_E_PREFIX_UNKNOWN; return; }
+    u32 fhd = s[4];
+    u32 single = (fhd >> 5) & 1, did = fhd & 3, fcs = fhd >> 6;
+    u32 need = 5 + (single ? 0 : 1) + (did == 3 ? 4 : did) + (fcs == 0 ? (single ? 1 : 0) : (1u << fcs));
+    if (n < need) { h.status = ZB_E_SRCSIZE_WRONG; return; }
+    h.hdr_size = need;
+    if (fhd & 8) { h.status = ZB_E_FRAMEPARAM_UNSUPPORTED; return; }
+    h.checksum = (fhd >> 2) & 1;
+    u32 pos = 5;
+    if (!single) {
+        u32 wl = s[pos++], wlog = (wl >> 3) + 10;
+        if (wlog > 31) { h.status = ZB_E_WINDOW_TOO_LARGE; return; }
+        h.window = 1ull << wlog; h.window += (h.window >> 3) * (wl & 7);
+    }
+    if (did == 1) { h.dict_id = s[pos]; pos += 1; }
+    else if (did == 2) { h.dict_id = zb_rd16(s + pos); pos += 2; }
+    else if (did == 3) { h.dict_id = zb_rd32(s + pos); pos += 4; }
+    if (fcs == 0) { if (single) h.content_size = s[pos]; }
+    else if (fcs == 1) h.content_size = zb_rd16(s + pos) + 256;
+    else if (fcs == 2) h.content_size = zb_rd32(s + pos);
+    else h.content_size = zb_rd64(s + pos);
+    if (single) h.window = h.content_size;
+}
+
+// skip leading skippable frames (ZSTD_decompressMultiFrame, zstd/zstd.c:44318-44330)
+__device__ static bool zb_skip_skippable(const u8*& s, u64& n)
+{
+    while (n >= 8 && (zb_rd32(s) & 0xFFFFFFF0u) == ZB_MAGIC_SKIP) {
+        u64 sz = (u64)zb_rd32(s + 4) + 8;
+        if (sz > n) return false;
+        s += sz; n -= sz;
+    }
+    return true;
+}
+
+// literal-section header.  returns false on a malformed header.
+struct ZbLitHdr { u32 type, hdr, regen, csize, single; };
+__device__ static u32 zb_parse_lit_header(const u8* s, u32 n, ZbLitHdr& L)
+{
+    if (n < 2) return ZB_E_CORRUPTION;                     // MIN_CBLOCK_SIZE
+    L.type = s[0] & 3; u32 sf = (s[0] >> 2) & 3; L.single = 0; L.csize = 0;
+    if (L.type < 2) {
+        if (sf == 1) { L.hdr = 2; L.regen = zb_rd16(s) >> 4; }
+        else if (sf == 3) { if (n < 3) return ZB_E_CORRUPTION; L.hdr = 3; L.regen = zb_rd24(s) >> 4; }
+        else { L.hdr = 1; L.regen = s[0] >> 3; }
+        return ZB_OK;
+    }
+    if (n < 5) return ZB_E_CORRUPTION;
+    u32 lhc = zb_rd32(s);
+    if (sf < 2) { L.single = (sf == 0); L.hdr = 3; L.regen = (lhc >> 4) & 0x3FF; L.csize = (lhc >> 14) & 0x3FF; }
+    else if (sf == 2) { L.hdr = 4; L.regen = (lhc >> 4) & 0x3FFF; L.csize = lhc >> 18; }
+    else { L.hdr = 5; L.regen = (lhc >> 4) & 0x3FFFF; L.csize = (lhc >> 22) + ((u32)s[4] << 10); }
+    return ZB_OK;
+}
+
+// ===========================================================================
+// K1: frame scan -- one lane per frame
+// ===========================================================================
+__global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
+                               ZbFrameInfo* __restrict__ info)
+{
+    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+    ZbFrameInfo fi; fi.content_size = ZB_CONTENT_UNKNOWN; fi.n_blocks = 0; fi.n_seq_rec = 0; fi.n_lit = 0;
+    fi.status = ZB_OK; fi.dict_id = 0; fi.flags = 0;
+    if (!zb_skip_skippable(s, n)) { fi.status = ZB_E_SRCSIZE_WRONG; info[f] = fi; return; }
+    ZbHdr h; zb_parse_header(s, n, h);
+    if (h.status == ZB_OK && n < 9) h.status = ZB_E_SRCSIZE_WRONG;       // zstd/zstd.c:44188
+    if (h.status != ZB_OK) { fi.status = h.status; info[f] = fi; return; }
+    fi.content_size = h.content_size; fi.dict_id = h.dict_id; fi.flags = h.checksum;
+    u64 pos = h.hdr_size;
+    for (;;) {
+        if (pos + 3 > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
+        u32 bh = zb_rd24(s + pos); pos += 3;
+        u32 type = (bh >> 1) & 3, bsize = bh >> 3;
+        fi.n_blocks++;
+        if (type == 3) { fi.status = ZB_E_CORRUPTION; break; }
+        if (type == 1) bsize = 1;
+        if (pos + bsize > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
+        if (type == 2) {
+            ZbLitHdr L; u32 e = zb_parse_lit_header(s + pos, bsize, L);
+            if (e) { fi.status = e; break; }
+            u32 lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
+            if (L.regen > ZB_BLOCK_MAX || lsec > bsize) { fi.status = ZB_E_CORRUPTION; break; }
+            if (L.type >= 2) fi.n_lit += (L.regen + 15) & ~15u;          // 16-byte aligned scratch slices
+            if (lsec >= bsize) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
+            const u8* q = s + pos + lsec; u32 left = bsize - lsec;
+            u32 nseq = q[0];
+            if (nseq > 0x7F) {
+                if (nseq == 0xFF) { if (left < 3) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(q + 1) + 0x7F00; }
+                else { if (left < 2) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + q[1]; }
+            }
+            fi.n_seq_rec += nseq + 1;
+        }
+        pos += bsize;
+        if (bh & 1) break;
+    }
+    info[f] = fi;
+}
+
+// ===========================================================================
+// K2: placement -- exclusive scans of the per-frame sizes by ONE CTA
+// totals[0..3] = dst bytes, blocks, seq records, literal scratch bytes; totals[4] = first failing frame + 1
+// ===========================================================================
+__global__ void zb_place_frames(const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_sizes,
+                                u32 n_frames, ZbFramePlace* __restrict__ place, u64* __restrict__ totals,
+                                u32* __restrict__ status)
+{
+    __shared__ u64 s_part[4][32];
+    __shared__ u64 s_run[4];
+    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (tid < 4) s_run[tid] = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n_frames; base += blockDim.x) {
+        u32 f = base + tid; u64 v[4] = {0, 0, 0, 0}; u64 cap = 0;
+        if (f < n_frames) {
+            ZbFrameInfo fi = info[f];
+            u32 st = fi.status;
+            if (dst_sizes) cap = dst_sizes[f];
+            else if (fi.content_size != ZB_CONTENT_UNKNOWN) cap = fi.content_size;
+            else st = ZB_E_UNKNOWN_SIZE;                 // ZSTD_getFrameContentSize UNKNOWN/ERROR, c-ext/decompressor.c:981-1014
+            status[f] = st;
+            v[0] = cap;                                  // outputs are packed tightly, like the reference's
+            if (st == ZB_OK) { v[1] = fi.n_blocks; v[2] = fi.n_seq_rec; v[3] = fi.n_lit; }
+        }
+        u64 incl[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u64 x = v[k];
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
+            incl[k] = x;
+            if (lane == 31) s_part[k][warp] = x;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u64 x = lane < nwarp ? s_part[k][lane] : 0;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
+                s_part[k][lane] = x;                      // inclusive over warps
+            }
+        }
+        __syncthreads();
+        if (f < n_frames) {
+            u64 off[4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) off[k] = s_run[k] + (warp ? s_part[k][warp - 1] : 0) + incl[k] - v[k];
+            ZbFramePlace p; p.dst_off = off[0]; p.dst_cap = cap; p.blk_off = off[1]; p.seq_off = off[2]; p.lit_off = off[3];
+            place[f] = p;
+        }
+        __syncthreads();
+        if (tid < 4) s_run[tid] += s_part[tid][nwarp - 1];
+        __syncthreads();
+    }
+    if (tid < 4) totals[tid] = s_run[tid];
+    if (tid == 0) {                                       // sentinel: place[n_frames] bounds the last frame's slices
+        ZbFramePlace p; p.dst_off = s_run[0]; p.dst_cap = 0; p.blk_off = s_run[1]; p.seq_off = s_run[2]; p.lit_off = s_run[3];
+        place[n_frames] = p;
+    }
+}
+
+// ===========================================================================
+// K3: entropy decode -- one lane per frame
+// ===========================================================================
+
+// forward (LSB-first) bit peek of <= 16 bits at bit position `bp` of s[0..n), zero padded
+__device__ __forceinline__ u32 zb_fwd_peek(const u8* s, u32 n, u32 bp, u32 nb)
+{
+    u32 by = bp >> 3, a = 0;
+    if (by < n) a = s[by];
+    if (by + 1 < n) a |= (u32)s[by + 1] << 8;
+    if (by + 2 < n) a |= (u32)s[by + 2] << 16;
+    return (a >> (bp & 7)) & ((1u << nb) - 1);
+}
+
+// normalized-count header (restates FSE_readNCount_body, zstd/zstd.c:3256-3413).
+// returns bytes consumed, 0 on error
+__device__ static u32 zb_read_ncount(short* norm, u32& max_sym, u32& table_log, const u8* s, u32 n)
+{
+    u32 const max_sv1 = max_sym + 1;
+    if (n == 0) return 0;
+    for (u32 i = 0; i < max_sv1; i++) norm[i] = 0;
+    u32 bp = 0, sym = 0; int prev0 = 0;
+    int nbits = (int)zb_fwd_peek(s, n, 0, 4) + 5; bp = 4;
+    if (nbits > 15) return 0;
+    table_log = (u32)nbits;
+    int remaining = (1 << nbits) + 1, threshold = 1 << nbits; nbits++;
+    for (;;) {
+        if (prev0) {
+            for (;;) {
+                u32 r = zb_fwd_peek(s, n, bp, 2); bp += 2; sym += r;
+                if (r != 3) break;
+                if (bp > 8 * n + 64) return 0;
+            }
+            if (sym >= max_sv1) break;
+        }
+        int const mx = (2 * threshold - 1) - remaining;
+        int count; int low = (int)zb_fwd_peek(s, n, bp, (u32)(nbits - 1));
+        if (low < mx) { count = low; bp += (u32)(nbits - 1); }
+        else { count = (int)zb_fwd_peek(s, n, bp, (u32)nbits); if (count >= threshold) count -= mx; bp += (u32)nbits; }
+        count--;
+        remaining -= count < 0 ? -count : count;
+        norm[sym++] = (short)count;
+        prev0 = !count;
+        if (remaining < threshold) {
+            if (remaining <= 1) break;
+            nbits = zb_hibit((u32)remaining) + 1; threshold = 1 << (nbits - 1);
+        }
+        if (sym >= max_sv1) break;
+    }
+    if (remaining != 1 || sym > max_sv1 || bp > 8 * n) return 0;
+    max_sym = sym - 1;
+    return (bp + 7) >> 3;
+}
+
+__device__ __forceinline__ void zb_cell_payload(ZbFseCell& c, u32 sym, int kind)
+{
+    if (kind == K_LL) { c.base = c_LL_base[sym]; c.add_bits = c_LL_bits[sym]; }
+    else if (kind == K_ML) { c.base = c_ML_base[sym]; c.add_bits = c_ML_bits[sym]; }
+    else { c.base = sym < 2 ? sym : (1u << sym) - 3; c.add_bits = (u8)sym; }
+}
+
+// tANS decode table (restates ZSTD_buildFSETable_body, zstd/zstd.c:46118-46233), serial per lane.
+// kind < 0: plain symbol table (Huffman weights): base = symbol.
+template <int MAXS>
+__device__ static void zb_build_fse(ZbFseCell* t, const short* norm, u32 max_sym, u32 log, int kind)
+{
+    u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    u16 next[MAXS];
+    u32 high = size - 1;
+    for (u32 s = 0; s <= max_sym; s++) {
+        if (norm[s] == -1) { t[high--].base = s; next[s] = 1; }
+        else next[s] = (u16)norm[s];
+    }
+    u32 pos = 0;
+    for (u32 s = 0; s <= max_sym; s++) {
+        int const c = norm[s];
+        for (int i = 0; i < c; i++) {
+            t[pos].base = s;
+            do pos = (pos + step) & mask; while (pos > high);
+        }
+    }
+    for (u32 u = 0; u < size; u++) {
+        u32 const s = t[u].base, x = next[s]++;
+        ZbFseCell c; c.nb = (u8)(log - (u32)zb_hibit(x)); c.next = (u16)((x << c.nb) - size);
+        if (kind >= 0) zb_cell_payload(c, s, kind); else { c.base = s; c.add_bits = 0; }
+        t[u] = c;
+    }
+}
+
+__global__ void zb_build_default_tables()
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        short norm[64];
+        for (int i = 0; i < 36; i++) norm[i] = c_LL_defnorm[i];
+        zb_build_fse<64>(g_defLL, norm, 35, 6, K_LL);
+        for (int i = 0; i < 29; i++) norm[i] = c_OF_defnorm[i];
+        zb_build_fse<64>(g_defOF, norm, 28, 5, K_OF);
+        for (int i = 0; i < 53; i++) norm[i] = c_ML_defnorm[i];
+        zb_build_fse<64>(g_defML, norm, 52, 6, K_ML);
+    }
+}
+
+// Huffman table description -> decode cells (restates HUF_readStats_body zstd/zstd.c:3457-3521 and
+// the cell layout of HUF_readDTableX1_wksp :39651-39783).  `fse_tmp` is scratch for the weight table
+// (<= 64 cells).  returns header bytes consumed, 0 on error.
+__device__ static u32 zb_read_huf_table(u16* cells, u32& out_log, const u8* s, u32 n, ZbFseCell* fse_tmp)
+{
+    u8 w[256]; u32 rank[16]; u32 nsym, hdr;
+    if (n == 0) return 0;
+    for (int i = 0; i < 16; i++) rank[i] = 0;
+    if (s[0] >= 128) {
+        nsym = (u32)s[0] - 127; hdr = (nsym + 1) / 2;
+        if (hdr + 1 > n) return 0;
+        for (u32 i = 0; i < nsym; i++) { u32 b = s[1 + i / 2]; w[i] = (i & 1) ? (b & 15) : (b >> 4); }
+    } else {
+        // FSE-compressed weights: two interleaved states (FSE_decompress_usingDTable_generic, zstd/zstd.c:3785-3858)
+        hdr = s[0];
+        if (hdr + 1 > n) return 0;
+        u32 max_sym = 255, log;
+        {
+            short nn[256];
+            u32 used = zb_read_ncount(nn, max_sym, log, s + 1, hdr);
+            if (used == 0 || log > 6) return 0;
+            zb_build_fse<256>(fse_tmp, nn, max_sym, log, -1);
+            ZbBitR b;
+            if (!b.init(s + 1 + used, hdr - used)) return 0;
+            u32 s1 = b.read(log), s2 = b.read(log); b.refill();
+            if (b.left < 0) return 0;
+            nsym = 0;
+            for (;;) {
+                if (nsym + 2 > 255) return 0;
+                { ZbFseCell c = fse_tmp[s1]; w[nsym++] = (u8)c.base; s1 = c.next + b.read(c.nb); b.refill(); }
+                if (b.left < 0) { w[nsym++] = (u8)fse_tmp[s2].base; break; }
+                if (nsym + 2 > 255) return 0;
+                { ZbFseCell c = fse_tmp[s2]; w[nsym++] = (u8)c.base; s2 = c.next + b.read(c.nb); b.refill(); }
+                if (b.left < 0) { w[nsym++] = (u8)fse_tmp[s1].base; break; }
+            }
+        }
+    }
+    u32 total = 0;
+    for (u32 i = 0; i < nsym; i++) {
+        if (w[i] > 12) return 0;
+        rank[w[i]]++; total += (1u << w[i]) >> 1;
+    }
+    if (total == 0) return 0;
+    u32 log = (u32)zb_hibit(total) + 1;
+    if (log > 12) return 0;
+    {
+        u32 rest = (1u << log) - total, hb = (u32)zb_hibit(rest);
+        if ((1u << hb) != rest) return 0;
+        w[nsym] = (u8)(hb + 1); rank[hb + 1]++; nsym++;
+    }
+    if (rank[1] < 2 || (rank[1] & 1)) return 0;
+    // start cell of every weight class
+    u32 start[14]; { u32 p = 0; for (u32 wt = 1; wt <= log; wt++) { start[wt] = p; p += rank[wt] << (wt - 1); } }
+    for (u32 i = 0; i < nsym; i++) {
+        u32 wt = w[i]; if (!wt) continue;
+        u32 len = 1u << (wt - 1), p = start[wt]; start[wt] = p + len;
+        u16 cell = (u16)(i | ((log + 1 - wt) << 8));
+        if (len >= 4) {                                   // cells are 2 bytes: fill 8 bytes at a time
+            u64 v = cell * 0x0001000100010001ull;
+            u64* q = (u64*)(cells + p);                   // p is a multiple of len >= 4 -> 8-byte aligned
+            for (u32 k = 0; k < len / 4; k++) q[k] = v;
+        } else for (u32 k = 0; k < len; k++) cells[p + k] = cell;
+    }
+    out_log = log;
+    return hdr + 1;
+}
+
+// one Huffman stream -> n_out literal bytes (restates HUF_decompress1X1_usingDTable_internal_body, zstd/zstd.c:39845)
+__device__ static bool zb_huf_stream(u8* out, u32 n_out, const u8* s, u32 n, const u16* cells, u32 log)
+{
+    ZbBitR b;
+    if (!b.init(s, n)) return false;
+    for (u32 i = 0; i < n_out; i++) {
+        u32 c = cells[b.peek(log)];
+        out[i] = (u8)c; b.skip(c >> 8); b.refill();
+    }
+    return b.left == 0;
+}
+
+struct ZbTab { const ZbFseCell* t; u32 log; };
+
+// sequence table per mode (restates ZSTD_buildSeqTable, zstd/zstd.c:46280-46326). returns bytes used or -1
+__device__ static int zb_seq_table(ZbTab& cur, ZbFseCell* own, u32 mode, u32 max_sym, u32 max_log, int kind,
+                                   const u8* s, u32 n, bool repeat_ok)
+{
+    if (mode == 0) {
+        cur.t = kind == K_LL ? g_defLL : (kind == K_OF ? g_defOF : g_defML);
+        cur.log = kind == K_OF ? 5 : 6;
+        return 0;
+    }
+    if (mode == 1) {
+        if (n == 0 || s[0] > max_sym) return -1;
+        ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, s[0], kind);
+        own[0] = c; cur.t = own; cur.log = 0;
+        return 1;
+    }
+    if (mode == 3) return repeat_ok ? 0 : -1;
+    short norm[64]; u32 log;
+    u32 used = zb_read_ncount(norm, max_sym, log, s, n);
+    if (used == 0 || log > max_log) return -1;
+    zb_build_fse<64>(own, norm, max_sym, log, kind);
+    cur.t = own; cur.log = log;
+    return (int)used;
+}
+
+__global__ void __launch_bounds__(128)
+zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
+                  const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
+                  ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
+                  u8* __restrict__ lane_scratch, u32* __restrict__ work_counter,
+                  ZbDictDev dict, u32* status, u64* __restrict__ out_sizes)
+{
+    u32 const lane = threadIdx.x & 31;
+    u32 const gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u8* const my = lane_scratch + ((u64)gwarp * 32 + lane) * ZB_LANE_BYTES;
+    u16* const huf_own = (u16*)(my + ZB_LANE_HUF);
+    ZbFseCell* const ll_own = (ZbFseCell*)(my + ZB_LANE_LL);
+    ZbFseCell* const ml_own = (ZbFseCell*)(my + ZB_LANE_ML);
+    ZbFseCell* const of_own = (ZbFseCell*)(my + ZB_LANE_OF);
+    ZbFseCell* const wt_own = (ZbFseCell*)(my + ZB_LANE_WT);
+
+    for (;;) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_frames) return;
+        u32 const f = base + lane;
+        if (f >= n_frames) continue;
+        if (status[f] != ZB_OK) { out_sizes[f] = 0; continue; }
+
+        const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+        zb_skip_skippable(s, n);
+        ZbHdr h; zb_parse_header(s, n, h);
+        ZbFramePlace const pl = place[f];
+        u32 err = ZB_OK;
+        u64 const cap = pl.dst_cap;
+        u64 out_pos = 0;                      // frame-relative output position
+        u64 blk_i = pl.blk_off, seq_i = pl.seq_off, lit_i = pl.lit_off;
+        u32 const block_max = h.window < ZB_BLOCK_MAX ? (u32)h.window : ZB_BLOCK_MAX;
+        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        const u16* huf = huf_own; u32 huf_log = 0; bool huf_valid = false, fse_valid = false;
+        ZbTab tLL = {g_defLL, 6}, tOF = {g_defOF, 5}, tML = {g_defML, 6};
+        u64 const hist_extra = dict.content_size;       // bytes of history before the frame
+        if (dict.has_entropy) {
+            huf = dict.huf; huf_log = dict.huf_log; huf_valid = true; fse_valid = true;
+            tLL.t = dict.ll; tLL.log = dict.ll_log; tOF.t = dict.of; tOF.log = dict.of_log; tML.t = dict.ml; tML.log = dict.ml_log;
+            rep0 = dict.rep[0]; rep1 = dict.rep[1]; rep2 = dict.rep[2];
+        }
+        if (h.dict_id && dict.dict_id && h.dict_id != dict.dict_id) err = ZB_E_DICT_WRONG;
+
+        u64 pos = h.hdr_size;
+        while (!err) {
+            if (pos + 3 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+            u32 bh = zb_rd24(s + pos); pos += 3;
+            u32 const last = bh & 1, type = (bh >> 1) & 3; u32 bsize = bh >> 3;
+            ZbBlock B; B.out_pos = out_pos; B.kind = type; B.seq_pos = seq_i; B.n_seq = 0; B.n_lit = 0; B.lit_kind = 0; B.lit_byte = 0;
+            if (type == ZB_BLK_RLE) {
+                if (pos + 1 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                B.src_pos = (u64)(s + pos - src); B.regen = bsize; B.lit_byte = s[pos];
+                pos += 1;
+            } else if (type == ZB_BLK_RAW) {
+                if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                B.src_pos = (u64)(s + pos - src); B.regen = bsize;
+                pos += bsize;
+            } else {
+                if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                if (bsize > block_max) { err = ZB_E_SRCSIZE_WRONG; break; }
+                const u8* const bs = s + pos; const u8* const bend = bs + bsize;
+                // ---- literals section (restates ZSTD_decodeLiteralsBlock, zstd/zstd.c:45767-45973)
+                ZbLitHdr L; err = zb_parse_lit_header(bs, bsize, L);
+                if (err) break;
+                if (L.regen > block_max) { err = ZB_E_CORRUPTION; break; }
+                const u8* ip;
+                B.n_lit = L.regen;
+                if (L.type == 0) {
+                    if (L.hdr + L.regen > bsize) { err = ZB_E_CORRUPTION; break; }
+                    B.lit_kind = ZB_LIT_RAW; B.src_pos = (u64)(bs + L.hdr - src); ip = bs + L.hdr + L.regen;
+                } else if (L.type == 1) {
+                    if (L.hdr + 1 > bsize) { err = ZB_E_CORRUPTION; break; }
+                    B.lit_kind = ZB_LIT_RLE; B.lit_byte = bs[L.hdr]; B.src_pos = 0; ip = bs + L.hdr + 1;
+                } else {
+                    if (L.type == 3 && !huf_valid) { err = ZB_E_DICT_CORRUPTED; break; }
+                    if (!L.single && L.regen < 6) { err = ZB_E_LITERALS_HEADER_WRONG; break; }
+                    if (L.csize + L.hdr > bsize) { err = ZB_E_CORRUPTION; break; }
+                    if (L.regen == 0) { err = ZB_E_CORRUPTION; break; }
+                    const u8* p = bs + L.hdr; u32 left = L.csize;
+                    if (L.type == 2) {
+                        u32 used = zb_read_huf_table(huf_own, huf_log, p, left, wt_own);
+                        if (used == 0 || used >= left) { err = ZB_E_CORRUPTION; break; }
+                        huf = huf_own; p += used; left -= used;
+                    }
+                    u8* const dstl = lits + lit_i;
+                    bool ok;
+                    if (L.single) ok = zb_huf_stream(dstl, L.regen, p, left, huf, huf_log);
+                    else {
+                        ok = left >= 10;
+                        if (ok) {
+                            u32 l1 = zb_rd16(p), l2 = zb_rd16(p + 2), l3 = zb_rd16(p + 4);
+                            u32 seg = (L.regen + 3) / 4;
+                            ok = (6 + l1 + l2 + l3 <= left) && (seg * 3 <= L.regen);
+                            if (ok) {
+                                u32 l4 = left - 6 - l1 - l2 - l3;
+                                ok = zb_huf_stream(dstl, seg, p + 6, l1, huf, huf_log)
+                                  && zb_huf_stream(dstl + seg, seg, p + 6 + l1, l2, huf, huf_log)
+                                  && zb_huf_stream(dstl + 2 * seg, seg, p + 6 + l1 + l2, l3, huf, huf_log)
+                                  && zb_huf_stream(dstl + 3 * seg, L.regen - 3 * seg, p + 6 + l1 + l2 + l3, l4, huf, huf_log);
+                            }
+                        }
+                    }
+                    if (!ok) { err = ZB_E_CORRUPTION; break; }
+                    huf_valid = true;
+                    B.lit_kind = ZB_LIT_SCRATCH; B.src_pos = lit_i; lit_i += (L.regen + 15) & ~15u;
+                    ip = bs + L.hdr + L.csize;
+                }
+                // ---- sequences section header (restates ZSTD_decodeSeqHeaders, zstd/zstd.c:46328-46410)
+                if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                u32 nseq = *ip++;
+                if (nseq > 0x7F) {
+                    if (nseq == 0xFF) { if (ip + 2 > bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
+                    else { if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
+                }
+                B.n_seq = nseq;
+                u32 lit_used = 0, produced = 0;         // block-relative
+                if (nseq == 0) {
+                    if (ip != bend) { err = ZB_E_CORRUPTION; break; }
+                } else {
+                    if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const modes = *ip++;
+                    if (modes & 3) { err = ZB_E_CORRUPTION; break; }
+                    int r;
+                    r = zb_seq_table(tLL, ll_own, modes >> 6, 35, 9, K_LL, ip, (u32)(bend - ip), fse_valid);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
+                    r = zb_seq_table(tOF, of_own, (modes >> 4) & 3, 31, 8, K_OF, ip, (u32)(bend - ip), fse_valid);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
+                    r = zb_seq_table(tML, ml_own, (modes >> 2) & 3, 52, 9, K_ML, ip, (u32)(bend - ip), fse_valid);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
+                    fse_valid = true;
+                    // ---- the 3-state FSE sequence stream (restates ZSTD_decodeSequence, zstd/zstd.c:46862-46986)
+                    ZbBitR b;
+                    if (!b.init(ip, (u32)(bend - ip))) { err = ZB_E_CORRUPTION; break; }
+                    u32 sLL = b.read(tLL.log); u32 sOF = b.read(tOF.log); b.refill(); u32 sML = b.read(tML.log); b.refill();
+                    const ZbFseCell* const TL = tLL.t; const ZbFseCell* const TO = tOF.t; const ZbFseCell* const TM = tML.t;
+                    u64 const room = cap - out_pos;
+                    for (u32 i = 0; i < nseq; i++) {
+                        ZbFseCell const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
+                        u32 ll = cl.base, ml = cm.base, off;
+                        if (co.add_bits > 1) {
+                            off = co.base + b.read(co.add_bits);
+                            rep2 = rep1; rep1 = rep0; rep0 = off;
+                        } else {
+                            u32 const ll0 = (cl.base == 0);
+                            if (co.add_bits == 0) {
+                                if (ll0) { off = rep1; rep1 = rep0; rep0 = off; } else off = rep0;
+                            } else {
+                                u32 idx = co.base + ll0 + b.read(1);
+                                u32 tmp = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
+                                if (tmp == 0) tmp = 0xFFFFFFFFu;
+                                if (idx != 1) rep2 = rep1;
+                                rep1 = rep0; rep0 = off = tmp;
+                            }
+                        }
+                        b.refill();
+                        ml += b.read(cm.add_bits);
+                        ll += b.read(cl.add_bits);
+                        b.refill();
+                        if (i + 1 < nseq) {
+                            sLL = cl.next + b.read(cl.nb);
+                            sML = cm.next + b.read(cm.nb);
+                            sOF = co.next + b.read(co.nb);
+                            b.refill();
+                        }
+                        seqs[seq_i + i] = make_uint4(lit_used, produced, ml, off);
+                        // validation (restates the checks of ZSTD_execSequence/ZSTD_execSequenceEnd, zstd/zstd.c:46540-46728)
+                        if ((u64)produced + ll + ml > room) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                        if (ll > L.regen - lit_used) { err = ZB_E_CORRUPTION; break; }
+                        lit_used += ll; produced += ll;
+                        if ((u64)off > out_pos + produced + hist_extra) { err = ZB_E_CORRUPTION; break; }
+                        produced += ml;
+                    }
+                    if (err) break;
+                    if (b.left != 0) { err = ZB_E_CORRUPTION; break; }
+                }
+                seqs[seq_i + nseq] = make_uint4(lit_used, produced, 0, 0);
+                seq_i += nseq + 1;
+                u32 const tail = L.regen - lit_used;
+                if ((u64)produced + tail > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                B.regen = produced + tail;
+                if (B.regen > block_max) { err = ZB_E_CORRUPTION; break; }
+                pos += bsize;
+            }
+            blocks[blk_i++] = B;
+            out_pos += B.regen;
+            if (last) break;
+        }
+        if (!err) {
+            if (h.content_size != ZB_CONTENT_UNKNOWN && out_pos != h.content_size) err = ZB_E_CORRUPTION;
+            else if (h.checksum && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
+        }
+        if (!err && dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;   // c-ext/decompressor.c:1151-1162
+        if (err) { status[f] = err; out_sizes[f] = 0; }       // the execute stage skips failed frames
+        else out_sizes[f] = out_pos;
+    }
+}
+
+// ===========================================================================
+// K4: LZ copy-execute -- one warp per frame
+// ===========================================================================
+
+// warp-cooperative byte copy (no overlap between src and dst)
+__device__ __forceinline__ void zb_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
+{
+    if (n >= 64 && ((((uintptr_t)dst) ^ ((uintptr_t)src)) & 15) == 0) {
+        u32 head = (u32)((16 - ((uintptr_t)dst & 15)) & 15);
+        if (lane < head) dst[lane] = src[lane];
+        dst += head; src += head; n -= head;
+        u32 nv = n >> 4;
+        const uint4* s4 = (const uint4*)src; uint4* d4 = (uint4*)dst;
+        for (u32 i = lane; i < nv; i += 32) d4[i] = s4[i];
+        u32 done = nv << 4;
+        if (done + lane < n) dst[done + lane] = src[done + lane];
+        return;
+    }
+    for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256)
+zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
+           const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
+           u8* dst, u32 n_frames, ZbDictDev dict)
+{
+    u32 const lane = threadIdx.x & 31;
+    u32 const f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= n_frames) return;
+    if (status[f] != ZB_OK) return;
+    ZbFramePlace const pl = place[f];
+    u8* const out = dst + pl.dst_off;
+    u64 const blk_end = place[f + 1].blk_off;            // place[] has n_frames + 1 entries
+    const u8* const dict_end = dict.content + dict.content_size;
+
+    for (u64 bi = pl.blk_off; bi < blk_end; bi++) {
+        ZbBlock const B = blocks[bi];
+        u8* const bout = out + B.out_pos;
+        if (B.kind == ZB_BLK_RAW) { zb_warp_copy(bout, src + B.src_pos, B.regen, lane); continue; }
+        if (B.kind == ZB_BLK_RLE) { for (u32 i = lane; i < B.regen; i += 32) bout[i] = (u8)B.lit_byte; continue; }
+        if (B.kind != ZB_BLK_COMPRESSED) return;
+        const u8* const lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
+        bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
+        const ZbSeq* const sq = seqs + B.seq_pos;
+        u32 const nseq = B.n_seq;
+        for (u32 g = 0; g < nseq; g += 32) {
+            u32 const i = g + lane; bool const valid = i < nseq;
+            ZbSeq r = valid ? sq[i] : make_uint4(0, 0, 0, 0);
+            ZbSeq r2 = valid ? sq[i + 1] : make_uint4(0, 0, 0, 0);
+            u32 const ll = r2.x - r.x, ml = r.z, off = r.w;
+            u32 const ostart = r.y, mstart = r.y + ll;
+            // literals: independent of everything else
+            if (valid) {
+                if (lit_rle) for (u32 k = 0; k < ll; k++) bout[ostart + k] = lit_byte;
+                else { const u8* lp = lit + r.x; for (u32 k = 0; k < ll; k++) bout[ostart + k] = lp[k]; }
+            }
+            __syncwarp();
+            // matches: a lane may run when every byte it reads that other sequences produce lies
+            // below the frontier F (= match start of the first unfinished sequence)
+            bool pending = valid;
+            long long const abs_m = (long long)B.out_pos + mstart;       // frame-relative match start
+            long long const srcp = abs_m - (long long)off;               // may be negative: dictionary
+            long long const need = min(srcp + (long long)ml, (long long)B.out_pos + ostart);
+            for (;;) {
+                u32 const pm = __ballot_sync(0xFFFFFFFFu, pending);
+                if (!pm) break;
+                int const fu = __ffs(pm) - 1;
+                long long const F = __shfl_sync(0xFFFFFFFFu, abs_m, fu);
+                bool const ready = pending && need <= F;
+                // long matches of ready lanes: the whole warp copies them, one at a time
+                u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 48);
+                while (big) {
+                    int const l = __ffs(big) - 1; big &= big - 1;
+                    long long const m0 = __shfl_sync(0xFFFFFFFFu, abs_m, l);
+                    u32 const o = __shfl_sync(0xFFFFFFFFu, off, l), len = __shfl_sync(0xFFFFFFFFu, ml, l);
+                    u8* d = out + m0;
+                    if ((long long)o > m0) {
+                        // starts in the dictionary: byte-wise with the source select
+                        for (u32 j = lane; j < len; j += 32) {
+                            long long sp = m0 - (long long)o + (long long)(j % o);
+                            d[j] = sp < 0 ? dict_end[sp] : out[sp];
+                        }
+                    } else if (o >= 32) {
+                        // chunks of 32 bytes never read bytes of their own chunk
+                        const u8* sp = d - o;
+                        for (u32 j = 0; j < len; j += 32) { if (j + lane < len) d[j + lane] = sp[j + lane]; __syncwarp(); }
+                    } else {
+                        const u8* sp = d - o;                            // periodic pattern of period o
+                        for (u32 j = lane; j < len; j += 32) d[j] = sp[j % o];
+                    }
+                    __syncwarp();
+                }
+                if (ready) {
+                    if (ml < 48) {
+                        u8* d = out + abs_m;
+                        if (srcp >= 0) {
+                            const u8* sp = out + srcp;
+                            if (off >= ml) for (u32 k = 0; k < ml; k++) d[k] = sp[k];
+                            else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
+                        } else {
+                            for (u32 k = 0; k < ml; k++) { long long p = srcp + (long long)(k % off); d[k] = p < 0 ? dict_end[p] : out[p]; }
+                        }
+                    }
+                    pending = false;
+                }
+                __syncwarp();
+            }
+        }
+        // last literals of the block
+        {
+            ZbSeq const e = sq[nseq];
+            u32 const tail = B.n_lit - e.x;
+            if (lit_rle) { for (u32 k = lane; k < tail; k += 32) bout[e.y + k] = lit_byte; }
+            else zb_warp_copy(bout + e.y, lit + e.x, tail, lane);
+        }
+        __syncwarp();
+    }
+}
+
+
+// ===========================================================================
+// K5: finish -- output segment table + lowest failing frame
+// ===========================================================================
+__global__ void zb_finish(const ZbFramePlace* __restrict__ place, const u64* __restrict__ out_sizes,
+                          const u32* __restrict__ status, u32 n_frames, ZbSegment* __restrict__ out_segs,
+                          u32* __restrict__ first_error)
+{
+    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    ZbSegment s; s.offset = place[f].dst_off; s.length = out_sizes[f];
+    out_segs[f] = s;
+    if (status[f] != ZB_OK) atomicMin(first_error, f);
+}
+
+// ===========================================================================
+// dictionary digest -- one thread, once per dictionary
+// (restates ZSTD_loadDEntropy zstd/zstd.c:44673-44757 and ZSTD_decompress_insertDictionary :44760)
+// ===========================================================================
+__global__ void zb_digest_dict(const u8* __restrict__ dict, u32 n, ZbDictDigest* __restrict__ out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    out->status = ZB_OK; out->has_entropy = 0; out->dict_id = 0; out->content_off = 0;
+    if (n < 8 || zb_rd32(dict) != ZB_MAGIC_DICT) return;            // raw-content dictionary
+    out->dict_id = zb_rd32(dict + 4);
+    const u8* p = dict + 8; const u8* const end = dict + n;
+    u32 used = zb_read_huf_table(out->huf, out->huf_log, p, (u32)(end - p), out->wt);
+    if (!used) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    p += used;
+    short norm[64]; u32 mx, log;
+    mx = 31; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
+    if (!used || log > 8) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    zb_build_fse<64>(out->of, norm, mx, log, K_OF); out->of_log = log; p += used;
+    mx = 52; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
+    if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    zb_build_fse<64>(out->ml, norm, mx, log, K_ML); out->ml_log = log; p += used;
+    mx = 35; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
+    if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    zb_build_fse<64>(out->ll, norm, mx, log, K_LL); out->ll_log = log; p += used;
+    if (p + 12 > end) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    u32 const content = (u32)(end - (p + 12));
+    for (int i = 0; i < 3; i++) {
+        u32 r = zb_rd32(p + 4 * i);
+        if (r == 0 || r > content) { out->status = ZB_E_DICT_CORRUPTED; return; }
+        out->rep[i] = r;
+    }
+    out->content_off = (u32)(p + 12 - dict);
+    out->has_entropy = 1;
+}
+
+// ===========================================================================
+// host-side launchers (called from zb_api.cu)
+// ===========================================================================
+extern "C" {
+
+void zb_launch_default_tables(cudaStream_t st) { zb_build_default_tables<<<1, 32, 0, st>>>(); }
+
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, cudaStream_t st)
+{
+    zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info);
+}
+
+void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
+                     u32* status, cudaStream_t st)
+{
+    zb_place_frames<<<1, 1024, 0, st>>>(info, dst_sizes, n, place, totals, status);
+}
+
+void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
+                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u8* lane_scratch, u32 n_warps, u32* work_counter,
+                       ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st)
+{
+    // n_warps resident warps of 32 lanes; 4 warps per CTA
+    zb_entropy_decode<<<(n_warps + 3) / 4, 128, 0, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
+                                                         lane_scratch, work_counter, dict, status, out_sizes);
+}
+
+void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
+                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st)
+{
+    u32 const warps_per_cta = 8;
+    zb_execute<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(src, place, status, blocks, seqs,
+                                                                                       lits, dst, n, dict);
+}
+
+void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,
+                      u32* first_error, cudaStream_t st)
+{
+    zb_finish<<<(n + 255) / 256, 256, 0, st>>>(place, out_sizes, status, n, out_segs, first_error);
+}
+
+void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st)
+{
+    zb_digest_dict<<<1, 32, 0, st>>>(dict, n, out);
+}
+
+}  // extern "C"

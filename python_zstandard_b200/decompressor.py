@@ -1,0 +1,263 @@
+"""ZstdDecompressor -- the decompression half of the reference API that sits on the batch path.
+
+Mirrors c-ext/decompressor.c: constructor :17-126, decompress() :263-395 and
+multi_decompress_to_buffer() :1460-1711 (same arguments, same error types and texts).
+The work itself runs as CUDA kernels through libzb200 (include/zb200.h); there is no CPU path.
+Streaming objects (stream_reader, copy_stream, ...) are out of scope for this tier.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .buffers import BufferWithSegments, BufferWithSegmentsCollection, SEGMENT_SIZE
+from .dictionary import ZstdCompressionDict
+from .errors import ZstdError
+
+FORMAT_ZSTD1 = 0
+FORMAT_ZSTD1_MAGICLESS = 1
+_UNKNOWN = (1 << 64) - 1
+_SIZES_ARE_CAPACITY = 4
+
+
+def _devices(threads):
+    """`threads` of the reference becomes a hint for how many GPUs to spread a batch over:
+    <= 1 -> the current device only; -1 -> every visible device (cpu_count() in the reference)."""
+    n = _native.device_count()
+    if threads is None or threads == 0 or threads == 1:
+        return 1
+    if threads < 0:
+        return max(1, n)
+    return max(1, min(threads, n))
+
+
+class ZstdDecompressor:
+    def __init__(self, dict_data=None, max_window_size=0, format=FORMAT_ZSTD1):
+        if dict_data is not None and not isinstance(dict_data, ZstdCompressionDict):
+            raise TypeError("dict_data must be a ZstdCompressionDict")
+        if format != FORMAT_ZSTD1:
+            raise ZstdError("only FORMAT_ZSTD1 is supported by the B200 backend")
+        if max_window_size < 0 or (max_window_size and max_window_size > (1 << 31)):
+            raise ZstdError("unable to set max window size: Parameter is out of bound")
+        self._dict_data = dict_data
+        self._max_window_size = max_window_size
+        self._format = format
+        self._ctx = None
+
+    def _context(self, device=0):
+        return _native.Context.get(device)
+
+    def memory_size(self):
+        return 0
+
+    # ------------------------------------------------------------------ one-shot
+    def decompress(self, data, max_output_size=0, read_across_frames=False, allow_extra_data=True):
+        if read_across_frames:
+            raise ZstdError("ZstdDecompressor.read_across_frames=True is not yet implemented")
+        view = memoryview(data)
+        buf = np.frombuffer(view, dtype=np.uint8) if len(view) else np.zeros(0, dtype=np.uint8)
+        L = _native.lib()
+        info = _native.FrameInfo()
+        L.zb200_frame_info(buf.ctypes.data if len(buf) else None, len(buf), C.byref(info))
+        if info.status != 0 or len(buf) < 5:
+            raise ZstdError("error determining content size from frame header")
+        size = info.content_size
+        if size == 0:
+            return b""
+        flags = 0
+        if size == _UNKNOWN:
+            if not max_output_size:
+                raise ZstdError("could not determine content size in frame header")
+            size = max_output_size
+            flags = _SIZES_ARE_CAPACITY
+        ctx = self._context()
+        seg = np.array([[0, len(buf)]], dtype=np.uint64)
+        sizes = np.array([size], dtype=np.uint64)
+        res = C.c_void_p()
+        dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
+        with ctx.lock:
+            rc = L.zb200_decompress_batch(ctx.h, buf.ctypes.data, seg.ctypes.data, 1, sizes.ctypes.data, dd, flags,
+                                          C.byref(res))
+        ctx.check(rc, "zb200_decompress_batch")
+        try:
+            item, code = C.c_size_t(), C.c_int()
+            got, exp = C.c_uint64(), C.c_uint64()
+            if L.zb200_result_first_error(res, C.byref(item), C.byref(code), C.byref(got), C.byref(exp)):
+                if code.value == 201:
+                    raise ZstdError("decompression error: did not decompress full frame")
+                raise ZstdError("decompression error: %s" % L.zb200_error_string(code.value).decode())
+            n = L.zb200_result_size(res)
+            out = C.string_at(L.zb200_result_data(res), n) if n else b""
+        finally:
+            L.zb200_result_free(res)
+        if not allow_extra_data:
+            used = self._frame_size(buf)
+            if used is not None and used < len(buf):
+                raise ZstdError("compressed input contains %d bytes of unused data, which is disallowed"
+                                % (len(buf) - used))
+        return out
+
+    @staticmethod
+    def _frame_size(buf):
+        """Compressed size of the first frame (header + block chain + checksum); host-side walk of
+        the 3-byte block headers only (ZSTD_findFrameCompressedSize, zstd/zstd.c:43905)."""
+        L = _native.lib()
+        info = _native.FrameInfo()
+        L.zb200_frame_info(buf.ctypes.data, len(buf), C.byref(info))
+        if info.status:
+            return None
+        pos = info.header_size
+        n = len(buf)
+        while True:
+            if pos + 3 > n:
+                return None
+            bh = int(buf[pos]) | (int(buf[pos + 1]) << 8) | (int(buf[pos + 2]) << 16)
+            pos += 3
+            btype = (bh >> 1) & 3
+            pos += 1 if btype == 1 else (bh >> 3)
+            if bh & 1:
+                break
+        return pos + (4 if info.has_checksum else 0)
+
+    # ------------------------------------------------------------------ batch
+    def multi_decompress_to_buffer(self, frames, decompressed_sizes=None, threads=0):
+        sizes = None
+        if decompressed_sizes is not None:
+            sizes = np.frombuffer(memoryview(decompressed_sizes), dtype=np.uint8)
+        L = _native.lib()
+
+        if isinstance(frames, BufferWithSegments):
+            sources = [frames]
+        elif isinstance(frames, BufferWithSegmentsCollection):
+            sources = frames._buffers
+        elif isinstance(frames, list):
+            sources = None
+        else:
+            raise TypeError("argument must be list of BufferWithSegments")
+
+        if sources is not None:
+            count = sum(len(b) for b in sources)
+            self._check_sizes(sizes, count)
+            if count == 0:
+                raise ValueError("no source elements found")
+            results = []
+            first = 0
+            for b in sources:
+                n = len(b)
+                sz = sizes[first * 8:(first + n) * 8] if sizes is not None else None
+                results.extend(self._run_contiguous(b, n, sz, first, threads))
+                first += n
+            return BufferWithSegmentsCollection(*results)
+
+        # list of bytes-like objects (c-ext/decompressor.c:1601-1685)
+        count = len(frames)
+        self._check_sizes(sizes, count)
+        views = []
+        for i, item in enumerate(frames):
+            try:
+                v = memoryview(item)
+            except TypeError:
+                raise TypeError("item %d not a bytes like object" % i)
+            if not v.contiguous:
+                raise TypeError("item %d not a bytes like object" % i)
+            views.append(v)
+        if count == 0:
+            raise ValueError("no source elements found")
+        return BufferWithSegmentsCollection(*self._run_list(views, sizes, threads))
+
+    @staticmethod
+    def _check_sizes(sizes, count):
+        if sizes is not None and len(sizes) != count * 8:
+            raise ValueError("decompressed_sizes size mismatch; expected %d, got %d" % (count * 8, len(sizes)))
+
+    def _raise_item_error(self, L, res, base):
+        item, code = C.c_size_t(), C.c_int()
+        got, exp = C.c_uint64(), C.c_uint64()
+        if not L.zb200_result_first_error(res, C.byref(item), C.byref(code), C.byref(got), C.byref(exp)):
+            return
+        L.zb200_result_free(res)
+        idx = base + item.value
+        if code.value == 200:
+            raise ValueError("could not determine decompressed size of item %d" % idx)
+        if code.value == 201:
+            raise ZstdError("error decompressing item %d: decompressed %d bytes; expected %d"
+                            % (idx, got.value, exp.value))
+        raise ZstdError("error decompressing item %d: %s" % (idx, L.zb200_error_string(code.value).decode()))
+
+    def _split(self, lengths, parts):
+        """Contiguous ranges balanced by input bytes -- the reference's static partition of the
+        batch over its workers (c-ext/decompressor.c:1237,1290-1305), here over devices."""
+        n = len(lengths)
+        if parts <= 1 or n < 2:
+            return [(0, n)]
+        cum = np.cumsum(lengths)
+        total = int(cum[-1])
+        cuts = [0]
+        for p in range(1, parts):
+            k = int(np.searchsorted(cum, total * p // parts, side="left")) + 1
+            k = min(max(k, cuts[-1] + 1), n - (parts - p))
+            cuts.append(k)
+        cuts.append(n)
+        return [(cuts[i], cuts[i + 1]) for i in range(parts) if cuts[i] < cuts[i + 1]]
+
+    def _launch(self, ctx, base_ptr, segs, n, sizes_arr, flags=0):
+        L = ctx.L
+        res = C.c_void_p()
+        dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
+        with ctx.lock:
+            rc = L.zb200_decompress_batch(ctx.h, base_ptr, segs.ctypes.data, n,
+                                          sizes_arr.ctypes.data if sizes_arr is not None else None, dd, flags,
+                                          C.byref(res))
+        ctx.check(rc, "zb200_decompress_batch")
+        return res
+
+    def _run_contiguous(self, b, n, sizes_bytes, first_index, threads):
+        if n == 0:
+            return []
+        L = _native.lib()
+        segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
+        data = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
+        sizes_arr = np.frombuffer(sizes_bytes, dtype=np.uint64) if sizes_bytes is not None else None
+        parts = self._split(segs[:, 1], _devices(threads))
+        handles = []
+        for dev, (lo, hi) in enumerate(parts):
+            ctx = self._context(dev)
+            sub = np.ascontiguousarray(segs[lo:hi])
+            ssz = np.ascontiguousarray(sizes_arr[lo:hi]) if sizes_arr is not None else None
+            handles.append((ctx, lo, self._launch(ctx, data.ctypes.data, sub, hi - lo, ssz)))
+        out = []
+        for ctx, lo, res in handles:
+            self._raise_item_error(L, res, first_index + lo)
+            out.append(BufferWithSegments._from_result(ctx, res))
+        return out
+
+    def _run_list(self, views, sizes, threads):
+        L = _native.lib()
+        n = len(views)
+        lengths = np.array([v.nbytes for v in views], dtype=np.uint64)
+        sizes_arr = np.frombuffer(sizes, dtype=np.uint64) if sizes is not None else None
+        parts = self._split(lengths, _devices(threads))
+        out = []
+        for dev, (lo, hi) in enumerate(parts):
+            ctx = self._context(dev)
+            k = hi - lo
+            arrs = [np.frombuffer(v, dtype=np.uint8) if v.nbytes else np.zeros(0, dtype=np.uint8) for v in views[lo:hi]]
+            ptrs = (C.c_void_p * k)(*[a.ctypes.data if len(a) else None for a in arrs])
+            lens = (C.c_size_t * k)(*[len(a) for a in arrs])
+            ssz = np.ascontiguousarray(sizes_arr[lo:hi]) if sizes_arr is not None else None
+            res = C.c_void_p()
+            dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
+            with ctx.lock:
+                rc = L.zb200_decompress_batch_ptrs(ctx.h, ptrs, lens, k, ssz.ctypes.data if ssz is not None else None,
+                                                   dd, 0, C.byref(res))
+            ctx.check(rc, "zb200_decompress_batch_ptrs")
+            self._raise_item_error(L, res, lo)
+            out.append(BufferWithSegments._from_result(ctx, res))
+        return out
+
+    # ------------------------------------------------------------------ out of scope
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("streaming decompression objects are outside the B200 batch path")
+
+    stream_reader = stream_writer = decompressobj = read_to_iter = copy_stream = _unsupported
+    decompress_content_dict_chain = _unsupported
