@@ -58,3 +58,29 @@ def frame_header_size(data):
         raise ZstdError("could not determine frame header size: %s"
                         % _native.lib().zb200_error_string(info.status).decode())
     return info.header_size
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the codec context's pool.  Data placed here (e.g. the `data`
+    of a BufferWithSegments) is DMA-copied to the device at full PCIe rate instead of being staged."""
+
+    def __init__(self, nbytes, device=0):
+        import ctypes as C
+        from . import _native
+        self._ctx = _native.Context.get(device)
+        self._ptr = self._ctx.L.zb200_host_alloc(self._ctx.h, nbytes)
+        if not self._ptr:
+            raise MemoryError("pinned allocation of %d bytes failed" % nbytes)
+        self.nbytes = nbytes
+        self._arr = (C.c_ubyte * nbytes).from_address(self._ptr)
+        import weakref
+        self._fin = weakref.finalize(self, self._ctx.L.zb200_host_free, self._ctx.h, self._ptr)
+
+    def __buffer__(self, flags):
+        return memoryview(self._arr).cast("B")
+
+    def __release_buffer__(self, view):
+        pass
+
+    def __len__(self):
+        return self.nbytes

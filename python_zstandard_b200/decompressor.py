@@ -86,8 +86,8 @@ class ZstdDecompressor:
                 if code.value == 201:
                     raise ZstdError("decompression error: did not decompress full frame")
                 raise ZstdError("decompression error: %s" % L.zb200_error_string(code.value).decode())
-            n = L.zb200_result_size(res)
-            out = C.string_at(L.zb200_result_data(res), n) if n else b""
+            seg0 = _native.Segment.from_address(L.zb200_result_segments(res))
+            out = C.string_at(L.zb200_result_data(res) + seg0.offset, seg0.length) if seg0.length else b""
         finally:
             L.zb200_result_free(res)
         if not allow_extra_data:

@@ -1,0 +1,54 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports every symbol that
+include/zb200.h declares.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import __graft_entry__ as entry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    entry.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "python_zstandard_b200", "libzb200.so"))
+    header = open(os.path.join(ROOT, "include", "zb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(zb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_error_strings_match_reference_texts():
+    entry.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "python_zstandard_b200", "libzb200.so"))
+    lib.zb200_error_string.restype = ctypes.c_char_p
+    assert lib.zb200_error_string(20) == b"Data corruption detected"
+    assert lib.zb200_error_string(70) == b"Destination buffer is too small"
+    assert lib.zb200_error_string(10) == b"Unknown frame descriptor"
+
+
+def test_frame_info_host_parse():
+    import python_zstandard_b200 as zstd
+    from tests import helpers
+    assert zstd.frame_content_size(helpers.KAT_FOO) == 3
+    assert zstd.frame_content_size(helpers.KAT_EMPTY_NOFCS) == -1
+    assert zstd.frame_header_size(helpers.KAT_FOO) == 6
+    for name, frame, raw, dct in helpers.golden_vectors():
+        if "nocs" in name:
+            assert zstd.frame_content_size(frame) == -1
+        else:
+            assert zstd.frame_content_size(frame) == len(raw), name
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must fail loudly, not fall back."""
+    import pytest
+    import python_zstandard_b200 as zstd
+    from python_zstandard_b200 import _native
+    if _native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    from tests import helpers
+    with pytest.raises(_native.NativeError, match="no CPU fallback"):
+        zstd.ZstdDecompressor().decompress(helpers.KAT_FOO)
