@@ -18,9 +18,9 @@ extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
 void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, cudaStream_t st);
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
-                     u32* status, cudaStream_t st);
+                     u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
-                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u8* lane_scratch, u32 n_warps, u32* work_counter,
+                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                        ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st);
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
                        const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st);
@@ -56,7 +56,7 @@ struct zb200_ctx {
     std::string last_error;
     int sm_count = 148;
     // device arenas (grow-only)
-    DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs;
+    DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -167,7 +167,7 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
-                     &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs};
+                     &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial};
     for (auto* b : all) b->release();
     for (auto& b : ctx->pinned) cudaFreeHost(b.p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -283,6 +283,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(ctx->out_sizes.ensure(n * sizeof(u64)));
     CK(ctx->out_segs.ensure(n * sizeof(ZbSegment)));
     CK(ctx->small.ensure(256));
+    CK(ctx->partial.ensure(((n + 1023) / 1024 + 1) * 4 * sizeof(u64)));
     u64* d_totals = ctx->small.as<u64>();                 // [0..3] totals
     u32* d_counter = (u32*)(d_totals + 8);                // work counter
     u32* d_first_err = d_counter + 1;
@@ -292,17 +293,15 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), ctx->stream); }
     { KSpan s(ctx, ZB200_K_PLACE);
       zb_launch_place(ctx->info.as<ZbFrameInfo>(), d_dst_sizes, nf, ctx->place.as<ZbFramePlace>(), d_totals,
-                      ctx->status.as<u32>(), ctx->stream); }
+                      ctx->status.as<u32>(), ctx->partial.as<u64>(), ctx->stream); }
     u64 totals[4];
     CK(cudaMemcpyAsync(totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
-    // persistent entropy grid: enough warps to fill the machine, no more than the work
-    u32 warps = (u32)ctx->sm_count * 16;
-    u32 need_warps = (nf + 31) / 32;
-    if (warps > need_warps) warps = need_warps;
-    warps = (warps + 3) & ~3u;
-    CK(ctx->lane.ensure((size_t)warps * 32 * ZB_LANE_BYTES));
+    // persistent entropy grid: one CTA per SM (its shared memory holds the decode tables), fewer if the batch is small
+    u32 ctas = (u32)ctx->sm_count;
+    u32 need_ctas = (nf + 127) / 128;
+    if (ctas > need_ctas) ctas = need_ctas;
     CK(ctx->blocks.ensure((totals[1] + 1) * sizeof(ZbBlock)));
     CK(ctx->seqs.ensure((totals[2] + 1) * sizeof(ZbSeq)));
     CK(ctx->lits.ensure(totals[3] + 64));
@@ -311,7 +310,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
 
     { KSpan s(ctx, ZB200_K_ENTROPY);
       zb_launch_entropy(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
-                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->lane.as<u8>(), warps, d_counter, dd,
+                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctas, d_counter, dd,
                         ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->stream); }
     { KSpan s(ctx, ZB200_K_EXECUTE);
       zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),

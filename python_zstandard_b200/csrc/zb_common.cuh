@@ -125,7 +125,7 @@ __device__ __forceinline__ int zb_hibit(u32 v) { return 31 - __clz(v); }
 // bytes (not zeros): harmless, because left < 0 then fails the block.
 // ---------------------------------------------------------------------------
 struct ZbBitR {
-    const u32* w; int widx; u64 win; int avail; int left;
+    const u32* w; int widx; u64 win; int avail; int left; u32 nx0, nx1;   // nx0/nx1: the next two words, loaded ahead
 
     __device__ __forceinline__ bool init(const u8* s, u32 n) {
         if (n == 0) return false;
@@ -137,14 +137,23 @@ struct ZbBitR {
         int hb = zb_hibit(last);
         int P = (skew + (int)n - 1) * 8 + hb;      // bits from the aligned base up to the end mark
         left = ((int)n - 1) * 8 + hb;
+        nx0 = nx1 = 0;
         if (P == 0) { win = 0; avail = 0; widx = -1; return true; }
         int wi = (P - 1) >> 5, k = P - wi * 32;    // k in 1..32 valid bits in the top word
         win = (u64)w[wi] << (64 - k); avail = k; widx = wi - 1;
+        if (widx >= 0) nx0 = w[widx];
+        if (widx >= 1) nx1 = w[widx - 1];
         refill();
         return true;
     }
+    // The word that enters the window was loaded two refills ago, so its (global-memory) latency is
+    // off the decode chain; the load issued here is consumed 64 stream bits later.
     __device__ __forceinline__ void refill() {
-        if (avail <= 32 && widx >= 0) { win |= (u64)w[widx] << (32 - avail); avail += 32; widx--; }
+        if (avail <= 32 && widx >= 0) {
+            win |= (u64)nx0 << (32 - avail); avail += 32; widx--;
+            nx0 = nx1;
+            if (widx >= 1) nx1 = w[widx - 1];
+        }
     }
     __device__ __forceinline__ u32 peek(u32 nb) const { return (u32)((win >> 1) >> (63 - nb)); }
     __device__ __forceinline__ void skip(u32 nb) { win <<= nb; avail -= (int)nb; left -= (int)nb; }

@@ -158,65 +158,116 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
 }
 
 // ===========================================================================
-// K2: placement -- exclusive scans of the per-frame sizes by ONE CTA
-// totals[0..3] = dst bytes, blocks, seq records, literal scratch bytes; totals[4] = first failing frame + 1
+// K2: placement -- exclusive scans of the per-frame sizes (dst bytes, blocks, sequence records,
+// literal scratch).  Two launches: zb_place_reduce sums each CTA's 1024 frames, zb_place_scan lets
+// every CTA add up the partials before it and scan its own frames.
+// totals[0..3] = the four grand totals
 // ===========================================================================
-__global__ void zb_place_frames(const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_sizes,
-                                u32 n_frames, ZbFramePlace* __restrict__ place, u64* __restrict__ totals,
-                                u32* __restrict__ status)
+#define ZB_PLACE_CTA 1024
+
+__device__ __forceinline__ void zb_place_values(const ZbFrameInfo& fi, const u64* dst_sizes, u32 f, u64 v[4], u64& cap, u32& st)
+{
+    st = fi.status; cap = 0;
+    if (dst_sizes) cap = dst_sizes[f];
+    else if (fi.content_size != ZB_CONTENT_UNKNOWN) cap = fi.content_size;
+    else st = ZB_E_UNKNOWN_SIZE;                 // ZSTD_getFrameContentSize UNKNOWN/ERROR, c-ext/decompressor.c:981-1014
+    v[0] = cap;                                  // outputs are packed tightly, like the reference's
+    v[1] = v[2] = v[3] = 0;
+    if (st == ZB_OK) { v[1] = fi.n_blocks; v[2] = fi.n_seq_rec; v[3] = fi.n_lit; }
+}
+
+__global__ void __launch_bounds__(ZB_PLACE_CTA)
+zb_place_reduce(const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_sizes, u32 n_frames, u64* __restrict__ partial)
 {
     __shared__ u64 s_part[4][32];
-    __shared__ u64 s_run[4];
-    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    if (tid < 4) s_run[tid] = 0;
+    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 const f = blockIdx.x * ZB_PLACE_CTA + tid;
+    u64 v[4] = {0, 0, 0, 0};
+    if (f < n_frames) { u64 cap; u32 st; zb_place_values(info[f], dst_sizes, f, v, cap, st); }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u64 x = v[k];
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+        if (lane == 0) s_part[k][warp] = x;
+    }
     __syncthreads();
-    for (u32 base = 0; base < n_frames; base += blockDim.x) {
-        u32 f = base + tid; u64 v[4] = {0, 0, 0, 0}; u64 cap = 0;
-        if (f < n_frames) {
-            ZbFrameInfo fi = info[f];
-            u32 st = fi.status;
-            if (dst_sizes) cap = dst_sizes[f];
-            else if (fi.content_size != ZB_CONTENT_UNKNOWN) cap = fi.content_size;
-            else st = ZB_E_UNKNOWN_SIZE;                 // ZSTD_getFrameContentSize UNKNOWN/ERROR, c-ext/decompressor.c:981-1014
-            status[f] = st;
-            v[0] = cap;                                  // outputs are packed tightly, like the reference's
-            if (st == ZB_OK) { v[1] = fi.n_blocks; v[2] = fi.n_seq_rec; v[3] = fi.n_lit; }
-        }
-        u64 incl[4];
+    if (warp == 0) {
         #pragma unroll
         for (int k = 0; k < 4; k++) {
-            u64 x = v[k];
+            u64 x = s_part[k][lane];
             #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
-            incl[k] = x;
-            if (lane == 31) s_part[k][warp] = x;
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+            if (lane == 0) partial[blockIdx.x * 4 + k] = x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ZB_PLACE_CTA)
+zb_place_scan(const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_sizes, u32 n_frames,
+              const u64* __restrict__ partial, ZbFramePlace* __restrict__ place, u64* __restrict__ totals,
+              u32* __restrict__ status)
+{
+    __shared__ u64 s_part[4][32];
+    __shared__ u64 s_base[4];
+    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // base of this CTA = sum of the partials of all CTAs before it
+    {
+        u64 acc[4] = {0, 0, 0, 0};
+        for (u32 c = tid; c < blockIdx.x; c += ZB_PLACE_CTA) { for (int k = 0; k < 4; k++) acc[k] += partial[c * 4 + k]; }
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u64 x = acc[k];
+            #pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+            if (lane == 0) s_part[k][warp] = x;
         }
         __syncthreads();
         if (warp == 0) {
             #pragma unroll
             for (int k = 0; k < 4; k++) {
-                u64 x = lane < nwarp ? s_part[k][lane] : 0;
+                u64 x = s_part[k][lane];
                 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
-                s_part[k][lane] = x;                      // inclusive over warps
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+                if (lane == 0) s_base[k] = x;
             }
         }
         __syncthreads();
-        if (f < n_frames) {
-            u64 off[4];
-            #pragma unroll
-            for (int k = 0; k < 4; k++) off[k] = s_run[k] + (warp ? s_part[k][warp - 1] : 0) + incl[k] - v[k];
-            ZbFramePlace p; p.dst_off = off[0]; p.dst_cap = cap; p.blk_off = off[1]; p.seq_off = off[2]; p.lit_off = off[3];
-            place[f] = p;
-        }
-        __syncthreads();
-        if (tid < 4) s_run[tid] += s_part[tid][nwarp - 1];
-        __syncthreads();
     }
-    if (tid < 4) totals[tid] = s_run[tid];
-    if (tid == 0) {                                       // sentinel: place[n_frames] bounds the last frame's slices
-        ZbFramePlace p; p.dst_off = s_run[0]; p.dst_cap = 0; p.blk_off = s_run[1]; p.seq_off = s_run[2]; p.lit_off = s_run[3];
+    u32 const f = blockIdx.x * ZB_PLACE_CTA + tid;
+    u64 v[4] = {0, 0, 0, 0}; u64 cap = 0; u32 st = ZB_OK;
+    if (f < n_frames) { zb_place_values(info[f], dst_sizes, f, v, cap, st); status[f] = st; }
+    u64 incl[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u64 x = v[k];
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
+        incl[k] = x;
+        if (lane == 31) s_part[k][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u64 x = s_part[k][lane];
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (u32)d) x += y; }
+            s_part[k][lane] = x;
+        }
+    }
+    __syncthreads();
+    u64 off[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) off[k] = s_base[k] + (warp ? s_part[k][warp - 1] : 0) + incl[k] - v[k];
+    if (f < n_frames) {
+        ZbFramePlace p; p.dst_off = off[0]; p.dst_cap = cap; p.blk_off = off[1]; p.seq_off = off[2]; p.lit_off = off[3];
+        place[f] = p;
+    }
+    if (f == n_frames - 1) {                      // grand totals + the sentinel that bounds the last frame's slices
+        ZbFramePlace p; p.dst_off = off[0] + v[0]; p.dst_cap = 0; p.blk_off = off[1] + v[1]; p.seq_off = off[2] + v[2]; p.lit_off = off[3] + v[3];
         place[n_frames] = p;
+        totals[0] = p.dst_off; totals[1] = p.blk_off; totals[2] = p.seq_off; totals[3] = p.lit_off;
     }
 }
 
@@ -224,15 +275,22 @@ __global__ void zb_place_frames(const ZbFrameInfo* __restrict__ info, const u64*
 // K3: entropy decode -- one lane per frame
 // ===========================================================================
 
-// forward (LSB-first) bit peek of <= 16 bits at bit position `bp` of s[0..n), zero padded
-__device__ __forceinline__ u32 zb_fwd_peek(const u8* s, u32 n, u32 bp, u32 nb)
-{
-    u32 by = bp >> 3, a = 0;
-    if (by < n) a = s[by];
-    if (by + 1 < n) a |= (u32)s[by + 1] << 8;
-    if (by + 2 < n) a |= (u32)s[by + 2] << 16;
-    return (a >> (bp & 7)) & ((1u << nb) - 1);
-}
+// forward (LSB-first) bit reader for the small table headers: a 64-bit window refilled 4 bytes at
+// a time, so a header costs a handful of memory round trips instead of one per field
+struct ZbFwdR {
+    const u8* s; u32 n; u32 next_byte; u64 win; u32 have; u32 bp;
+    __device__ __forceinline__ void init(const u8* s_, u32 n_) { s = s_; n = n_; next_byte = 0; win = 0; have = 0; bp = 0; fill(); fill(); }
+    __device__ __forceinline__ void fill() {
+        if (have <= 32) {
+            u32 v = 0;
+            #pragma unroll
+            for (u32 k = 0; k < 4; k++) if (next_byte + k < n) v |= (u32)s[next_byte + k] << (8 * k);
+            win |= (u64)v << have; have += 32; next_byte += 4;
+        }
+    }
+    __device__ __forceinline__ u32 peek(u32 nb) const { return (u32)win & ((1u << nb) - 1); }
+    __device__ __forceinline__ void skip(u32 nb) { win >>= nb; have -= nb; bp += nb; fill(); }
+};
 
 // normalized-count header (restates FSE_readNCount_body, zstd/zstd.c:3256-3413).
 // returns bytes consumed, 0 on error
@@ -241,24 +299,25 @@ __device__ static u32 zb_read_ncount(short* norm, u32& max_sym, u32& table_log, 
     u32 const max_sv1 = max_sym + 1;
     if (n == 0) return 0;
     for (u32 i = 0; i < max_sv1; i++) norm[i] = 0;
-    u32 bp = 0, sym = 0; int prev0 = 0;
-    int nbits = (int)zb_fwd_peek(s, n, 0, 4) + 5; bp = 4;
+    ZbFwdR r; r.init(s, n);
+    u32 sym = 0; int prev0 = 0;
+    int nbits = (int)r.peek(4) + 5; r.skip(4);
     if (nbits > 15) return 0;
     table_log = (u32)nbits;
     int remaining = (1 << nbits) + 1, threshold = 1 << nbits; nbits++;
     for (;;) {
         if (prev0) {
             for (;;) {
-                u32 r = zb_fwd_peek(s, n, bp, 2); bp += 2; sym += r;
-                if (r != 3) break;
-                if (bp > 8 * n + 64) return 0;
+                u32 rp = r.peek(2); r.skip(2); sym += rp;
+                if (rp != 3) break;
+                if (r.bp > 8 * n + 64) return 0;
             }
             if (sym >= max_sv1) break;
         }
         int const mx = (2 * threshold - 1) - remaining;
-        int count; int low = (int)zb_fwd_peek(s, n, bp, (u32)(nbits - 1));
-        if (low < mx) { count = low; bp += (u32)(nbits - 1); }
-        else { count = (int)zb_fwd_peek(s, n, bp, (u32)nbits); if (count >= threshold) count -= mx; bp += (u32)nbits; }
+        int count; int low = (int)r.peek((u32)(nbits - 1));
+        if (low < mx) { count = low; r.skip((u32)(nbits - 1)); }
+        else { count = (int)r.peek((u32)nbits); if (count >= threshold) count -= mx; r.skip((u32)nbits); }
         count--;
         remaining -= count < 0 ? -count : count;
         norm[sym++] = (short)count;
@@ -269,9 +328,9 @@ __device__ static u32 zb_read_ncount(short* norm, u32& max_sym, u32& table_log, 
         }
         if (sym >= max_sv1) break;
     }
-    if (remaining != 1 || sym > max_sv1 || bp > 8 * n) return 0;
+    if (remaining != 1 || sym > max_sv1 || r.bp > 8 * n) return 0;
     max_sym = sym - 1;
-    return (bp + 7) >> 3;
+    return (r.bp + 7) >> 3;
 }
 
 __device__ __forceinline__ void zb_cell_payload(ZbFseCell& c, u32 sym, int kind)
@@ -389,250 +448,30 @@ __device__ static u32 zb_read_huf_table(u16* cells, u32& out_log, const u8* s, u
     return hdr + 1;
 }
 
-// one Huffman stream -> n_out literal bytes (restates HUF_decompress1X1_usingDTable_internal_body, zstd/zstd.c:39845)
-__device__ static bool zb_huf_stream(u8* out, u32 n_out, const u8* s, u32 n, const u16* cells, u32 log)
-{
-    ZbBitR b;
-    if (!b.init(s, n)) return false;
-    for (u32 i = 0; i < n_out; i++) {
-        u32 c = cells[b.peek(log)];
-        out[i] = (u8)c; b.skip(c >> 8); b.refill();
-    }
-    return b.left == 0;
-}
-
 struct ZbTab { const ZbFseCell* t; u32 log; };
 
-// sequence table per mode (restates ZSTD_buildSeqTable, zstd/zstd.c:46280-46326). returns bytes used or -1
-__device__ static int zb_seq_table(ZbTab& cur, ZbFseCell* own, u32 mode, u32 max_sym, u32 max_log, int kind,
-                                   const u8* s, u32 n, bool repeat_ok)
-{
-    if (mode == 0) {
-        cur.t = kind == K_LL ? g_defLL : (kind == K_OF ? g_defOF : g_defML);
-        cur.log = kind == K_OF ? 5 : 6;
-        return 0;
-    }
-    if (mode == 1) {
-        if (n == 0 || s[0] > max_sym) return -1;
-        ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, s[0], kind);
-        own[0] = c; cur.t = own; cur.log = 0;
-        return 1;
-    }
-    if (mode == 3) return repeat_ok ? 0 : -1;
-    short norm[64]; u32 log;
-    u32 used = zb_read_ncount(norm, max_sym, log, s, n);
-    if (used == 0 || log > max_log) return -1;
-    zb_build_fse<64>(own, norm, max_sym, log, kind);
-    cur.t = own; cur.log = log;
-    return (int)used;
-}
-
-__global__ void __launch_bounds__(128)
-zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
-                  const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
-                  ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
-                  u8* __restrict__ lane_scratch, u32* __restrict__ work_counter,
-                  ZbDictDev dict, u32* status, u64* __restrict__ out_sizes)
-{
-    u32 const lane = threadIdx.x & 31;
-    u32 const gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    u8* const my = lane_scratch + ((u64)gwarp * 32 + lane) * ZB_LANE_BYTES;
-    u16* const huf_own = (u16*)(my + ZB_LANE_HUF);
-    ZbFseCell* const ll_own = (ZbFseCell*)(my + ZB_LANE_LL);
-    ZbFseCell* const ml_own = (ZbFseCell*)(my + ZB_LANE_ML);
-    ZbFseCell* const of_own = (ZbFseCell*)(my + ZB_LANE_OF);
-    ZbFseCell* const wt_own = (ZbFseCell*)(my + ZB_LANE_WT);
-
-    for (;;) {
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n_frames) return;
-        u32 const f = base + lane;
-        if (f >= n_frames) continue;
-        if (status[f] != ZB_OK) { out_sizes[f] = 0; continue; }
-
-        const u8* s = src + segs[f].offset; u64 n = segs[f].length;
-        zb_skip_skippable(s, n);
-        ZbHdr h; zb_parse_header(s, n, h);
-        ZbFramePlace const pl = place[f];
-        u32 err = ZB_OK;
-        u64 const cap = pl.dst_cap;
-        u64 out_pos = 0;                      // frame-relative output position
-        u64 blk_i = pl.blk_off, seq_i = pl.seq_off, lit_i = pl.lit_off;
-        u32 const block_max = h.window < ZB_BLOCK_MAX ? (u32)h.window : ZB_BLOCK_MAX;
-        u32 rep0 = 1, rep1 = 4, rep2 = 8;
-        const u16* huf = huf_own; u32 huf_log = 0; bool huf_valid = false, fse_valid = false;
-        ZbTab tLL = {g_defLL, 6}, tOF = {g_defOF, 5}, tML = {g_defML, 6};
-        u64 const hist_extra = dict.content_size;       // bytes of history before the frame
-        if (dict.has_entropy) {
-            huf = dict.huf; huf_log = dict.huf_log; huf_valid = true; fse_valid = true;
-            tLL.t = dict.ll; tLL.log = dict.ll_log; tOF.t = dict.of; tOF.log = dict.of_log; tML.t = dict.ml; tML.log = dict.ml_log;
-            rep0 = dict.rep[0]; rep1 = dict.rep[1]; rep2 = dict.rep[2];
-        }
-        if (h.dict_id && dict.dict_id && h.dict_id != dict.dict_id) err = ZB_E_DICT_WRONG;
-
-        u64 pos = h.hdr_size;
-        while (!err) {
-            if (pos + 3 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
-            u32 bh = zb_rd24(s + pos); pos += 3;
-            u32 const last = bh & 1, type = (bh >> 1) & 3; u32 bsize = bh >> 3;
-            ZbBlock B; B.out_pos = out_pos; B.kind = type; B.seq_pos = seq_i; B.n_seq = 0; B.n_lit = 0; B.lit_kind = 0; B.lit_byte = 0;
-            if (type == ZB_BLK_RLE) {
-                if (pos + 1 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
-                if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
-                if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
-                B.src_pos = (u64)(s + pos - src); B.regen = bsize; B.lit_byte = s[pos];
-                pos += 1;
-            } else if (type == ZB_BLK_RAW) {
-                if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
-                if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
-                if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
-                B.src_pos = (u64)(s + pos - src); B.regen = bsize;
-                pos += bsize;
-            } else {
-                if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
-                if (bsize > block_max) { err = ZB_E_SRCSIZE_WRONG; break; }
-                const u8* const bs = s + pos; const u8* const bend = bs + bsize;
-                // ---- literals section (restates ZSTD_decodeLiteralsBlock, zstd/zstd.c:45767-45973)
-                ZbLitHdr L; err = zb_parse_lit_header(bs, bsize, L);
-                if (err) break;
-                if (L.regen > block_max) { err = ZB_E_CORRUPTION; break; }
-                const u8* ip;
-                B.n_lit = L.regen;
-                if (L.type == 0) {
-                    if (L.hdr + L.regen > bsize) { err = ZB_E_CORRUPTION; break; }
-                    B.lit_kind = ZB_LIT_RAW; B.src_pos = (u64)(bs + L.hdr - src); ip = bs + L.hdr + L.regen;
-                } else if (L.type == 1) {
-                    if (L.hdr + 1 > bsize) { err = ZB_E_CORRUPTION; break; }
-                    B.lit_kind = ZB_LIT_RLE; B.lit_byte = bs[L.hdr]; B.src_pos = 0; ip = bs + L.hdr + 1;
-                } else {
-                    if (L.type == 3 && !huf_valid) { err = ZB_E_DICT_CORRUPTED; break; }
-                    if (!L.single && L.regen < 6) { err = ZB_E_LITERALS_HEADER_WRONG; break; }
-                    if (L.csize + L.hdr > bsize) { err = ZB_E_CORRUPTION; break; }
-                    if (L.regen == 0) { err = ZB_E_CORRUPTION; break; }
-                    const u8* p = bs + L.hdr; u32 left = L.csize;
-                    if (L.type == 2) {
-                        u32 used = zb_read_huf_table(huf_own, huf_log, p, left, wt_own);
-                        if (used == 0 || used >= left) { err = ZB_E_CORRUPTION; break; }
-                        huf = huf_own; p += used; left -= used;
-                    }
-                    u8* const dstl = lits + lit_i;
-                    bool ok;
-                    if (L.single) ok = zb_huf_stream(dstl, L.regen, p, left, huf, huf_log);
-                    else {
-                        ok = left >= 10;
-                        if (ok) {
-                            u32 l1 = zb_rd16(p), l2 = zb_rd16(p + 2), l3 = zb_rd16(p + 4);
-                            u32 seg = (L.regen + 3) / 4;
-                            ok = (6 + l1 + l2 + l3 <= left) && (seg * 3 <= L.regen);
-                            if (ok) {
-                                u32 l4 = left - 6 - l1 - l2 - l3;
-                                ok = zb_huf_stream(dstl, seg, p + 6, l1, huf, huf_log)
-                                  && zb_huf_stream(dstl + seg, seg, p + 6 + l1, l2, huf, huf_log)
-                                  && zb_huf_stream(dstl + 2 * seg, seg, p + 6 + l1 + l2, l3, huf, huf_log)
-                                  && zb_huf_stream(dstl + 3 * seg, L.regen - 3 * seg, p + 6 + l1 + l2 + l3, l4, huf, huf_log);
-                            }
-                        }
-                    }
-                    if (!ok) { err = ZB_E_CORRUPTION; break; }
-                    huf_valid = true;
-                    B.lit_kind = ZB_LIT_SCRATCH; B.src_pos = lit_i; lit_i += (L.regen + 15) & ~15u;
-                    ip = bs + L.hdr + L.csize;
-                }
-                // ---- sequences section header (restates ZSTD_decodeSeqHeaders, zstd/zstd.c:46328-46410)
-                if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; }
-                u32 nseq = *ip++;
-                if (nseq > 0x7F) {
-                    if (nseq == 0xFF) { if (ip + 2 > bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
-                    else { if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
-                }
-                B.n_seq = nseq;
-                u32 lit_used = 0, produced = 0;         // block-relative
-                if (nseq == 0) {
-                    if (ip != bend) { err = ZB_E_CORRUPTION; break; }
-                } else {
-                    if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
-                    u32 const modes = *ip++;
-                    if (modes & 3) { err = ZB_E_CORRUPTION; break; }
-                    int r;
-                    r = zb_seq_table(tLL, ll_own, modes >> 6, 35, 9, K_LL, ip, (u32)(bend - ip), fse_valid);
-                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
-                    r = zb_seq_table(tOF, of_own, (modes >> 4) & 3, 31, 8, K_OF, ip, (u32)(bend - ip), fse_valid);
-                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
-                    r = zb_seq_table(tML, ml_own, (modes >> 2) & 3, 52, 9, K_ML, ip, (u32)(bend - ip), fse_valid);
-                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r;
-                    fse_valid = true;
-                    // ---- the 3-state FSE sequence stream (restates ZSTD_decodeSequence, zstd/zstd.c:46862-46986)
-                    ZbBitR b;
-                    if (!b.init(ip, (u32)(bend - ip))) { err = ZB_E_CORRUPTION; break; }
-                    u32 sLL = b.read(tLL.log); u32 sOF = b.read(tOF.log); b.refill(); u32 sML = b.read(tML.log); b.refill();
-                    const ZbFseCell* const TL = tLL.t; const ZbFseCell* const TO = tOF.t; const ZbFseCell* const TM = tML.t;
-                    u64 const room = cap - out_pos;
-                    for (u32 i = 0; i < nseq; i++) {
-                        ZbFseCell const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
-                        u32 ll = cl.base, ml = cm.base, off;
-                        if (co.add_bits > 1) {
-                            off = co.base + b.read(co.add_bits);
-                            rep2 = rep1; rep1 = rep0; rep0 = off;
-                        } else {
-                            u32 const ll0 = (cl.base == 0);
-                            if (co.add_bits == 0) {
-                                if (ll0) { off = rep1; rep1 = rep0; rep0 = off; } else off = rep0;
-                            } else {
-                                u32 idx = co.base + ll0 + b.read(1);
-                                u32 tmp = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
-                                if (tmp == 0) tmp = 0xFFFFFFFFu;
-                                if (idx != 1) rep2 = rep1;
-                                rep1 = rep0; rep0 = off = tmp;
-                            }
-                        }
-                        b.refill();
-                        ml += b.read(cm.add_bits);
-                        ll += b.read(cl.add_bits);
-                        b.refill();
-                        if (i + 1 < nseq) {
-                            sLL = cl.next + b.read(cl.nb);
-                            sML = cm.next + b.read(cm.nb);
-                            sOF = co.next + b.read(co.nb);
-                            b.refill();
-                        }
-                        seqs[seq_i + i] = make_uint4(lit_used, produced, ml, off);
-                        // validation (restates the checks of ZSTD_execSequence/ZSTD_execSequenceEnd, zstd/zstd.c:46540-46728)
-                        if ((u64)produced + ll + ml > room) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
-                        if (ll > L.regen - lit_used) { err = ZB_E_CORRUPTION; break; }
-                        lit_used += ll; produced += ll;
-                        if ((u64)off > out_pos + produced + hist_extra) { err = ZB_E_CORRUPTION; break; }
-                        produced += ml;
-                    }
-                    if (err) break;
-                    if (b.left != 0) { err = ZB_E_CORRUPTION; break; }
-                }
-                seqs[seq_i + nseq] = make_uint4(lit_used, produced, 0, 0);
-                seq_i += nseq + 1;
-                u32 const tail = L.regen - lit_used;
-                if ((u64)produced + tail > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
-                B.regen = produced + tail;
-                if (B.regen > block_max) { err = ZB_E_CORRUPTION; break; }
-                pos += bsize;
-            }
-            blocks[blk_i++] = B;
-            out_pos += B.regen;
-            if (last) break;
-        }
-        if (!err) {
-            if (h.content_size != ZB_CONTENT_UNKNOWN && out_pos != h.content_size) err = ZB_E_CORRUPTION;
-            else if (h.checksum && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
-        }
-        if (!err && dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;   // c-ext/decompressor.c:1151-1162
-        if (err) { status[f] = err; out_sizes[f] = 0; }       // the execute stage skips failed frames
-        else out_sizes[f] = out_pos;
-    }
-}
+#include "zb_entropy.cuh"
 
 // ===========================================================================
 // K4: LZ copy-execute -- one warp per frame
 // ===========================================================================
+
+// per-lane forward copy in chunks of 8 bytes: the 8 loads of a chunk are independent (issued back to
+// back) and precede its 8 stores, so a copy costs one memory latency per 8 bytes instead of per byte.
+// Safe for overlapping ranges whenever dst - src >= 8.
+__device__ __forceinline__ void zb_copy_fwd8(u8* d, const u8* s, u32 n)
+{
+    u32 k = 0;
+    for (; k + 8 <= n; k += 8) {
+        u8 t0 = s[k], t1 = s[k + 1], t2 = s[k + 2], t3 = s[k + 3], t4 = s[k + 4], t5 = s[k + 5], t6 = s[k + 6], t7 = s[k + 7];
+        d[k] = t0; d[k + 1] = t1; d[k + 2] = t2; d[k + 3] = t3; d[k + 4] = t4; d[k + 5] = t5; d[k + 6] = t6; d[k + 7] = t7;
+    }
+    if (k + 4 <= n) {
+        u8 t0 = s[k], t1 = s[k + 1], t2 = s[k + 2], t3 = s[k + 3];
+        d[k] = t0; d[k + 1] = t1; d[k + 2] = t2; d[k + 3] = t3; k += 4;
+    }
+    for (; k < n; k++) d[k] = s[k];
+}
 
 // warp-cooperative byte copy (no overlap between src and dst)
 __device__ __forceinline__ void zb_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
@@ -654,13 +493,14 @@ __device__ __forceinline__ void zb_warp_copy(u8* dst, const u8* src, u32 n, u32 
 __global__ void __launch_bounds__(256)
 zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
            const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
-           u8* dst, u32 n_frames, ZbDictDev dict)
+           u8* dst, u32 n_frames, ZbDictDev dict, u64 min_cap)
 {
     u32 const lane = threadIdx.x & 31;
     u32 const f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= n_frames) return;
     if (status[f] != ZB_OK) return;
     ZbFramePlace const pl = place[f];
+    if (pl.dst_cap < min_cap) return;                    // staged in shared memory by zb_execute_tile
     u8* const out = dst + pl.dst_off;
     u64 const blk_end = place[f + 1].blk_off;            // place[] has n_frames + 1 entries
     const u8* const dict_end = dict.content + dict.content_size;
@@ -684,7 +524,7 @@ zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, c
             // literals: independent of everything else
             if (valid) {
                 if (lit_rle) for (u32 k = 0; k < ll; k++) bout[ostart + k] = lit_byte;
-                else { const u8* lp = lit + r.x; for (u32 k = 0; k < ll; k++) bout[ostart + k] = lp[k]; }
+                else zb_copy_fwd8(bout + ostart, lit + r.x, ll);
             }
             __syncwarp();
             // matches: a lane may run when every byte it reads that other sequences produce lies
@@ -727,7 +567,7 @@ zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, c
                         u8* d = out + abs_m;
                         if (srcp >= 0) {
                             const u8* sp = out + srcp;
-                            if (off >= ml) for (u32 k = 0; k < ml; k++) d[k] = sp[k];
+                            if (off >= 8) zb_copy_fwd8(d, sp, ml);
                             else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
                         } else {
                             for (u32 k = 0; k < ml; k++) { long long p = srcp + (long long)(k % off); d[k] = p < 0 ? dict_end[p] : out[p]; }
@@ -749,6 +589,131 @@ zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, c
     }
 }
 
+
+
+
+// ---------------------------------------------------------------------------
+// K4 (tile variant): frames whose whole output fits a shared-memory tile.  The warp regenerates the
+// frame in shared memory -- literal runs and match copies become LDS/STS with no global-memory
+// sector scatter -- and writes the finished frame to HBM with 128-bit coalesced stores.
+// ---------------------------------------------------------------------------
+#define ZB_TILE_CAP    4096
+#define ZB_TILE_WARPS  8
+#define ZB_TILE_WARP_BYTES (2 * ZB_TILE_CAP + 64)
+#define ZB_TILE_SMEM   (ZB_TILE_WARPS * ZB_TILE_WARP_BYTES)
+
+__global__ void __launch_bounds__(ZB_TILE_WARPS * 32)
+zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
+                const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
+                u8* __restrict__ dst, u32 n_frames, ZbDictDev dict)
+{
+    extern __shared__ __align__(16) u8 zb_tile[];
+    u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 const f = blockIdx.x * ZB_TILE_WARPS + warp;
+    if (f >= n_frames) return;
+    if (status[f] != ZB_OK) return;
+    ZbFramePlace const pl = place[f];
+    if (pl.dst_cap > ZB_TILE_CAP) return;                // handled by zb_execute
+    u64 const blk_end = place[f + 1].blk_off;
+    u32 const skew = (u32)(pl.dst_off & 15);             // same 16-byte phase in smem as in dst
+    u8* const so = zb_tile + warp * ZB_TILE_WARP_BYTES + skew;          // output tile
+    u8* const sl = zb_tile + warp * ZB_TILE_WARP_BYTES + ZB_TILE_CAP + 32;   // literal tile (16-byte aligned)
+    const u8* const dict_end = dict.content + dict.content_size;
+    u32 total = 0;
+
+    for (u64 bi = pl.blk_off; bi < blk_end; bi++) {
+        ZbBlock const B = blocks[bi];
+        u8* const bout = so + B.out_pos;
+        total = (u32)B.out_pos + B.regen;
+        if (B.kind == ZB_BLK_RAW) { const u8* p = src + B.src_pos; for (u32 i = lane; i < B.regen; i += 32) bout[i] = p[i]; __syncwarp(); continue; }
+        if (B.kind == ZB_BLK_RLE) { for (u32 i = lane; i < B.regen; i += 32) bout[i] = (u8)B.lit_byte; __syncwarp(); continue; }
+        if (B.kind != ZB_BLK_COMPRESSED) return;
+        bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
+        if (B.lit_kind == ZB_LIT_SCRATCH) {               // 16-byte aligned slice of the literal scratch
+            const uint4* g = (const uint4*)(lits + B.src_pos); uint4* d4 = (uint4*)sl;
+            for (u32 i = lane; i < (B.n_lit + 15) / 16; i += 32) d4[i] = g[i];
+        } else if (B.lit_kind == ZB_LIT_RAW) {
+            const u8* g = src + B.src_pos; for (u32 i = lane; i < B.n_lit; i += 32) sl[i] = g[i];
+        }
+        __syncwarp();
+        const ZbSeq* const sq = seqs + B.seq_pos;
+        u32 const nseq = B.n_seq;
+        for (u32 g = 0; g < nseq; g += 32) {
+            u32 const i = g + lane; bool const valid = i < nseq;
+            ZbSeq const r = valid ? sq[i] : make_uint4(0, 0, 0, 0);
+            u32 nx = __shfl_down_sync(0xFFFFFFFFu, r.x, 1);
+            if (lane == 31 || i + 1 >= nseq) nx = valid ? sq[i + 1].x : 0;
+            u32 const ll = nx - r.x, ml = r.z, off = r.w;
+            u32 const ostart = r.y, mstart = r.y + ll;
+            if (valid) {
+                u8* o = bout + ostart;
+                if (lit_rle) for (u32 k = 0; k < ll; k++) o[k] = lit_byte;
+                else zb_copy_fwd8(o, sl + r.x, ll);
+            }
+            __syncwarp();
+            bool pending = valid;
+            int const abs_m = (int)B.out_pos + (int)mstart;             // frame-relative match start
+            int const srcp = abs_m - (int)off;                          // negative: reaches into the dictionary
+            int const need = min(srcp + (int)ml, (int)B.out_pos + (int)ostart);
+            for (;;) {
+                u32 const pm = __ballot_sync(0xFFFFFFFFu, pending);
+                if (!pm) break;
+                int const fu = __ffs(pm) - 1;
+                int const F = __shfl_sync(0xFFFFFFFFu, abs_m, fu);
+                bool const ready = pending && need <= F;
+                u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 32);
+                while (big) {
+                    int const l = __ffs(big) - 1; big &= big - 1;
+                    int const m0 = __shfl_sync(0xFFFFFFFFu, abs_m, l);
+                    u32 const o = __shfl_sync(0xFFFFFFFFu, off, l), len = __shfl_sync(0xFFFFFFFFu, ml, l);
+                    u8* d = so + m0;
+                    if ((int)o > m0) {
+                        for (u32 j = lane; j < len; j += 32) { int sp = m0 - (int)o + (int)(j % o); d[j] = sp < 0 ? dict_end[sp] : so[sp]; }
+                    } else if (o >= 32) {
+                        const u8* sp = d - o;
+                        for (u32 j = 0; j < len; j += 32) { if (j + lane < len) d[j + lane] = sp[j + lane]; __syncwarp(); }
+                    } else {
+                        const u8* sp = d - o;
+                        for (u32 j = lane; j < len; j += 32) d[j] = sp[j % o];
+                    }
+                    __syncwarp();
+                }
+                if (ready) {
+                    if (ml < 32) {
+                        u8* d = so + abs_m;
+                        if (srcp >= 0) {
+                            const u8* sp = so + srcp;
+                            if (off >= 8) zb_copy_fwd8(d, sp, ml);      // 8-byte chunks never read their own output
+                            else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
+                        } else {
+                            for (u32 k = 0; k < ml; k++) { int p = srcp + (int)(k % off); d[k] = p < 0 ? dict_end[p] : so[p]; }
+                        }
+                    }
+                    pending = false;
+                }
+                __syncwarp();
+            }
+        }
+        {
+            ZbSeq const e = sq[nseq];
+            u32 const tail = B.n_lit - e.x;
+            if (lit_rle) { for (u32 k = lane; k < tail; k += 32) bout[e.y + k] = lit_byte; }
+            else for (u32 k = lane; k < tail; k += 32) bout[e.y + k] = sl[e.x + k];
+        }
+        __syncwarp();
+    }
+    // finished frame -> HBM, 128-bit stores (so and dst share the same 16-byte phase)
+    {
+        u8* const out = dst + pl.dst_off;
+        u32 head = (16 - skew) & 15; if (head > total) head = total;
+        if (lane < head) out[lane] = so[lane];
+        u32 const nv = (total - head) >> 4;
+        const uint4* s4 = (const uint4*)(so + head); uint4* d4 = (uint4*)(out + head);
+        for (u32 i = lane; i < nv; i += 32) d4[i] = s4[i];
+        u32 const done = head + (nv << 4);
+        if (done + lane < total) out[done + lane] = so[done + lane];
+    }
+}
 
 // ===========================================================================
 // K5: finish -- output segment table + lowest failing frame
@@ -812,26 +777,35 @@ void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* in
 }
 
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
-                     u32* status, cudaStream_t st)
+                     u32* status, u64* partial, cudaStream_t st)
 {
-    zb_place_frames<<<1, 1024, 0, st>>>(info, dst_sizes, n, place, totals, status);
+    u32 const ctas = (n + ZB_PLACE_CTA - 1) / ZB_PLACE_CTA;
+    zb_place_reduce<<<ctas, ZB_PLACE_CTA, 0, st>>>(info, dst_sizes, n, partial);
+    zb_place_scan<<<ctas, ZB_PLACE_CTA, 0, st>>>(info, dst_sizes, n, partial, place, totals, status);
 }
 
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
-                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u8* lane_scratch, u32 n_warps, u32* work_counter,
+                       ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                        ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st)
 {
-    // n_warps resident warps of 32 lanes; 4 warps per CTA
-    zb_entropy_decode<<<(n_warps + 3) / 4, 128, 0, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
-                                                         lane_scratch, work_counter, dict, status, out_sizes);
+    // persistent grid: one CTA of ZB_ENT_WARPS warps per SM, each warp with its own shared-memory table pool
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM); attr_set = true; }
+    zb_entropy_decode<<<n_ctas, ZB_ENT_WARPS * 32, ZB_ENT_SMEM, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
+                                                                     work_counter, dict, status, out_sizes);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
                        const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st)
 {
+    // frames <= ZB_TILE_CAP bytes are regenerated in shared memory, larger ones straight in HBM/L2
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM); attr_set = true; }
+    zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
+                                                                                                 seqs, lits, dst, n, dict);
     u32 const warps_per_cta = 8;
     zb_execute<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(src, place, status, blocks, seqs,
-                                                                                       lits, dst, n, dict);
+                                                                                       lits, dst, n, dict, (u64)ZB_TILE_CAP + 1);
 }
 
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,

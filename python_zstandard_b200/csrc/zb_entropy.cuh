@@ -1,0 +1,455 @@
+// zb_entropy.cuh -- K3, the entropy stage (included by zb_decode.cu).
+//
+// One LANE per frame: the bit-serial chains of a frame (Huffman literal streams, FSE table
+// builds, the 3-state FSE sequence stream, repcode history) cannot be parallelised inside a
+// block, so 32 independent frames advance in lock-step per warp and every issue slot carries
+// 32 frames' worth of serial work.
+//
+// Every decode table lives in SHARED MEMORY: each warp owns a pool, lanes claim exactly the
+// bytes their tables need (2^log cells) through a warp prefix-scan, and when a pool cannot hold
+// all 32 claims the remaining lanes run in a second pass.  A frame's tables are rebuilt per block
+// from the header that defined them ("repeat" modes re-read that header), so nothing but a few
+// descriptors has to survive between blocks.
+//
+// Restates, per lane: ZSTD_decodeLiteralsBlock (zstd/zstd.c:45767), HUF_readStats (:3457),
+// HUF_readDTableX1_wksp (:39651), HUF_decompress{1,4}X1_usingDTable_internal_body (:39845,:39868),
+// ZSTD_decodeSeqHeaders (:46328), ZSTD_buildFSETable_body (:46118), ZSTD_decodeSequence (:46862).
+#pragma once
+
+#define ZB_ENT_WARPS      4                       // warps per CTA
+#define ZB_ENT_WS_BYTES   256                     // per-lane workspace (weights / normalized counts)
+#define ZB_ENT_POOL_BYTES (55 * 1024)             // per-warp pool, workspace included
+#define ZB_ENT_SMEM       (ZB_ENT_WARPS * ZB_ENT_POOL_BYTES)
+
+// where a table comes from; enough to rebuild it for a later block
+enum : u32 { ZB_SRC_NONE = 0, ZB_SRC_PREDEF = 1, ZB_SRC_RLE = 2, ZB_SRC_NCOUNT = 3, ZB_SRC_DICT = 4 };
+struct ZbTabSrc { u32 kind; u32 sym; const u8* p; u32 n; };
+
+__device__ __forceinline__ u32 zb_warp_incl_scan(u32 v, u32 lane)
+{
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (u32)d) v += y; }
+    return v;
+}
+
+// --- Huffman weights (HUF_readStats_body).  Weights go to ws as nibbles; the weight-FSE table
+// --- (<= 64 cells, u16: sym | nb << 4 | next << 8) sits in ws + 128.
+// returns header bytes consumed (0 = error); out: log, rank[] (count of every weight)
+__device__ static u32 zb_huf_weights(u8* ws, const u8* s, u32 n, u32& out_log, u32& out_nsym, u32* rank)
+{
+    u8* const wn = ws;                       // 128 bytes: 256 nibbles
+    u16* const wt = (u16*)(ws + 128);        // 64 cells
+    u32 nsym, hdr;
+    if (n == 0) return 0;
+    #pragma unroll
+    for (int i = 0; i < 13; i++) rank[i] = 0;
+    for (int i = 0; i < 32; i++) ((u32*)wn)[i] = 0;
+    u32 total = 0;
+    auto put = [&](u32 i, u32 w) { wn[i >> 1] |= (u8)(w << ((i & 1) * 4)); };
+    if (s[0] >= 128) {
+        nsym = (u32)s[0] - 127; hdr = (nsym + 1) / 2;
+        if (hdr + 1 > n) return 0;
+        for (u32 i = 0; i < nsym; i++) {
+            u32 b = s[1 + i / 2], w = (i & 1) ? (b & 15) : (b >> 4);
+            if (w > 12) return 0;
+            put(i, w); rank[w]++; total += (1u << w) >> 1;
+        }
+    } else {
+        hdr = s[0];
+        if (hdr + 1 > n) return 0;
+        // normalized counts of the weight alphabet: only symbols 0..15 can carry a count here
+        short norm[16]; u32 max_sym = 255, log;
+        {
+            short nn[256];
+            u32 used = zb_read_ncount(nn, max_sym, log, s + 1, hdr);
+            if (used == 0 || log > 6) return 0;
+            for (u32 i = 16; i <= max_sym; i++) if (nn[i]) return 0;   // a weight > 15 could never be valid
+            if (max_sym > 15) max_sym = 15;
+            for (u32 i = 0; i <= max_sym; i++) norm[i] = nn[i];
+            // spread (FSE_buildDTable_internal, zstd/zstd.c:3680)
+            u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+            u32 high = size - 1, pos = 0;
+            u8 next[16];
+            for (u32 sy = 0; sy <= max_sym; sy++) {
+                if (norm[sy] == -1) { wt[high--] = (u16)sy; next[sy] = 1; } else next[sy] = (u8)norm[sy];
+            }
+            for (u32 sy = 0; sy <= max_sym; sy++) {
+                int const c = norm[sy];
+                for (int i = 0; i < c; i++) { wt[pos] = (u16)sy; do pos = (pos + step) & mask; while (pos > high); }
+            }
+            for (u32 u = 0; u < size; u++) {
+                u32 const sy = wt[u], x = next[sy]++;
+                u32 const nb = log - (u32)zb_hibit(x);
+                wt[u] = (u16)(sy | (nb << 4) | (((x << nb) - size) << 8));
+            }
+            ZbBitR b;
+            if (!b.init(s + 1 + used, hdr - used)) return 0;
+            u32 s1 = b.read(log), s2 = b.read(log); b.refill();
+            if (b.left < 0) return 0;
+            nsym = 0;
+            for (;;) {     // two interleaved states (FSE_decompress_usingDTable_generic, zstd/zstd.c:3840-3856)
+                if (nsym + 2 > 255) return 0;
+                { u32 c = wt[s1], w = c & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++;
+                  s1 = (c >> 8) + b.read((c >> 4) & 15); b.refill(); }
+                if (b.left < 0) { u32 w = wt[s2] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
+                if (nsym + 2 > 255) return 0;
+                { u32 c = wt[s2], w = c & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++;
+                  s2 = (c >> 8) + b.read((c >> 4) & 15); b.refill(); }
+                if (b.left < 0) { u32 w = wt[s1] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
+            }
+        }
+    }
+    if (total == 0) return 0;
+    u32 const log = (u32)zb_hibit(total) + 1;
+    if (log > 12) return 0;
+    u32 const rest = (1u << log) - total, hb = (u32)zb_hibit(rest);
+    if ((1u << hb) != rest) return 0;
+    put(nsym, hb + 1); rank[hb + 1]++; nsym++;
+    if (rank[1] < 2 || (rank[1] & 1)) return 0;
+    out_log = log; out_nsym = nsym;
+    return hdr + 1;
+}
+
+// fill the decode cells (u16: symbol | nbBits << 8) from the nibble weights (HUF_readDTableX1_wksp layout)
+__device__ static void zb_huf_fill(u16* cells, const u8* ws, u32 log, u32 nsym, const u32* rank)
+{
+    u32 start[13]; { u32 p = 0; for (u32 wt = 1; wt <= 12; wt++) { start[wt] = p; p += wt <= log ? (rank[wt] << (wt - 1)) : 0; } }
+    for (u32 i = 0; i < nsym; i++) {
+        u32 const wt = (ws[i >> 1] >> ((i & 1) * 4)) & 15; if (!wt) continue;
+        u32 const len = 1u << (wt - 1), p = start[wt]; start[wt] = p + len;
+        u32 const cell = i | ((log + 1 - wt) << 8);
+        if (len >= 4) { u64 const v = cell * 0x0001000100010001ull; u64* q = (u64*)(cells + p); for (u32 k = 0; k < len / 4; k++) q[k] = v; }
+        else if (len == 2) *(u32*)(cells + p) = cell * 0x00010001u;
+        else cells[p] = (u16)cell;
+    }
+}
+
+// one Huffman stream -> n_out bytes at out (global scratch), 4 symbols per 32-bit store where aligned
+__device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, const u16* cells, u32 log)
+{
+    ZbBitR b;
+    if (!b.init(s, n)) return false;
+    u32 i = 0;
+    while (i < n_out && ((uintptr_t)(out + i) & 3)) { u32 c = cells[b.peek(log)]; out[i++] = (u8)c; b.skip(c >> 8); b.refill(); }
+    for (; i + 4 <= n_out; i += 4) {
+        u32 c0 = cells[b.peek(log)]; b.skip(c0 >> 8);
+        u32 c1 = cells[b.peek(log)]; b.skip(c1 >> 8); b.refill();
+        u32 c2 = cells[b.peek(log)]; b.skip(c2 >> 8);
+        u32 c3 = cells[b.peek(log)]; b.skip(c3 >> 8); b.refill();
+        *(u32*)(out + i) = (c0 & 255) | ((c1 & 255) << 8) | ((c2 & 255) << 16) | (c3 << 24);
+    }
+    for (; i < n_out; i++) { u32 c = cells[b.peek(log)]; out[i] = (u8)c; b.skip(c >> 8); b.refill(); }
+    return b.left == 0;
+}
+
+// all literal streams of a block
+__device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, bool single, const u16* cells, u32 log)
+{
+    if (single) return zb_huf_stream2(dstl, regen, p, left, cells, log);
+    if (left < 10) return false;
+    u32 const l1 = zb_rd16(p), l2 = zb_rd16(p + 2), l3 = zb_rd16(p + 4), seg = (regen + 3) / 4;
+    if (6 + l1 + l2 + l3 > left || seg * 3 > regen) return false;
+    u32 const l4 = left - 6 - l1 - l2 - l3;
+    return zb_huf_stream2(dstl, seg, p + 6, l1, cells, log)
+        && zb_huf_stream2(dstl + seg, seg, p + 6 + l1, l2, cells, log)
+        && zb_huf_stream2(dstl + 2 * seg, seg, p + 6 + l1 + l2, l3, cells, log)
+        && zb_huf_stream2(dstl + 3 * seg, regen - 3 * seg, p + 6 + l1 + l2 + l3, l4, cells, log);
+}
+
+// tANS table build into shared memory from normalized counts held in the lane workspace.
+// `norm` is consumed: it is turned into the per-symbol "next state" counters in place.
+__device__ static void zb_build_fse_smem(ZbFseCell* t, short* norm, u32 max_sym, u32 log, int kind)
+{
+    u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    u32 high = size - 1;
+    for (u32 s = 0; s <= max_sym; s++) if (norm[s] == -1) { t[high--].base = s; norm[s] = 0x4001; }
+    u32 pos = 0;
+    for (u32 s = 0; s <= max_sym; s++) {
+        int const c = norm[s];
+        if (c & 0x4000) { norm[s] = 1; continue; }
+        for (int i = 0; i < c; i++) { t[pos].base = s; do pos = (pos + step) & mask; while (pos > high); }
+    }
+    for (u32 u = 0; u < size; u++) {
+        u32 const s = t[u].base, x = (u32)(u16)norm[s]; norm[s] = (short)(x + 1);
+        ZbFseCell c; c.nb = (u8)(log - (u32)zb_hibit(x)); c.next = (u16)((x << c.nb) - size);
+        zb_cell_payload(c, s, kind);
+        t[u] = c;
+    }
+}
+
+// Resolve one sequence-table descriptor for this block.  For ZB_SRC_NCOUNT the normalized counts
+// are parsed into `norm` (lane workspace) and the table log returned; bytes of smem needed -> need.
+// returns consumed header bytes, or -1
+__device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 max_log, const u8* ip, u32 avail,
+                                  bool repeat_ok, short* norm, u32& log, u32& max_sym, u32& need)
+{
+    int used = 0;
+    if (mode == 0) { d.kind = ZB_SRC_PREDEF; }
+    else if (mode == 1) { if (avail == 0 || ip[0] > max_sym_kind) return -1; d.kind = ZB_SRC_RLE; d.sym = ip[0]; used = 1; }
+    else if (mode == 2) { d.kind = ZB_SRC_NCOUNT; d.p = ip; d.n = avail; }
+    else if (!repeat_ok || d.kind == ZB_SRC_NONE) return -1;
+    need = 0; log = 0; max_sym = max_sym_kind;
+    if (d.kind == ZB_SRC_NCOUNT) {
+        u32 const u = zb_read_ncount(norm, max_sym, log, d.p, d.n);
+        if (u == 0 || log > max_log) return -1;
+        if (mode == 2) { used = (int)u; d.n = u; }
+        need = 8u << log;
+    } else if (d.kind == ZB_SRC_RLE) need = 8;
+    return used;
+}
+
+__global__ void __launch_bounds__(ZB_ENT_WARPS * 32)
+zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
+                  const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
+                  ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
+                  u32* __restrict__ work_counter, ZbDictDev dict, u32* status, u64* __restrict__ out_sizes)
+{
+    extern __shared__ __align__(16) u8 zb_smem[];
+    u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u8* const pool = zb_smem + warp * ZB_ENT_POOL_BYTES;
+    u8* const ws = pool + lane * ZB_ENT_WS_BYTES;                       // lane workspace
+    u8* const tabs = pool + 32 * ZB_ENT_WS_BYTES;                       // claimable table space
+    u32 const TAB_BYTES = ZB_ENT_POOL_BYTES - 32 * ZB_ENT_WS_BYTES;
+
+    for (;;) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_frames) return;
+        u32 const f = base + lane;
+        bool done = !(f < n_frames) || status[f] != ZB_OK;
+
+        // ---- per-frame lane state
+        const u8* s = src; u64 n = 0; ZbHdr h; ZbFramePlace pl; u32 err = ZB_OK;
+        u64 cap = 0, out_pos = 0, blk_i = 0, seq_i = 0, lit_i = 0, pos = 0; u32 block_max = 0;
+        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        ZbTabSrc dHuf = {ZB_SRC_NONE, 0, nullptr, 0}, dLL = dHuf, dOF = dHuf, dML = dHuf;
+        bool fse_valid = false;
+        if (!done) {
+            s = src + segs[f].offset; n = segs[f].length;
+            zb_skip_skippable(s, n);
+            zb_parse_header(s, n, h);
+            pl = place[f]; cap = pl.dst_cap; blk_i = pl.blk_off; seq_i = pl.seq_off; lit_i = pl.lit_off; pos = h.hdr_size;
+            block_max = h.window < ZB_BLOCK_MAX ? (u32)h.window : ZB_BLOCK_MAX;
+            if (dict.has_entropy) {
+                dHuf.kind = dLL.kind = dOF.kind = dML.kind = ZB_SRC_DICT; fse_valid = true;
+                rep0 = dict.rep[0]; rep1 = dict.rep[1]; rep2 = dict.rep[2];
+            }
+            if (h.dict_id && dict.dict_id && h.dict_id != dict.dict_id) { err = ZB_E_DICT_WRONG; done = true; }
+        }
+        u64 const hist_extra = dict.content_size;
+
+        // ---- one block per lane per round
+        while (__any_sync(0xFFFFFFFFu, !done)) {
+            ZbBlock B; B.kind = 0; B.regen = 0; B.n_seq = 0; B.n_lit = 0; B.lit_kind = 0; B.lit_byte = 0; B.src_pos = 0; B.seq_pos = seq_i; B.out_pos = out_pos;
+            bool comp = false, last = false;
+            u32 bsize = 0; const u8* bs = nullptr; const u8* bend = nullptr; const u8* ip = nullptr;
+            ZbLitHdr L; L.type = 0; L.regen = 0; L.hdr = 0; L.csize = 0; L.single = 0;
+            // -- A: block header
+            if (!done) {
+                do {
+                    if (pos + 3 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const bh = zb_rd24(s + pos); pos += 3;
+                    last = bh & 1; u32 const type = (bh >> 1) & 3; bsize = bh >> 3; B.kind = type;
+                    if (type == 3) { err = ZB_E_CORRUPTION; break; }
+                    if (type == ZB_BLK_RLE) {
+                        if (pos + 1 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                        if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                        B.src_pos = (u64)(s + pos - src); B.regen = bsize; B.lit_byte = s[pos]; pos += 1;
+                    } else if (type == ZB_BLK_RAW) {
+                        if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                        if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                        B.src_pos = (u64)(s + pos - src); B.regen = bsize; pos += bsize;
+                    } else {
+                        if (pos + bsize > n || bsize > block_max) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        bs = s + pos; bend = bs + bsize;
+                        err = zb_parse_lit_header(bs, bsize, L);
+                        if (err) break;
+                        if (L.regen > block_max) { err = ZB_E_CORRUPTION; break; }
+                        B.n_lit = L.regen; comp = true;
+                    }
+                } while (0);
+                if (err) { done = true; comp = false; }
+            }
+            // -- B: literals
+            bool wantH = false; u32 hlog = 0, hns = 0; u32 rank[13]; const u8* hp = nullptr; u32 hleft = 0;
+            if (comp) {
+                do {
+                    if (L.type == 0) {
+                        if (L.hdr + L.regen > bsize) { err = ZB_E_CORRUPTION; break; }
+                        B.lit_kind = ZB_LIT_RAW; B.src_pos = (u64)(bs + L.hdr - src); ip = bs + L.hdr + L.regen;
+                    } else if (L.type == 1) {
+                        if (L.hdr + 1 > bsize) { err = ZB_E_CORRUPTION; break; }
+                        B.lit_kind = ZB_LIT_RLE; B.lit_byte = bs[L.hdr]; ip = bs + L.hdr + 1;
+                    } else {
+                        if (L.type == 3 && dHuf.kind == ZB_SRC_NONE) { err = ZB_E_DICT_CORRUPTED; break; }
+                        if (!L.single && L.regen < 6) { err = ZB_E_LITERALS_HEADER_WRONG; break; }
+                        if (L.csize + L.hdr > bsize || L.regen == 0) { err = ZB_E_CORRUPTION; break; }
+                        hp = bs + L.hdr; hleft = L.csize;
+                        if (L.type == 2) { dHuf.kind = ZB_SRC_NCOUNT; dHuf.p = hp; dHuf.n = hleft; }
+                        if (dHuf.kind == ZB_SRC_NCOUNT) {
+                            u32 const used = zb_huf_weights(ws, dHuf.p, dHuf.n, hlog, hns, rank);
+                            if (used == 0 || (L.type == 2 && used >= hleft)) { err = ZB_E_CORRUPTION; break; }
+                            if (L.type == 2) { hp += used; hleft -= used; dHuf.n = used; }
+                            wantH = true;
+                        }
+                        B.lit_kind = ZB_LIT_SCRATCH; B.src_pos = lit_i; ip = bs + L.hdr + L.csize;
+                    }
+                } while (0);
+                if (err) { done = true; comp = false; wantH = false; }
+            }
+            // dictionary Huffman table: read in place from the digest (shared by every lane, cache resident)
+            if (comp && B.lit_kind == ZB_LIT_SCRATCH && dHuf.kind == ZB_SRC_DICT) {
+                if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, dict.huf, dict.huf_log)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+            }
+            {   // claim pool space for the Huffman cells, decode; lanes that do not fit wait for the next pass
+                bool pending = wantH;
+                while (__any_sync(0xFFFFFFFFu, pending)) {
+                    u32 const need = pending ? (2u << hlog) : 0;
+                    u32 const incl = zb_warp_incl_scan((need + 15) & ~15u, lane);
+                    if (pending && incl <= TAB_BYTES) {
+                        u16* cells = (u16*)(tabs + incl - ((need + 15) & ~15u));
+                        zb_huf_fill(cells, ws, hlog, hns, rank);
+                        if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, cells, hlog)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+                        pending = false;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (comp && B.lit_kind == ZB_LIT_SCRATCH) lit_i += (L.regen + 15) & ~15u;
+            // -- C: sequences section header
+            u32 nseq = 0, logLL = 0, logOF = 0, logML = 0, msLL = 0, msOF = 0, msML = 0, needS = 0;
+            short* const normLL = (short*)ws; short* const normOF = normLL + 36; short* const normML = normOF + 32;
+            if (comp) {
+                do {
+                    if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    nseq = *ip++;
+                    if (nseq > 0x7F) {
+                        if (nseq == 0xFF) { if (ip + 2 > bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
+                        else { if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
+                    }
+                    B.n_seq = nseq;
+                    if (nseq == 0) { if (ip != bend) err = ZB_E_CORRUPTION; break; }
+                    if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const modes = *ip++;
+                    if (modes & 3) { err = ZB_E_CORRUPTION; break; }
+                    u32 nd; int r;
+                    r = zb_seq_desc(dLL, modes >> 6, 35, 9, ip, (u32)(bend - ip), fse_valid, normLL, logLL, msLL, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    r = zb_seq_desc(dOF, (modes >> 4) & 3, 31, 8, ip, (u32)(bend - ip), fse_valid, normOF, logOF, msOF, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    r = zb_seq_desc(dML, (modes >> 2) & 3, 52, 9, ip, (u32)(bend - ip), fse_valid, normML, logML, msML, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    fse_valid = true;
+                } while (0);
+                if (err) { done = true; comp = false; nseq = 0; }
+            }
+            // -- D: build the three tables in the pool and run the sequence stream
+            u32 lit_used = 0, produced = 0;
+            {
+                bool pending = comp && nseq > 0;
+                while (__any_sync(0xFFFFFFFFu, pending)) {
+                    u32 const need = pending ? ((needS + 15) & ~15u) : 0;
+                    u32 const incl = zb_warp_incl_scan(need, lane);
+                    if (pending && incl <= TAB_BYTES) {
+                        u8* q = tabs + incl - need;
+                        ZbTab tLL, tOF, tML;
+                        // LL
+                        if (dLL.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normLL, msLL, logLL, K_LL); tLL.t = (ZbFseCell*)q; tLL.log = logLL; q += 8u << logLL; }
+                        else if (dLL.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dLL.sym, K_LL); *(ZbFseCell*)q = c; tLL.t = (ZbFseCell*)q; tLL.log = 0; q += 8; }
+                        else if (dLL.kind == ZB_SRC_DICT) { tLL.t = dict.ll; tLL.log = dict.ll_log; }
+                        else { tLL.t = g_defLL; tLL.log = 6; }
+                        // OF
+                        if (dOF.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normOF, msOF, logOF, K_OF); tOF.t = (ZbFseCell*)q; tOF.log = logOF; q += 8u << logOF; }
+                        else if (dOF.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dOF.sym, K_OF); *(ZbFseCell*)q = c; tOF.t = (ZbFseCell*)q; tOF.log = 0; q += 8; }
+                        else if (dOF.kind == ZB_SRC_DICT) { tOF.t = dict.of; tOF.log = dict.of_log; }
+                        else { tOF.t = g_defOF; tOF.log = 5; }
+                        // ML
+                        if (dML.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normML, msML, logML, K_ML); tML.t = (ZbFseCell*)q; tML.log = logML; q += 8u << logML; }
+                        else if (dML.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dML.sym, K_ML); *(ZbFseCell*)q = c; tML.t = (ZbFseCell*)q; tML.log = 0; q += 8; }
+                        else if (dML.kind == ZB_SRC_DICT) { tML.t = dict.ml; tML.log = dict.ml_log; }
+                        else { tML.t = g_defML; tML.log = 6; }
+
+                        // the 3-state FSE sequence stream (restates ZSTD_decodeSequence, zstd/zstd.c:46862-46986)
+                        ZbBitR b;
+                        if (!b.init(ip, (u32)(bend - ip))) err = ZB_E_CORRUPTION;
+                        else {
+                            u32 sLL = b.read(tLL.log); u32 sOF = b.read(tOF.log); b.refill(); u32 sML = b.read(tML.log); b.refill();
+                            const ZbFseCell* const TL = tLL.t; const ZbFseCell* const TO = tOF.t; const ZbFseCell* const TM = tML.t;
+                            u64 const room = cap - out_pos;
+                            ZbSeq* const sq = seqs + seq_i;
+                            for (u32 i = 0; i < nseq; i++) {
+                                ZbFseCell const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
+                                u32 ll = cl.base, ml = cm.base, off;
+                                if (co.add_bits > 1) {
+                                    off = co.base + b.read(co.add_bits);
+                                    rep2 = rep1; rep1 = rep0; rep0 = off;
+                                } else {
+                                    u32 const ll0 = (cl.base == 0);
+                                    if (co.add_bits == 0) {
+                                        if (ll0) { off = rep1; rep1 = rep0; rep0 = off; } else off = rep0;
+                                    } else {
+                                        u32 const idx = co.base + ll0 + b.read(1);
+                                        u32 tmp = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
+                                        if (tmp == 0) tmp = 0xFFFFFFFFu;
+                                        if (idx != 1) rep2 = rep1;
+                                        rep1 = rep0; rep0 = off = tmp;
+                                    }
+                                }
+                                b.refill();
+                                ml += b.read(cm.add_bits);
+                                ll += b.read(cl.add_bits);
+                                b.refill();
+                                if (i + 1 < nseq) {
+                                    sLL = cl.next + b.read(cl.nb);
+                                    sML = cm.next + b.read(cm.nb);
+                                    sOF = co.next + b.read(co.nb);
+                                    b.refill();
+                                }
+                                sq[i] = make_uint4(lit_used, produced, ml, off);
+                                // the checks of ZSTD_execSequence / ZSTD_execSequenceEnd (zstd/zstd.c:46540-46728)
+                                if ((u64)produced + ll + ml > room) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                                if (ll > L.regen - lit_used) { err = ZB_E_CORRUPTION; break; }
+                                lit_used += ll; produced += ll;
+                                if ((u64)off > out_pos + produced + hist_extra) { err = ZB_E_CORRUPTION; break; }
+                                produced += ml;
+                            }
+                            if (!err && b.left != 0) err = ZB_E_CORRUPTION;
+                        }
+                        if (err) { done = true; comp = false; }
+                        pending = false;
+                    }
+                    __syncwarp();
+                }
+            }
+            // -- E: close the block
+            if (!done) {
+                if (comp) {
+                    seqs[seq_i + nseq] = make_uint4(lit_used, produced, 0, 0);
+                    seq_i += nseq + 1;
+                    u32 const tail = L.regen - lit_used;
+                    if ((u64)produced + tail > cap - out_pos) err = ZB_E_DSTSIZE_TOO_SMALL;
+                    B.regen = produced + tail;
+                    if (!err && B.regen > block_max) err = ZB_E_CORRUPTION;
+                    pos += bsize;
+                }
+                if (!err) {
+                    blocks[blk_i++] = B;
+                    out_pos += B.regen;
+                    if (last) {
+                        if (h.content_size != ZB_CONTENT_UNKNOWN && out_pos != h.content_size) err = ZB_E_CORRUPTION;
+                        else if (h.checksum && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
+                        else if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;   // c-ext/decompressor.c:1151-1162
+                        done = true;
+                    }
+                }
+                if (err) done = true;
+            }
+        }
+        if (f < n_frames && status[f] == ZB_OK) {
+            if (err) { status[f] = err; out_sizes[f] = 0; } else out_sizes[f] = out_pos;
+        } else if (f < n_frames) out_sizes[f] = 0;
+    }
+}
