@@ -93,6 +93,23 @@ int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const s
                                 const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags,
                                 zb200_result** out);
 
+/* ---- batch compression.
+ * src_base + segs[i].offset .. +length is the i-th input (DataSource, c-ext/compressor.c:805-808).
+ * Every input becomes one zstd frame (RFC 8878) of independent <=128 KiB blocks. */
+typedef struct {
+    int32_t  level;               /* accepted for API parity; the GPU parse is one strategy (level-3 class) */
+    uint32_t write_checksum;      /* append XXH64 content checksum  (ZSTD_c_checksumFlag)    */
+    uint32_t write_content_size;  /* frame content size in header   (ZSTD_c_contentSizeFlag) */
+    uint32_t dict_id;             /* dictionary id to record, 0 = none (ZSTD_c_dictIDFlag)   */
+} zb200_cparams;
+int zb200_compress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                         const zb200_cparams* params, uint32_t flags, zb200_result** out);
+/* same, from an array of independent host buffers (list input, c-ext/compressor.c:1434-1466) */
+int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
+                              const zb200_cparams* params, uint32_t flags, zb200_result** out);
+/* ZSTD_compressBound (zstd/zstd.c:4547) */
+uint64_t zb200_compress_bound(uint64_t src_size);
+
 /* ---- result accessors */
 const void*          zb200_result_data(const zb200_result* r);       /* host (pinned) or device pointer */
 uint64_t             zb200_result_size(const zb200_result* r);       /* bytes in data */
@@ -113,6 +130,9 @@ int zb200_frame_info(const void* src, size_t size, zb200_frame_info_t* out);
 #define ZB200_K_ENTROPY  2
 #define ZB200_K_EXECUTE  3
 #define ZB200_K_FINISH   4
+#define ZB200_K_COMPRESS 5
+#define ZB200_K_LAYOUT   6
+#define ZB200_K_FRAMES   7
 #define ZB200_K_COUNT    16
 void zb200_profile_enable(zb200_ctx* ctx, int on);
 void zb200_profile_reset(zb200_ctx* ctx);

@@ -16,10 +16,11 @@ from .buffers import (BufferSegment, BufferSegments, BufferWithSegments,  # noqa
 from .dictionary import (ZstdCompressionDict, DICT_TYPE_AUTO, DICT_TYPE_RAWCONTENT,  # noqa: F401
                          DICT_TYPE_FULLDICT)
 from .decompressor import ZstdDecompressor, FORMAT_ZSTD1, FORMAT_ZSTD1_MAGICLESS  # noqa: F401
+from .compressor import ZstdCompressor, ZstdCompressionParameters  # noqa: F401
 
 __version__ = "0.25.0+b200"
 backend = "b200"
-backend_features = {"buffer_types", "multi_decompress_to_buffer"}
+backend_features = {"buffer_types", "multi_compress_to_buffer", "multi_decompress_to_buffer"}
 
 ZSTD_VERSION = (1, 5, 7)
 FRAME_HEADER = b"\x28\xb5\x2f\xfd"

@@ -1,0 +1,199 @@
+"""ZstdCompressor -- the compression half of the reference API that sits on the batch path.
+
+Mirrors c-ext/compressor.c: constructor :88-261 (same keyword arguments, defaults and error
+texts), compress() :509-574 and multi_compress_to_buffer() :1341-1504.  The frames come from the
+CUDA block compressor in libzb200 (zb_encode.cu); they are RFC 8878 zstd and decode with any zstd
+decoder, but they are not byte-identical to CPU zstd's -- the parse is this project's own.
+Dictionary *compression* (config 4) is not implemented yet: a dict_data argument raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .buffers import BufferWithSegments, BufferWithSegmentsCollection
+from .decompressor import _devices
+from .dictionary import ZstdCompressionDict
+from .errors import ZstdError
+
+MAX_COMPRESSION_LEVEL = 22
+
+
+class CParams(C.Structure):
+    _fields_ = [("level", C.c_int32), ("write_checksum", C.c_uint32), ("write_content_size", C.c_uint32),
+                ("dict_id", C.c_uint32)]
+
+
+class ZstdCompressionParameters:
+    """The subset of c-ext/compressionparams.c that reaches this backend: level and the three
+    frame flags.  Strategy/window/LDM knobs are accepted only at their defaults (0)."""
+
+    _FIELDS = ("format", "compression_level", "window_log", "hash_log", "chain_log", "search_log", "min_match",
+               "target_length", "strategy", "write_content_size", "write_checksum", "write_dict_id", "job_size",
+               "overlap_log", "force_max_window", "enable_ldm", "ldm_hash_log", "ldm_min_match",
+               "ldm_bucket_size_log", "ldm_hash_rate_log", "threads")
+
+    def __init__(self, **kw):
+        for k in kw:
+            if k not in self._FIELDS:
+                raise TypeError("'%s' is an invalid keyword argument" % k)
+        self.format = kw.get("format", 0)
+        self.compression_level = kw.get("compression_level", 0)
+        self.write_content_size = kw.get("write_content_size", 1)
+        self.write_checksum = kw.get("write_checksum", 0)
+        self.write_dict_id = kw.get("write_dict_id", 0)
+        self.threads = kw.get("threads", 0)
+        for k in ("window_log", "hash_log", "chain_log", "search_log", "min_match", "target_length", "strategy",
+                  "job_size", "overlap_log", "force_max_window", "enable_ldm", "ldm_hash_log", "ldm_min_match",
+                  "ldm_bucket_size_log", "ldm_hash_rate_log"):
+            v = kw.get(k, 0)
+            if v not in (0, -1, None):
+                raise ZstdError("compression parameter %s is not supported by the B200 backend" % k)
+            setattr(self, k, 0)
+
+    @classmethod
+    def from_level(cls, level, source_size=0, dict_size=0, **kwargs):
+        return cls(compression_level=level, **kwargs)
+
+
+class ZstdCompressor:
+    def __init__(self, level=3, dict_data=None, compression_params=None, write_checksum=None,
+                 write_content_size=None, write_dict_id=None, threads=0):
+        if level > MAX_COMPRESSION_LEVEL:
+            raise ValueError("level must be less than %d" % (MAX_COMPRESSION_LEVEL + 1))
+        if dict_data is not None and not isinstance(dict_data, ZstdCompressionDict):
+            raise TypeError("dict_data must be zstd.ZstdCompressionDict")
+        if compression_params is not None and not isinstance(compression_params, ZstdCompressionParameters):
+            raise TypeError("compression_params must be zstd.ZstdCompressionParameters")
+        if compression_params is not None:
+            if write_checksum is not None:
+                raise ValueError("cannot define compression_params and write_checksum")
+            if write_content_size is not None:
+                raise ValueError("cannot define compression_params and write_content_size")
+            if write_dict_id is not None:
+                raise ValueError("cannot define compression_params and write_dict_id")
+            if threads:
+                raise ValueError("cannot define compression_params and threads")
+            self._level = compression_params.compression_level or 3
+            self._checksum = bool(compression_params.write_checksum)
+            self._content_size = bool(compression_params.write_content_size)
+            self._write_dict_id = bool(compression_params.write_dict_id)
+        else:
+            self._level = level
+            # defaults: content size on, checksum off, dict id on (c-ext/compressor.c:213-227)
+            self._checksum = bool(write_checksum) if write_checksum is not None else False
+            self._content_size = bool(write_content_size) if write_content_size is not None else True
+            self._write_dict_id = bool(write_dict_id) if write_dict_id is not None else True
+        if dict_data is not None:
+            raise ZstdError("dictionary compression is not implemented by the B200 backend yet")
+        self._dict_data = dict_data
+        self._threads = threads
+
+    def _params(self):
+        return CParams(self._level, int(self._checksum), int(self._content_size), 0)
+
+    def memory_size(self):
+        return 0
+
+    def frame_progression(self):
+        return (0, 0, 0)
+
+    # ------------------------------------------------------------------ one-shot
+    def compress(self, data):
+        view = memoryview(data)
+        buf = np.frombuffer(view, dtype=np.uint8) if view.nbytes else np.zeros(0, dtype=np.uint8)
+        ctx = _native.Context.get(0)
+        L = ctx.L
+        seg = np.array([[0, len(buf)]], dtype=np.uint64)
+        res = C.c_void_p()
+        p = self._params()
+        with ctx.lock:
+            rc = L.zb200_compress_batch(ctx.h, buf.ctypes.data if len(buf) else None, seg.ctypes.data, 1, C.byref(p), 0,
+                                        C.byref(res))
+        ctx.check(rc, "zb200_compress_batch")
+        try:
+            n = L.zb200_result_size(res)
+            return C.string_at(L.zb200_result_data(res), n)
+        finally:
+            L.zb200_result_free(res)
+
+    # ------------------------------------------------------------------ batch
+    def multi_compress_to_buffer(self, data, threads=0):
+        if isinstance(data, BufferWithSegments):
+            sources = [data]
+        elif isinstance(data, BufferWithSegmentsCollection):
+            sources = data._buffers
+        elif isinstance(data, list):
+            sources = None
+        else:
+            raise TypeError("argument must be list of BufferWithSegments")
+        L = _native.lib()
+        results = []
+        if sources is not None:
+            count = sum(len(b) for b in sources)
+            total = 0
+            for b in sources:
+                segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
+                total += int(segs[:, 1].sum()) if len(segs) else 0
+            if count == 0:
+                raise ValueError("no source elements found")
+            if total == 0:
+                raise ValueError("source elements are empty")
+            for b in sources:
+                if len(b) == 0:
+                    continue
+                segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
+                dat = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
+                results.extend(self._run(dat.ctypes.data, segs, threads, keep=(dat,)))
+            return BufferWithSegmentsCollection(*results)
+        views = []
+        for i, item in enumerate(data):
+            try:
+                v = memoryview(item)
+            except TypeError:
+                raise TypeError("item %d not a bytes like object" % i)
+            if not v.contiguous:
+                raise TypeError("item %d not a bytes like object" % i)
+            views.append(v)
+        if not views:
+            raise ValueError("no source elements found")
+        if sum(v.nbytes for v in views) == 0:
+            raise ValueError("source elements are empty")
+        lengths = np.array([v.nbytes for v in views], dtype=np.uint64)
+        from .decompressor import ZstdDecompressor
+        parts = ZstdDecompressor._split(None, lengths, _devices(threads))
+        p = self._params()
+        for dev, (lo, hi) in enumerate(parts):
+            ctx = _native.Context.get(dev)
+            k = hi - lo
+            arrs = [np.frombuffer(v, dtype=np.uint8) if v.nbytes else np.zeros(0, dtype=np.uint8) for v in views[lo:hi]]
+            ptrs = (C.c_void_p * k)(*[a.ctypes.data if len(a) else None for a in arrs])
+            lens = (C.c_size_t * k)(*[len(a) for a in arrs])
+            res = C.c_void_p()
+            with ctx.lock:
+                rc = L.zb200_compress_batch_ptrs(ctx.h, ptrs, lens, k, C.byref(p), 0, C.byref(res))
+            ctx.check(rc, "zb200_compress_batch_ptrs")
+            results.append(BufferWithSegments._from_result(ctx, res))
+        return BufferWithSegmentsCollection(*results)
+
+    def _run(self, base_ptr, segs, threads, keep=()):
+        from .decompressor import ZstdDecompressor
+        L = _native.lib()
+        parts = ZstdDecompressor._split(None, segs[:, 1], _devices(threads))
+        p = self._params()
+        out = []
+        for dev, (lo, hi) in enumerate(parts):
+            ctx = _native.Context.get(dev)
+            sub = np.ascontiguousarray(segs[lo:hi])
+            res = C.c_void_p()
+            with ctx.lock:
+                rc = L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, hi - lo, C.byref(p), 0, C.byref(res))
+            ctx.check(rc, "zb200_compress_batch")
+            out.append(BufferWithSegments._from_result(ctx, res))
+        return out
+
+    # ------------------------------------------------------------------ out of scope
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("streaming compression objects are outside the B200 batch path")
+
+    stream_reader = stream_writer = compressobj = read_to_iter = copy_stream = chunker = _unsupported

@@ -27,6 +27,14 @@ void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* stat
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,
                       u32* first_error, cudaStream_t st);
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
+size_t zb_encode_scratch_bytes();
+void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
+                               void* outs, u32* work_counter, cudaStream_t st);
+void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
+                            u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
+void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
+                            u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, const ZbSegment* out_segs, u8* dst, cudaStream_t st);
+u32 zb_encode_smem_bytes();
 }
 
 namespace {
@@ -57,6 +65,7 @@ struct zb200_ctx {
     int sm_count = 148;
     // device arenas (grow-only)
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
+    DevBuf jobs, seginfo, slots, bouts, escratch, fsizes;
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -167,7 +176,8 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
-                     &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial};
+                     &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial,
+                     &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes};
     for (auto* b : all) b->release();
     for (auto& b : ctx->pinned) cudaFreeHost(b.p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -300,7 +310,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
 
     // persistent entropy grid: one CTA per SM (its shared memory holds the decode tables), fewer if the batch is small
     u32 ctas = (u32)ctx->sm_count;
-    u32 need_ctas = (nf + 127) / 128;
+    u32 need_ctas = (nf + 255) / 256;
     if (ctas > need_ctas) ctas = need_ctas;
     CK(ctx->blocks.ensure((totals[1] + 1) * sizeof(ZbBlock)));
     CK(ctx->seqs.ensure((totals[2] + 1) * sizeof(ZbSeq)));
@@ -403,6 +413,123 @@ int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const s
     return rc;
 }
 
+
+// ---------------------------------------------------------------- batch compression
+namespace {
+struct HostJob { u64 src_pos; u32 size, seg, last, first; };
+struct HostSegInfo { u64 first_job; u32 n_jobs, pad; };
+}
+
+static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                           const zb200_cparams* params, uint32_t flags, zb200_result** out)
+{
+    *out = nullptr;
+    if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_compress_batch: bad arguments", cudaSuccess);
+    cudaSetDevice(ctx->device);
+    zb200_cparams P; if (params) P = *params; else { P.level = 3; P.write_checksum = 0; P.write_content_size = 1; P.dict_id = 0; }
+    std::vector<zb200_segment> hsegs;
+    const u8* d_src; const ZbSegment* d_segs;
+    if (flags & ZB200_SRC_DEVICE) {
+        hsegs.resize(n);
+        CK(cudaMemcpyAsync(hsegs.data(), segs, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        d_src = (const u8*)src_base; d_segs = (const ZbSegment*)segs;
+    } else {
+        hsegs.assign(segs, segs + n);
+        u64 lo = ~0ull, hi = 0;
+        for (size_t i = 0; i < n; i++) { if (segs[i].offset < lo) lo = segs[i].offset; if (segs[i].offset + segs[i].length > hi) hi = segs[i].offset + segs[i].length; }
+        if (hi < lo) { lo = hi = 0; }
+        for (auto& s : hsegs) s.offset -= lo;
+        CK(ctx->src.ensure(hi - lo + 64));
+        CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
+        CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->segs.p, hsegs.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
+    }
+    // block jobs: every <=128 KiB slice of every segment (ZSTD_compress_frameChunk's block loop, zstd/zstd.c:27545)
+    std::vector<HostJob> jobs; std::vector<HostSegInfo> sinfo(n);
+    jobs.reserve(n);
+    u32 max_block = 0;
+    for (size_t i = 0; i < n; i++) {
+        u64 const len = hsegs[i].length; u64 pos = 0;
+        sinfo[i].first_job = jobs.size(); sinfo[i].n_jobs = 0; sinfo[i].pad = 0;
+        while (pos < len) {
+            u32 const sz = (u32)(len - pos < ZB_BLOCK_MAX ? len - pos : ZB_BLOCK_MAX);
+            HostJob j; j.src_pos = hsegs[i].offset + pos; j.size = sz; j.seg = (u32)i; j.first = pos == 0; j.last = pos + sz == len;
+            jobs.push_back(j); sinfo[i].n_jobs++; pos += sz;
+            if (sz > max_block) max_block = sz;
+        }
+    }
+    size_t const nj = jobs.size();
+    u64 const slot_bytes = ((u64)max_block + (max_block >> 7) + 64 + 15) & ~15ull;
+    u32 ctas = (u32)ctx->sm_count * (227u * 1024u / zb_encode_smem_bytes());
+    if (ctas > nj) ctas = (u32)nj;
+    if (ctas == 0) ctas = 1;
+    CK(ctx->jobs.ensure((nj + 1) * sizeof(HostJob)));
+    CK(ctx->seginfo.ensure(n * sizeof(HostSegInfo)));
+    CK(ctx->slots.ensure((nj + 1) * slot_bytes));
+    CK(ctx->bouts.ensure((nj + 1) * 8));
+    CK(ctx->escratch.ensure((size_t)ctas * zb_encode_scratch_bytes()));
+    CK(ctx->fsizes.ensure(n * sizeof(u64)));
+    CK(ctx->out_segs.ensure(n * sizeof(ZbSegment)));
+    CK(ctx->small.ensure(256));
+    u64* d_total = ctx->small.as<u64>();
+    u32* d_counter = (u32*)(d_total + 8);
+    u32 zero = 0;
+    if (nj) CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(HostJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->seginfo.p, sinfo.data(), n * sizeof(HostSegInfo), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_counter, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+    if (nj) { KSpan s(ctx, ZB200_K_COMPRESS);
+      zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter, ctx->stream); }
+    { KSpan s(ctx, ZB200_K_LAYOUT);
+      zb_launch_frame_layout(d_segs, ctx->seginfo.p, ctx->bouts.p, (u32)n, P.write_checksum ? 1 : 0, P.write_content_size ? 1 : 0, P.dict_id,
+                             ctx->fsizes.as<u64>(), ctx->out_segs.as<ZbSegment>(), d_total, ctx->stream); }
+    u64 total = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->dst.ensure(total + 64));
+    { KSpan s(ctx, ZB200_K_FRAMES);
+      zb_launch_write_frames(d_src, d_segs, ctx->seginfo.p, ctx->bouts.p, ctx->slots.as<u8>(), slot_bytes, (u32)n, P.write_checksum ? 1 : 0,
+                             P.write_content_size ? 1 : 0, P.dict_id, ctx->out_segs.as<ZbSegment>(), ctx->dst.as<u8>(), ctx->stream); }
+    zb200_result* res = new zb200_result(); res->ctx = ctx; res->n = n; res->size = total; res->segs.resize(n);
+    CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & ZB200_DST_DEVICE)) {
+        res->data = pinned_get(ctx, total ? total : 1);
+        if (!res->data) { delete res; return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation); }
+        res->data_pinned_pool = true;
+        CK(cudaMemcpyAsync(res->data, ctx->dst.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    } else { res->data = ctx->dst.p; res->data_on_device = true; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prof) fold_spans(ctx);
+    ctx->last_scratch = (u64)ctas * zb_encode_scratch_bytes() + nj * slot_bytes;
+    *out = res;
+    return 0;
+}
+
+int zb200_compress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                         const zb200_cparams* params, uint32_t flags, zb200_result** out)
+{
+    return compress_common(ctx, src_base, segs, n, params, flags, out);
+}
+
+int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
+                              const zb200_cparams* params, uint32_t flags, zb200_result** out)
+{
+    *out = nullptr;
+    if (!ctx || !srcs || !sizes || n == 0) return fail(ctx, "zb200_compress_batch_ptrs: bad arguments", cudaSuccess);
+    cudaSetDevice(ctx->device);
+    u64 total = 0; for (size_t i = 0; i < n; i++) total += sizes[i];
+    u8* stage = (u8*)pinned_get(ctx, total ? total : 1);
+    if (!stage) return fail(ctx, "pinned staging allocation", cudaErrorMemoryAllocation);
+    std::vector<zb200_segment> segs(n); u64 pos = 0;
+    for (size_t i = 0; i < n; i++) { if (sizes[i]) memcpy(stage + pos, srcs[i], sizes[i]); segs[i].offset = pos; segs[i].length = sizes[i]; pos += sizes[i]; }
+    int rc = compress_common(ctx, stage, segs.data(), n, params, flags & ~ZB200_SRC_DEVICE, out);
+    pinned_put(ctx, stage);
+    return rc;
+}
+
+uint64_t zb200_compress_bound(uint64_t n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }
+
 const void* zb200_result_data(const zb200_result* r) { return r->data; }
 uint64_t zb200_result_size(const zb200_result* r) { return r->size; }
 size_t zb200_result_count(const zb200_result* r) { return r->n; }
@@ -457,7 +584,8 @@ int zb200_profile_read(zb200_ctx* ctx, float ms[ZB200_K_COUNT], uint32_t launche
 }
 const char* zb200_kernel_name(int k)
 {
-    static const char* names[ZB200_K_COUNT] = {"zb_scan_frames", "zb_place_frames", "zb_entropy_decode", "zb_execute", "zb_finish"};
+    static const char* names[ZB200_K_COUNT] = {"zb_scan_frames", "zb_place_frames", "zb_entropy_decode", "zb_execute", "zb_finish",
+                                                "zb_compress_blocks", "zb_frame_layout", "zb_write_frames"};
     return (k >= 0 && k < ZB200_K_COUNT && names[k]) ? names[k] : "";
 }
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }

@@ -84,8 +84,15 @@ struct ZbBlock {
 // A sentinel record {.x = literals consumed, .y = output produced} ends every block.
 typedef uint4 ZbSeq;
 
-// FSE decode cell, same information as ZSTD_seqSymbol (zstd/zstd.c:41301-41306)
-struct __align__(8) ZbFseCell { u16 next; u8 nb; u8 add_bits; u32 base; };
+// FSE decode cell, 32 bits: the information of ZSTD_seqSymbol (zstd/zstd.c:41301-41306) minus the
+// baseline, which is looked up from the symbol (off the state chain):
+//   bits 0-9 nextState base, 10-13 nbBits, 14-18 nbAdditionalBits, 19-24 symbol code
+typedef u32 ZbFseCell;
+#define ZB_CELL(next, nb, add, sym) ((u32)(next) | ((u32)(nb) << 10) | ((u32)(add) << 14) | ((u32)(sym) << 19))
+#define ZB_CELL_NEXT(c) ((c) & 1023u)
+#define ZB_CELL_NB(c)   (((c) >> 10) & 15u)
+#define ZB_CELL_ADD(c)  (((c) >> 14) & 31u)
+#define ZB_CELL_SYM(c)  ((c) >> 19)
 
 // digested dictionary, device resident (restates what ZSTD_loadDEntropy keeps, zstd/zstd.c:44673-44757)
 struct ZbDictDev {
@@ -98,18 +105,9 @@ struct ZbDictDev {
 
 // dictionary digest as the device kernel writes it
 struct ZbDictDigest {
-    u16 huf[4096]; ZbFseCell ll[512]; ZbFseCell ml[512]; ZbFseCell of[256]; ZbFseCell wt[64];
+    u16 huf[4096]; ZbFseCell ll[512]; ZbFseCell ml[512]; ZbFseCell of[256];
     u32 huf_log, ll_log, of_log, ml_log; u32 rep[3]; u32 dict_id; u32 content_off; u32 status; u32 has_entropy; u32 pad;
 };
-
-// per-lane scratch layout of the entropy stage
-#define ZB_HUF_CELLS   4096
-#define ZB_LANE_HUF    0                                   // u16[4096]
-#define ZB_LANE_LL     (ZB_HUF_CELLS * 2)                  // ZbFseCell[512]
-#define ZB_LANE_ML     (ZB_LANE_LL + 512 * 8)              // ZbFseCell[512]
-#define ZB_LANE_OF     (ZB_LANE_ML + 512 * 8)              // ZbFseCell[256]
-#define ZB_LANE_WT     (ZB_LANE_OF + 256 * 8)              // ZbFseCell[64]  (Huffman-weight table)
-#define ZB_LANE_BYTES  (ZB_LANE_WT + 64 * 8)               // 18944
 
 __device__ __forceinline__ u32 zb_rd16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
 __device__ __forceinline__ u32 zb_rd24(const u8* p) { return zb_rd16(p) | ((u32)p[2] << 16); }
@@ -118,44 +116,51 @@ __device__ __forceinline__ u64 zb_rd64(const u8* p) { return (u64)zb_rd32(p) | (
 __device__ __forceinline__ int zb_hibit(u32 v) { return 31 - __clz(v); }
 
 // ---------------------------------------------------------------------------
-// Backward bit reader over an arbitrary byte range, built on ALIGNED 32-bit loads.
-// `win` holds the next unread bits at its top; `left` counts unread stream bits and
-// goes negative when the stream is over-read (the reference's BIT_DStream_overflow,
-// zstd/zstd.c:2517-2556).  Reads below the stream start return the neighbouring
-// bytes (not zeros): harmless, because left < 0 then fails the block.
+// Backward bit reader over an arbitrary byte range, built on ALIGNED 32-bit loads and 32-bit
+// funnel shifts.  (hi:lo) holds the next unread bits top-aligned; `avail` counts them.  The two
+// words below the window are loaded ahead (nx0, nx1) so that global-memory latency is off the
+// decode chain.  left() is the number of unread stream bits; it goes negative when the stream is
+// over-read (the reference's BIT_DStream_overflow, zstd/zstd.c:2517-2556).  Reads below the stream
+// start return the neighbouring bytes (not zeros): harmless, because left() < 0 fails the block.
 // ---------------------------------------------------------------------------
 struct ZbBitR {
-    const u32* w; int widx; u64 win; int avail; int left; u32 nx0, nx1;   // nx0/nx1: the next two words, loaded ahead
+    const u32* w; int widx; u32 hi, lo; int avail; u32 nx0, nx1; int skew_bits;
 
     __device__ __forceinline__ bool init(const u8* s, u32 n) {
         if (n == 0) return false;
-        u32 last = s[n - 1];
+        u32 const last = s[n - 1];
         if (last == 0) return false;
-        uintptr_t a = (uintptr_t)s & ~(uintptr_t)3;
+        uintptr_t const a = (uintptr_t)s & ~(uintptr_t)3;
         w = (const u32*)a;
-        int skew = (int)((uintptr_t)s - a);
-        int hb = zb_hibit(last);
-        int P = (skew + (int)n - 1) * 8 + hb;      // bits from the aligned base up to the end mark
-        left = ((int)n - 1) * 8 + hb;
-        nx0 = nx1 = 0;
-        if (P == 0) { win = 0; avail = 0; widx = -1; return true; }
-        int wi = (P - 1) >> 5, k = P - wi * 32;    // k in 1..32 valid bits in the top word
-        win = (u64)w[wi] << (64 - k); avail = k; widx = wi - 1;
+        int const skew = (int)((uintptr_t)s - a);
+        skew_bits = skew * 8;
+        int const P = (skew + (int)n - 1) * 8 + zb_hibit(last);   // bits from the aligned base up to the end mark
+        nx0 = nx1 = 0; lo = 0;
+        if (P == 0) { hi = 0; avail = 0; widx = -1; return true; }
+        int const wi = (P - 1) >> 5, k = P - wi * 32;              // k in 1..32 valid bits in the top word
+        hi = w[wi] << (32 - k); avail = k; widx = wi - 1;
         if (widx >= 0) nx0 = w[widx];
         if (widx >= 1) nx1 = w[widx - 1];
         refill();
         return true;
     }
-    // The word that enters the window was loaded two refills ago, so its (global-memory) latency is
-    // off the decode chain; the load issued here is consumed 64 stream bits later.
+    // branch-free: lanes of a warp refill at different moments, so the body is predicated, not branched
     __device__ __forceinline__ void refill() {
-        if (avail <= 32 && widx >= 0) {
-            win |= (u64)nx0 << (32 - avail); avail += 32; widx--;
-            nx0 = nx1;
-            if (widx >= 1) nx1 = w[widx - 1];
-        }
+        bool const r = (avail <= 32) & (widx >= 0);                // lo is empty when r holds
+        u32 const a = (u32)avail;
+        u32 const add_hi = __funnelshift_rc(nx0, 0u, a);           // nx0 >> avail        (0 when avail == 32)
+        u32 const new_lo = __funnelshift_lc(0u, nx0, 32u - a);     // nx0 << (32 - avail) (0 when avail == 0)
+        hi |= r ? add_hi : 0u;
+        lo = r ? new_lo : lo;
+        avail += r ? 32 : 0;
+        widx -= r ? 1 : 0;
+        nx0 = r ? nx1 : nx0;
+        if (r && widx >= 1) nx1 = w[widx - 1];
     }
-    __device__ __forceinline__ u32 peek(u32 nb) const { return (u32)((win >> 1) >> (63 - nb)); }
-    __device__ __forceinline__ void skip(u32 nb) { win <<= nb; avail -= (int)nb; left -= (int)nb; }
-    __device__ __forceinline__ u32 read(u32 nb) { u32 v = peek(nb); skip(nb); return v; }
+    __device__ __forceinline__ u32 peek(u32 nb) const { return __funnelshift_rc(hi, 0u, 32u - nb); }   // nb in 0..32
+    __device__ __forceinline__ void skip(u32 nb) {                                                      // nb in 0..32
+        hi = __funnelshift_lc(lo, hi, nb); lo = __funnelshift_lc(0u, lo, nb); avail -= (int)nb;
+    }
+    __device__ __forceinline__ u32 read(u32 nb) { u32 const v = peek(nb); skip(nb); return v; }
+    __device__ __forceinline__ int left() const { return avail + 32 * (widx + 1) - skew_bits; }
 };

@@ -333,38 +333,29 @@ __device__ static u32 zb_read_ncount(short* norm, u32& max_sym, u32& table_log, 
     return (r.bp + 7) >> 3;
 }
 
-__device__ __forceinline__ void zb_cell_payload(ZbFseCell& c, u32 sym, int kind)
+// additional-bit count of a symbol code (LL_bits / ML_bits / OF_bits, zstd/zstd.c:15615-15659, :41279)
+__device__ __forceinline__ u32 zb_code_add_bits(u32 sym, int kind)
 {
-    if (kind == K_LL) { c.base = c_LL_base[sym]; c.add_bits = c_LL_bits[sym]; }
-    else if (kind == K_ML) { c.base = c_ML_base[sym]; c.add_bits = c_ML_bits[sym]; }
-    else { c.base = sym < 2 ? sym : (1u << sym) - 3; c.add_bits = (u8)sym; }
+    return kind == K_LL ? c_LL_bits[sym] : (kind == K_ML ? c_ML_bits[sym] : sym);
 }
 
-// tANS decode table (restates ZSTD_buildFSETable_body, zstd/zstd.c:46118-46233), serial per lane.
-// kind < 0: plain symbol table (Huffman weights): base = symbol.
-template <int MAXS>
-__device__ static void zb_build_fse(ZbFseCell* t, const short* norm, u32 max_sym, u32 log, int kind)
+// tANS decode table of 32-bit cells (restates ZSTD_buildFSETable_body, zstd/zstd.c:46118-46233), serial.
+// `norm` (max_sym + 1 shorts) is consumed: it becomes the per-symbol next-state counters in place.
+__device__ static void zb_build_fse(ZbFseCell* t, short* norm, u32 max_sym, u32 log, int kind)
 {
     u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-    u16 next[MAXS];
     u32 high = size - 1;
-    for (u32 s = 0; s <= max_sym; s++) {
-        if (norm[s] == -1) { t[high--].base = s; next[s] = 1; }
-        else next[s] = (u16)norm[s];
-    }
+    for (u32 s = 0; s <= max_sym; s++) if (norm[s] == -1) { t[high--] = s; norm[s] = 0x4001; }
     u32 pos = 0;
     for (u32 s = 0; s <= max_sym; s++) {
         int const c = norm[s];
-        for (int i = 0; i < c; i++) {
-            t[pos].base = s;
-            do pos = (pos + step) & mask; while (pos > high);
-        }
+        if (c & 0x4000) { norm[s] = 1; continue; }
+        for (int i = 0; i < c; i++) { t[pos] = s; do pos = (pos + step) & mask; while (pos > high); }
     }
     for (u32 u = 0; u < size; u++) {
-        u32 const s = t[u].base, x = next[s]++;
-        ZbFseCell c; c.nb = (u8)(log - (u32)zb_hibit(x)); c.next = (u16)((x << c.nb) - size);
-        if (kind >= 0) zb_cell_payload(c, s, kind); else { c.base = s; c.add_bits = 0; }
-        t[u] = c;
+        u32 const s = t[u], x = (u32)(u16)norm[s]; norm[s] = (short)(x + 1);
+        u32 const nb = log - (u32)zb_hibit(x);
+        t[u] = ZB_CELL((x << nb) - size, nb, zb_code_add_bits(s, kind), s);
     }
 }
 
@@ -373,79 +364,12 @@ __global__ void zb_build_default_tables()
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         short norm[64];
         for (int i = 0; i < 36; i++) norm[i] = c_LL_defnorm[i];
-        zb_build_fse<64>(g_defLL, norm, 35, 6, K_LL);
+        zb_build_fse(g_defLL, norm, 35, 6, K_LL);
         for (int i = 0; i < 29; i++) norm[i] = c_OF_defnorm[i];
-        zb_build_fse<64>(g_defOF, norm, 28, 5, K_OF);
+        zb_build_fse(g_defOF, norm, 28, 5, K_OF);
         for (int i = 0; i < 53; i++) norm[i] = c_ML_defnorm[i];
-        zb_build_fse<64>(g_defML, norm, 52, 6, K_ML);
+        zb_build_fse(g_defML, norm, 52, 6, K_ML);
     }
-}
-
-// Huffman table description -> decode cells (restates HUF_readStats_body zstd/zstd.c:3457-3521 and
-// the cell layout of HUF_readDTableX1_wksp :39651-39783).  `fse_tmp` is scratch for the weight table
-// (<= 64 cells).  returns header bytes consumed, 0 on error.
-__device__ static u32 zb_read_huf_table(u16* cells, u32& out_log, const u8* s, u32 n, ZbFseCell* fse_tmp)
-{
-    u8 w[256]; u32 rank[16]; u32 nsym, hdr;
-    if (n == 0) return 0;
-    for (int i = 0; i < 16; i++) rank[i] = 0;
-    if (s[0] >= 128) {
-        nsym = (u32)s[0] - 127; hdr = (nsym + 1) / 2;
-        if (hdr + 1 > n) return 0;
-        for (u32 i = 0; i < nsym; i++) { u32 b = s[1 + i / 2]; w[i] = (i & 1) ? (b & 15) : (b >> 4); }
-    } else {
-        // FSE-compressed weights: two interleaved states (FSE_decompress_usingDTable_generic, zstd/zstd.c:3785-3858)
-        hdr = s[0];
-        if (hdr + 1 > n) return 0;
-        u32 max_sym = 255, log;
-        {
-            short nn[256];
-            u32 used = zb_read_ncount(nn, max_sym, log, s + 1, hdr);
-            if (used == 0 || log > 6) return 0;
-            zb_build_fse<256>(fse_tmp, nn, max_sym, log, -1);
-            ZbBitR b;
-            if (!b.init(s + 1 + used, hdr - used)) return 0;
-            u32 s1 = b.read(log), s2 = b.read(log); b.refill();
-            if (b.left < 0) return 0;
-            nsym = 0;
-            for (;;) {
-                if (nsym + 2 > 255) return 0;
-                { ZbFseCell c = fse_tmp[s1]; w[nsym++] = (u8)c.base; s1 = c.next + b.read(c.nb); b.refill(); }
-                if (b.left < 0) { w[nsym++] = (u8)fse_tmp[s2].base; break; }
-                if (nsym + 2 > 255) return 0;
-                { ZbFseCell c = fse_tmp[s2]; w[nsym++] = (u8)c.base; s2 = c.next + b.read(c.nb); b.refill(); }
-                if (b.left < 0) { w[nsym++] = (u8)fse_tmp[s1].base; break; }
-            }
-        }
-    }
-    u32 total = 0;
-    for (u32 i = 0; i < nsym; i++) {
-        if (w[i] > 12) return 0;
-        rank[w[i]]++; total += (1u << w[i]) >> 1;
-    }
-    if (total == 0) return 0;
-    u32 log = (u32)zb_hibit(total) + 1;
-    if (log > 12) return 0;
-    {
-        u32 rest = (1u << log) - total, hb = (u32)zb_hibit(rest);
-        if ((1u << hb) != rest) return 0;
-        w[nsym] = (u8)(hb + 1); rank[hb + 1]++; nsym++;
-    }
-    if (rank[1] < 2 || (rank[1] & 1)) return 0;
-    // start cell of every weight class
-    u32 start[14]; { u32 p = 0; for (u32 wt = 1; wt <= log; wt++) { start[wt] = p; p += rank[wt] << (wt - 1); } }
-    for (u32 i = 0; i < nsym; i++) {
-        u32 wt = w[i]; if (!wt) continue;
-        u32 len = 1u << (wt - 1), p = start[wt]; start[wt] = p + len;
-        u16 cell = (u16)(i | ((log + 1 - wt) << 8));
-        if (len >= 4) {                                   // cells are 2 bytes: fill 8 bytes at a time
-            u64 v = cell * 0x0001000100010001ull;
-            u64* q = (u64*)(cells + p);                   // p is a multiple of len >= 4 -> 8-byte aligned
-            for (u32 k = 0; k < len / 4; k++) q[k] = v;
-        } else for (u32 k = 0; k < len; k++) cells[p + k] = cell;
-    }
-    out_log = log;
-    return hdr + 1;
 }
 
 struct ZbTab { const ZbFseCell* t; u32 log; };
@@ -740,19 +664,23 @@ __global__ void zb_digest_dict(const u8* __restrict__ dict, u32 n, ZbDictDigest*
     if (n < 8 || zb_rd32(dict) != ZB_MAGIC_DICT) return;            // raw-content dictionary
     out->dict_id = zb_rd32(dict + 4);
     const u8* p = dict + 8; const u8* const end = dict + n;
-    u32 used = zb_read_huf_table(out->huf, out->huf_log, p, (u32)(end - p), out->wt);
-    if (!used) { out->status = ZB_E_DICT_CORRUPTED; return; }
-    p += used;
-    short norm[64]; u32 mx, log;
+    {
+        __align__(16) u8 ws[256]; u32 rank[13], log, nsym;
+        u32 const used = zb_huf_weights(ws, p, (u32)(end - p), log, nsym, rank);
+        if (!used) { out->status = ZB_E_DICT_CORRUPTED; return; }
+        zb_huf_fill(out->huf, ws, log, nsym, rank);
+        out->huf_log = log; p += used;
+    }
+    short norm[64]; u32 mx, log, used;
     mx = 31; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 8) { out->status = ZB_E_DICT_CORRUPTED; return; }
-    zb_build_fse<64>(out->of, norm, mx, log, K_OF); out->of_log = log; p += used;
+    zb_build_fse(out->of, norm, mx, log, K_OF); out->of_log = log; p += used;
     mx = 52; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
-    zb_build_fse<64>(out->ml, norm, mx, log, K_ML); out->ml_log = log; p += used;
+    zb_build_fse(out->ml, norm, mx, log, K_ML); out->ml_log = log; p += used;
     mx = 35; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
-    zb_build_fse<64>(out->ll, norm, mx, log, K_LL); out->ll_log = log; p += used;
+    zb_build_fse(out->ll, norm, mx, log, K_LL); out->ll_log = log; p += used;
     if (p + 12 > end) { out->status = ZB_E_DICT_CORRUPTED; return; }
     u32 const content = (u32)(end - (p + 12));
     for (int i = 0; i < 3; i++) {

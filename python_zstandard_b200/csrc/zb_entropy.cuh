@@ -16,10 +16,11 @@
 // ZSTD_decodeSeqHeaders (:46328), ZSTD_buildFSETable_body (:46118), ZSTD_decodeSequence (:46862).
 #pragma once
 
-#define ZB_ENT_WARPS      4                       // warps per CTA
+#define ZB_ENT_WARPS      8                       // warps per CTA (one CTA per SM)
 #define ZB_ENT_WS_BYTES   256                     // per-lane workspace (weights / normalized counts)
-#define ZB_ENT_POOL_BYTES (55 * 1024)             // per-warp pool, workspace included
-#define ZB_ENT_SMEM       (ZB_ENT_WARPS * ZB_ENT_POOL_BYTES)
+#define ZB_ENT_POOL_BYTES (27 * 1024 + 512)       // per-warp pool, workspace included
+#define ZB_ENT_LUT_BYTES  512                     // CTA-wide baseline tables (LL_base, ML_base)
+#define ZB_ENT_SMEM       (ZB_ENT_WARPS * ZB_ENT_POOL_BYTES + ZB_ENT_LUT_BYTES)
 
 // where a table comes from; enough to rebuild it for a later block
 enum : u32 { ZB_SRC_NONE = 0, ZB_SRC_PREDEF = 1, ZB_SRC_RLE = 2, ZB_SRC_NCOUNT = 3, ZB_SRC_DICT = 4 };
@@ -85,17 +86,17 @@ __device__ static u32 zb_huf_weights(u8* ws, const u8* s, u32 n, u32& out_log, u
             ZbBitR b;
             if (!b.init(s + 1 + used, hdr - used)) return 0;
             u32 s1 = b.read(log), s2 = b.read(log); b.refill();
-            if (b.left < 0) return 0;
+            if (b.left() < 0) return 0;
             nsym = 0;
             for (;;) {     // two interleaved states (FSE_decompress_usingDTable_generic, zstd/zstd.c:3840-3856)
                 if (nsym + 2 > 255) return 0;
                 { u32 c = wt[s1], w = c & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++;
                   s1 = (c >> 8) + b.read((c >> 4) & 15); b.refill(); }
-                if (b.left < 0) { u32 w = wt[s2] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
+                if (b.left() < 0) { u32 w = wt[s2] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
                 if (nsym + 2 > 255) return 0;
                 { u32 c = wt[s2], w = c & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++;
                   s2 = (c >> 8) + b.read((c >> 4) & 15); b.refill(); }
-                if (b.left < 0) { u32 w = wt[s1] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
+                if (b.left() < 0) { u32 w = wt[s1] & 15; if (w > 12) return 0; put(nsym, w); rank[w]++; total += (1u << w) >> 1; nsym++; break; }
             }
         }
     }
@@ -139,7 +140,7 @@ __device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, co
         *(u32*)(out + i) = (c0 & 255) | ((c1 & 255) << 8) | ((c2 & 255) << 16) | (c3 << 24);
     }
     for (; i < n_out; i++) { u32 c = cells[b.peek(log)]; out[i] = (u8)c; b.skip(c >> 8); b.refill(); }
-    return b.left == 0;
+    return b.left() == 0;
 }
 
 // all literal streams of a block
@@ -154,27 +155,6 @@ __device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, 
         && zb_huf_stream2(dstl + seg, seg, p + 6 + l1, l2, cells, log)
         && zb_huf_stream2(dstl + 2 * seg, seg, p + 6 + l1 + l2, l3, cells, log)
         && zb_huf_stream2(dstl + 3 * seg, regen - 3 * seg, p + 6 + l1 + l2 + l3, l4, cells, log);
-}
-
-// tANS table build into shared memory from normalized counts held in the lane workspace.
-// `norm` is consumed: it is turned into the per-symbol "next state" counters in place.
-__device__ static void zb_build_fse_smem(ZbFseCell* t, short* norm, u32 max_sym, u32 log, int kind)
-{
-    u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-    u32 high = size - 1;
-    for (u32 s = 0; s <= max_sym; s++) if (norm[s] == -1) { t[high--].base = s; norm[s] = 0x4001; }
-    u32 pos = 0;
-    for (u32 s = 0; s <= max_sym; s++) {
-        int const c = norm[s];
-        if (c & 0x4000) { norm[s] = 1; continue; }
-        for (int i = 0; i < c; i++) { t[pos].base = s; do pos = (pos + step) & mask; while (pos > high); }
-    }
-    for (u32 u = 0; u < size; u++) {
-        u32 const s = t[u].base, x = (u32)(u16)norm[s]; norm[s] = (short)(x + 1);
-        ZbFseCell c; c.nb = (u8)(log - (u32)zb_hibit(x)); c.next = (u16)((x << c.nb) - size);
-        zb_cell_payload(c, s, kind);
-        t[u] = c;
-    }
 }
 
 // Resolve one sequence-table descriptor for this block.  For ZB_SRC_NCOUNT the normalized counts
@@ -193,8 +173,8 @@ __device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 m
         u32 const u = zb_read_ncount(norm, max_sym, log, d.p, d.n);
         if (u == 0 || log > max_log) return -1;
         if (mode == 2) { used = (int)u; d.n = u; }
-        need = 8u << log;
-    } else if (d.kind == ZB_SRC_RLE) need = 8;
+        need = 4u << log;
+    } else if (d.kind == ZB_SRC_RLE) need = 4;
     return used;
 }
 
@@ -206,7 +186,11 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
 {
     extern __shared__ __align__(16) u8 zb_smem[];
     u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u8* const pool = zb_smem + warp * ZB_ENT_POOL_BYTES;
+    u32* const lutLL = (u32*)zb_smem; u32* const lutML = lutLL + 36;      // baselines, indexed by symbol code
+    if (threadIdx.x < 36) lutLL[threadIdx.x] = c_LL_base[threadIdx.x];
+    if (threadIdx.x < 53) lutML[threadIdx.x] = c_ML_base[threadIdx.x];
+    __syncthreads();
+    u8* const pool = zb_smem + ZB_ENT_LUT_BYTES + warp * ZB_ENT_POOL_BYTES;
     u8* const ws = pool + lane * ZB_ENT_WS_BYTES;                       // lane workspace
     u8* const tabs = pool + 32 * ZB_ENT_WS_BYTES;                       // claimable table space
     u32 const TAB_BYTES = ZB_ENT_POOL_BYTES - 32 * ZB_ENT_WS_BYTES;
@@ -356,21 +340,16 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                     if (pending && incl <= TAB_BYTES) {
                         u8* q = tabs + incl - need;
                         ZbTab tLL, tOF, tML;
-                        // LL
-                        if (dLL.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normLL, msLL, logLL, K_LL); tLL.t = (ZbFseCell*)q; tLL.log = logLL; q += 8u << logLL; }
-                        else if (dLL.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dLL.sym, K_LL); *(ZbFseCell*)q = c; tLL.t = (ZbFseCell*)q; tLL.log = 0; q += 8; }
-                        else if (dLL.kind == ZB_SRC_DICT) { tLL.t = dict.ll; tLL.log = dict.ll_log; }
-                        else { tLL.t = g_defLL; tLL.log = 6; }
-                        // OF
-                        if (dOF.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normOF, msOF, logOF, K_OF); tOF.t = (ZbFseCell*)q; tOF.log = logOF; q += 8u << logOF; }
-                        else if (dOF.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dOF.sym, K_OF); *(ZbFseCell*)q = c; tOF.t = (ZbFseCell*)q; tOF.log = 0; q += 8; }
-                        else if (dOF.kind == ZB_SRC_DICT) { tOF.t = dict.of; tOF.log = dict.of_log; }
-                        else { tOF.t = g_defOF; tOF.log = 5; }
-                        // ML
-                        if (dML.kind == ZB_SRC_NCOUNT) { zb_build_fse_smem((ZbFseCell*)q, normML, msML, logML, K_ML); tML.t = (ZbFseCell*)q; tML.log = logML; q += 8u << logML; }
-                        else if (dML.kind == ZB_SRC_RLE) { ZbFseCell c; c.next = 0; c.nb = 0; zb_cell_payload(c, dML.sym, K_ML); *(ZbFseCell*)q = c; tML.t = (ZbFseCell*)q; tML.log = 0; q += 8; }
-                        else if (dML.kind == ZB_SRC_DICT) { tML.t = dict.ml; tML.log = dict.ml_log; }
-                        else { tML.t = g_defML; tML.log = 6; }
+                        auto setup = [&](const ZbTabSrc& d, short* norm, u32 ms, u32 lg, int kind, const ZbFseCell* dct, u32 dlog,
+                                         const ZbFseCell* def, u32 deflog, ZbTab& t) {
+                            if (d.kind == ZB_SRC_NCOUNT) { zb_build_fse((ZbFseCell*)q, norm, ms, lg, kind); t.t = (ZbFseCell*)q; t.log = lg; q += 4u << lg; }
+                            else if (d.kind == ZB_SRC_RLE) { *(ZbFseCell*)q = ZB_CELL(0, 0, zb_code_add_bits(d.sym, kind), d.sym); t.t = (ZbFseCell*)q; t.log = 0; q += 4; }
+                            else if (d.kind == ZB_SRC_DICT) { t.t = dct; t.log = dlog; }
+                            else { t.t = def; t.log = deflog; }
+                        };
+                        setup(dLL, normLL, msLL, logLL, K_LL, dict.ll, dict.ll_log, g_defLL, 6, tLL);
+                        setup(dOF, normOF, msOF, logOF, K_OF, dict.of, dict.of_log, g_defOF, 5, tOF);
+                        setup(dML, normML, msML, logML, K_ML, dict.ml, dict.ml_log, g_defML, 6, tML);
 
                         // the 3-state FSE sequence stream (restates ZSTD_decodeSequence, zstd/zstd.c:46862-46986)
                         ZbBitR b;
@@ -381,17 +360,18 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                             u64 const room = cap - out_pos;
                             ZbSeq* const sq = seqs + seq_i;
                             for (u32 i = 0; i < nseq; i++) {
-                                ZbFseCell const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
-                                u32 ll = cl.base, ml = cm.base, off;
-                                if (co.add_bits > 1) {
-                                    off = co.base + b.read(co.add_bits);
+                                u32 const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
+                                u32 const ofc = ZB_CELL_SYM(co), llc = ZB_CELL_SYM(cl);
+                                u32 ll = lutLL[llc], ml = lutML[ZB_CELL_SYM(cm)], off;      // baselines: off the state chain
+                                if (ofc > 1) {
+                                    off = (1u << ofc) - 3 + b.read(ofc);
                                     rep2 = rep1; rep1 = rep0; rep0 = off;
                                 } else {
-                                    u32 const ll0 = (cl.base == 0);
-                                    if (co.add_bits == 0) {
+                                    u32 const ll0 = (llc == 0);
+                                    if (ofc == 0) {
                                         if (ll0) { off = rep1; rep1 = rep0; rep0 = off; } else off = rep0;
                                     } else {
-                                        u32 const idx = co.base + ll0 + b.read(1);
+                                        u32 const idx = 1 + ll0 + b.read(1);
                                         u32 tmp = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
                                         if (tmp == 0) tmp = 0xFFFFFFFFu;
                                         if (idx != 1) rep2 = rep1;
@@ -399,13 +379,17 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                                     }
                                 }
                                 b.refill();
-                                ml += b.read(cm.add_bits);
-                                ll += b.read(cl.add_bits);
+                                {   // ML then LL additional bits in one read (<= 32 bits)
+                                    u32 const llb = ZB_CELL_ADD(cl), both = b.read(ZB_CELL_ADD(cm) + llb);
+                                    ml += both >> llb; ll += both & ((1u << llb) - 1);
+                                }
                                 b.refill();
-                                if (i + 1 < nseq) {
-                                    sLL = cl.next + b.read(cl.nb);
-                                    sML = cm.next + b.read(cm.nb);
-                                    sOF = co.next + b.read(co.nb);
+                                if (i + 1 < nseq) {   // the three state updates (LL, ML, OF) in one read (<= 26 bits)
+                                    u32 const nl = ZB_CELL_NB(cl), nm = ZB_CELL_NB(cm), no = ZB_CELL_NB(co);
+                                    u32 const v = b.read(nl + nm + no);
+                                    sLL = ZB_CELL_NEXT(cl) + (v >> (nm + no));
+                                    sML = ZB_CELL_NEXT(cm) + ((v >> no) & ((1u << nm) - 1));
+                                    sOF = ZB_CELL_NEXT(co) + (v & ((1u << no) - 1));
                                     b.refill();
                                 }
                                 sq[i] = make_uint4(lit_used, produced, ml, off);
@@ -416,7 +400,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                                 if ((u64)off > out_pos + produced + hist_extra) { err = ZB_E_CORRUPTION; break; }
                                 produced += ml;
                             }
-                            if (!err && b.left != 0) err = ZB_E_CORRUPTION;
+                            if (!err && b.left() != 0) err = ZB_E_CORRUPTION;
                         }
                         if (err) { done = true; comp = false; }
                         pending = false;

@@ -184,6 +184,7 @@ class ZstdDecompressor:
                             % (idx, got.value, exp.value))
         raise ZstdError("error decompressing item %d: %s" % (idx, L.zb200_error_string(code.value).decode()))
 
+    @staticmethod
     def _split(self, lengths, parts):
         """Contiguous ranges balanced by input bytes -- the reference's static partition of the
         batch over its workers (c-ext/decompressor.c:1237,1290-1305), here over devices."""
@@ -218,7 +219,7 @@ class ZstdDecompressor:
         segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
         data = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
         sizes_arr = np.frombuffer(sizes_bytes, dtype=np.uint64) if sizes_bytes is not None else None
-        parts = self._split(segs[:, 1], _devices(threads))
+        parts = self._split(None, segs[:, 1], _devices(threads))
         handles = []
         for dev, (lo, hi) in enumerate(parts):
             ctx = self._context(dev)
@@ -236,7 +237,7 @@ class ZstdDecompressor:
         n = len(views)
         lengths = np.array([v.nbytes for v in views], dtype=np.uint64)
         sizes_arr = np.frombuffer(sizes, dtype=np.uint64) if sizes is not None else None
-        parts = self._split(lengths, _devices(threads))
+        parts = self._split(None, lengths, _devices(threads))
         out = []
         for dev, (lo, hi) in enumerate(parts):
             ctx = self._context(dev)
