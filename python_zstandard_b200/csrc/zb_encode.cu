@@ -465,7 +465,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         __syncthreads();
 
         // ---------------- trivial blocks
-        bool raw = n < 32;
+        bool raw = n < 9;
         if (!raw) {   // RLE block? (all bytes equal)
             if (tid == 0) S.all_same = 1;
             __syncthreads();
@@ -501,12 +501,12 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 u32 const m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
                 u32 const lower = m & lt;
                 int cand = -1;
-                if (lower) cand = (int)(base + (31 - __clz(lower)));
+                if (lower) { cand = (int)(base + (31 - __clz(lower))); if (cand == 0 && job.first) cand = -1; }
                 else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= (int)p) cand -= 0x10000; }
                 u32 d = 0;
                 if (valid && cand >= 0 && p - (u32)cand <= 65535u) d = p - (u32)cand;
                 if (p < n) G.dist[p] = (u16)d;
-                if (valid && (m >> lane) == 1u && (p & 0xFFFFu) != 0xFFFFu) S.head[h] = (u16)p;     // highest lane of its group
+                if (valid && (m >> lane) == 1u && (p & 0xFFFFu) != 0xFFFFu && (p | (job.first ^ 1u))) S.head[h] = (u16)p;   // highest lane of its group; like the reference, the first position of a frame is never a match source (zstd/zstd.c:31075)
                 __syncwarp();
             }
         }
@@ -521,7 +521,8 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 u32 const ilimit = n >= 8 ? n - 8 : 0;
                 u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
                 uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
-                while (ip + 4 <= end && ip <= ilimit) {
+                if (ip == 0 && job.first) ip = 1;                      // the reference starts its search at position 1 (zstd/zstd.c:31075)
+                while (ip + 4 <= end && ip < ilimit) {                 // ... and stops one short of ilimit (:31100-31180)
                     u32 start = 0, ml = 0, off = 0;
                     if (r0 && ip + 5 <= end && ip + 1 <= ilimit && ip + 1 >= r0 && ze_ld32(in + ip + 1) == ze_ld32(in + ip + 1 - r0)) {
                         start = ip + 1; off = r0; ml = 4 + ze_count(in + start - off + 4, in + start + 4, end - start - 4);

@@ -1,0 +1,158 @@
+"""Compression parity: frames made by the CUDA compressor must decode bit-exact through the
+reference's own decoder (oracle/_ref) and the plain-C oracle, and stay within a stated size
+margin of the reference's level 3 (the parse is ours, so the bytes differ by design)."""
+import struct
+
+import numpy as np
+import pytest
+
+import corpus
+import python_zstandard_b200 as zstd
+from oracle import Oracle, RefZstd, have_ref
+
+pytestmark = pytest.mark.gpu
+
+# stated size margins vs the reference at level 3 (single-block inputs; measured: +0.3% / +0.7% / +3.2%)
+MARGIN_4K_TEXT = 1.02
+MARGIN_128K_MIX = 1.03
+MARGIN_128K_TEXT = 1.06
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    return RefZstd()
+
+
+def _cases():
+    text = corpus.text_corpus().tobytes()
+    rng = np.random.default_rng(5)
+    return {
+        "empty": b"", "one": b"a", "foo12": b"foo" * 12, "x64": b"x" * 64, "text100": text[:100], "text1k": text[:1000],
+        "text4k": text[5000:9096], "text64k": text[:65536], "text128k": text[:131072], "text300k": text[:300000],
+        "rand5k": rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(), "zeros100k": b"\0" * 100000,
+        "abcd": bytes(rng.choice(list(b"abcd"), 20000).astype(np.uint8)), "bin": corpus.binary_blob(100000).tobytes(),
+        "two_symbols": bytes(rng.choice(list(b"ab"), 3000).astype(np.uint8)), "block_edge": text[:131072 + 1],
+    }
+
+
+def test_one_shot_roundtrip_through_oracle(oracle):
+    for ck in (False, True):
+        for cs in (True, False):
+            c = zstd.ZstdCompressor(write_checksum=ck, write_content_size=cs)
+            for name, data in _cases().items():
+                frame = c.compress(data)
+                assert oracle.decompress(frame, len(data)) == data, (name, ck, cs)
+                if cs:
+                    assert zstd.frame_content_size(frame) == len(data)
+                else:
+                    assert zstd.frame_content_size(frame) == -1
+
+
+def test_one_shot_roundtrip_through_reference_decoder(ref):
+    c = zstd.ZstdCompressor(write_checksum=True)
+    for name, data in _cases().items():
+        frame = c.compress(data)
+        assert ref.decompress(frame, len(data)) == data, name
+
+
+def test_tiny_inputs_match_reference_sizes(ref):
+    # the reference's exact-size expectations (tests/test_compressor_multi_compress_to_buffer.py:45,64):
+    # 'foo'*12 + 'bar'*6 with checksums -> 44 bytes, 'foo'*4 + 'bar'*6 -> 47 bytes
+    cctx = zstd.ZstdCompressor(write_checksum=True)
+    b = cctx.multi_compress_to_buffer([b"foo" * 12, b"bar" * 6])
+    assert isinstance(b, zstd.BufferWithSegmentsCollection)
+    assert len(b) == 2 and b.size() == 44
+    assert b[0].tobytes() == cctx.compress(b"foo" * 12) and b[1].tobytes() == cctx.compress(b"bar" * 6)
+    offsets = struct.pack("=QQQQ", 0, 12, 12, 18)
+    r = cctx.multi_compress_to_buffer(zstd.BufferWithSegments(b"foo" * 4 + b"bar" * 6, offsets))
+    assert len(r) == 2 and r.size() == 47
+    # empty-frame known answers (tests/test_compressor_compress.py:19,28)
+    assert zstd.ZstdCompressor(write_content_size=False).compress(b"") == bytes.fromhex("28b52ffd0000010000")
+    assert zstd.ZstdCompressor().compress(b"") == bytes.fromhex("28b52ffd2000010000")
+    assert zstd.ZstdCompressor().compress(b"foo") == bytes.fromhex("28b52ffd2003190000666f6f")
+
+
+def test_argument_errors():
+    cctx = zstd.ZstdCompressor()
+    with pytest.raises(TypeError):
+        cctx.multi_compress_to_buffer(True)
+    with pytest.raises(TypeError):
+        cctx.multi_compress_to_buffer((1, 2))
+    with pytest.raises(TypeError, match="item 0 not a bytes like object"):
+        cctx.multi_compress_to_buffer(["foo"])
+    with pytest.raises(ValueError, match="no source elements found"):
+        cctx.multi_compress_to_buffer([])
+    with pytest.raises(ValueError, match="source elements are empty"):
+        cctx.multi_compress_to_buffer([b"", b"", b""])
+    with pytest.raises(ValueError, match="level must be less than 23"):
+        zstd.ZstdCompressor(level=23)
+
+
+def test_collection_input_and_many_items(oracle):
+    cctx = zstd.ZstdCompressor(write_checksum=True)
+    original = [b"foo1", b"foo2" * 2, b"foo3" * 3, b"foo4" * 4, b"foo5" * 5]
+    b1 = zstd.BufferWithSegments(original[0] + original[1], struct.pack("=QQQQ", 0, 4, 4, 8))
+    b2 = zstd.BufferWithSegments(b"".join(original[2:]), struct.pack("=QQQQQQ", 0, 12, 12, 16, 28, 20))
+    result = cctx.multi_compress_to_buffer(zstd.BufferWithSegmentsCollection(b1, b2))
+    assert len(result) == 5
+    for i, d in enumerate(original):
+        assert result[i].tobytes() == cctx.compress(d)
+        assert oracle.decompress(result[i].tobytes(), len(d)) == d
+    frames = [b"x" * 64] * 256 + [b"y" * 64] * 256
+    result = cctx.multi_compress_to_buffer(frames, threads=-1)
+    assert len(result) == 512
+    assert all(result[i].tobytes() == result[0].tobytes() for i in range(256))
+    assert all(result[i].tobytes() == result[256].tobytes() for i in range(256, 512))
+    out = zstd.ZstdDecompressor().multi_decompress_to_buffer(result)
+    assert out[0].tobytes() == b"x" * 64 and out[511].tobytes() == b"y" * 64
+
+
+def _batch_check(ref, blob, off, ln, margin):
+    segs = np.stack([off, ln], axis=1).astype(np.uint64)
+    res = zstd.ZstdCompressor().multi_compress_to_buffer(zstd.BufferWithSegments(blob, segs.tobytes()))
+    cb = res._buffers[0]
+    csegs = np.frombuffer(cb._segments, dtype=np.uint64).reshape(-1, 2)
+    cblob = np.frombuffer(cb._data, dtype=np.uint8)
+    # the reference decoder regenerates the input bit-exact
+    rb, rl = ref.batch(False, cblob, np.ascontiguousarray(csegs[:, 0]), np.ascontiguousarray(csegs[:, 1]), threads=8)
+    assert np.array_equal(rb, blob)
+    # size within the stated margin of the reference's level 3
+    refc, _ = ref.batch(True, blob, off, ln, level=3, threads=8)
+    assert len(cblob) <= len(refc) * margin, (len(cblob), len(refc))
+    # and our own decoder agrees
+    d = zstd.ZstdDecompressor().multi_decompress_to_buffer(res)
+    assert np.array_equal(np.frombuffer(d._buffers[0]._data, dtype=np.uint8), blob)
+    return len(cblob) / len(refc)
+
+
+def test_batch_4k_text(ref):
+    blob, off, ln = corpus.text_segments(4096, 4096)
+    _batch_check(ref, blob, off, ln, MARGIN_4K_TEXT)
+
+
+def test_batch_128k_mix(ref):
+    blob, off, ln = corpus.silesia_mix(96, 131072)
+    _batch_check(ref, blob, off, ln, MARGIN_128K_MIX)
+
+
+def test_batch_128k_text(ref):
+    blob, off, ln = corpus.text_segments(64, 131072)
+    _batch_check(ref, blob, off, ln, MARGIN_128K_TEXT)
+
+
+def test_ragged_sizes(ref, oracle):
+    rng = np.random.default_rng(9)
+    text = corpus.text_corpus().tobytes()
+    sizes = [int(x) for x in rng.integers(1, 20000, 200)] + [131072, 131073, 262144 + 5, 7, 31, 32, 33]
+    items = [text[i * 37: i * 37 + s] for i, s in enumerate(sizes)]
+    res = zstd.ZstdCompressor().multi_compress_to_buffer(items)
+    assert len(res) == len(items)
+    for i, d in enumerate(items):
+        assert oracle.decompress(res[i].tobytes(), len(d)) == d, i
