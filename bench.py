@@ -226,10 +226,62 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     assert last == blob[-FRAME:].tobytes()
 
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    # ---------------- secondary arm: multi_compress_to_buffer on 128 KiB Silesia-mix segments (configs[2], scaled)
+    cn = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "2048"))
+    cblob_in, coff_in, cln_in = corpus.silesia_mix(cn, 131072)
+    csegs = np.stack([coff_in, cln_in], axis=1).astype(np.uint64)
+    d_cin = torch.from_numpy(cblob_in).cuda()
+    d_csegs = torch.from_numpy(csegs.view(np.int64).copy()).cuda()
+    cparams = zstd.compressor.CParams(3, 0, 1, 0)
+
+    def step_compress():
+        r_ = C.c_void_p()
+        rc_ = L.zb200_compress_batch(ctx.h, d_cin.data_ptr(), d_csegs.data_ptr(), cn, C.byref(cparams),
+                                     _native.SRC_DEVICE | _native.DST_DEVICE, C.byref(r_))
+        ctx.check(rc_, "zb200_compress_batch")
+        return r_
+
+    r0 = step_compress()
+    csz = int(L.zb200_result_size(r0))
+    comp_bytes = np.empty(csz, dtype=np.uint8)
+    ctx.check(L.zb200_memcpy_d2h(ctx.h, comp_bytes.ctypes.data, L.zb200_result_data(r0), csz), "d2h")
+    comp_segs = np.ctypeslib.as_array(C.cast(L.zb200_result_segments(r0), C.POINTER(C.c_uint64)), shape=(cn, 2)).copy()
+    L.zb200_result_free(r0)
+    # correctness gate: the reference decoder regenerates the input bit-exact
+    rb, _ = ref.batch(False, comp_bytes, np.ascontiguousarray(comp_segs[:, 0]), np.ascontiguousarray(comp_segs[:, 1]),
+                      threads=threads)
+    if not np.array_equal(rb, cblob_in):
+        raise SystemExit("compressed batch does not round-trip through the reference decoder")
+    for _ in range(2):
+        L.zb200_result_free(step_compress())
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    csteps = max(2, args.steps // 2)
+    barrier()
+    ce0.record(stream)
+    for _ in range(csteps):
+        L.zb200_result_free(step_compress())
+    ce1.record(stream)
+    barrier()
+    comp_ms = ce0.elapsed_time(ce1) / csteps
+    cpin = zstd.PinnedBuffer(len(cblob_in), device=local)
+    np.frombuffer(cpin, dtype=np.uint8)[:] = cblob_in
+    cbws = zstd.BufferWithSegments(cpin, csegs.tobytes())
+    cctx = zstd.ZstdCompressor(level=3)
+    cctx.multi_compress_to_buffer(cbws)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(csteps):
+        rr = cctx.multi_compress_to_buffer(cbws)
+        _ = rr[cn - 1].tobytes()
+        del rr
+    barrier()
+    comp_e2e_ms = (time.perf_counter() - t0) * 1e3 / csteps
+    del d_cin
+
+    times = torch.tensor([dev_ms, e2e_ms, comp_ms, comp_e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    dev_ms, e2e_ms, comp_ms, comp_e2e_ms = (float(times[i]) for i in range(4))
 
     if rank != 0:
         if world > 1:
@@ -269,6 +321,20 @@ def main():
     ref.batch(False, cblob, coff[:sub].copy(), clens[:sub].copy(), dst_len=sizes[:sub].copy(), threads=1, gather=False)
     one_core = sub * FRAME / (time.perf_counter() - t0) / 1e9
 
+    tcb = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter()
+        refc_total = ref.batch(True, cblob_in, coff_in, cln_in, level=3, threads=cores, gather=False)
+        tcb = min(tcb, time.perf_counter() - t0)
+    compress_info = {
+        "workload": "multi_compress_to_buffer: %d x 128 KiB Silesia-mix segments per GPU, level-3 class" % cn,
+        "value": world * len(cblob_in) / (comp_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": comp_ms,
+        "e2e": {"value": world * len(cblob_in) / (comp_e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": comp_e2e_ms},
+        "ratio": len(cblob_in) / csz, "reference_level3_ratio": len(cblob_in) / refc_total,
+        "size_vs_reference_pct": 100.0 * (csz / refc_total - 1.0),
+        "roundtrip": "reference decoder regenerates the input bit-exact",
+        "cpu_baseline": {"value": len(cblob_in) / tcb / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference"},
+    }
     print(json.dumps({
         "metric": METRIC, "value": world * U / (dev_ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
@@ -287,6 +353,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "latency/issue-bound bitstream work; fraction of HBM copy bandwidth"},
         "kernels": kernels,
+        "compress": compress_info,
         "scratch_bytes_per_step": scratch,
         "cpu_baseline": {"value": U / best / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference",
                          "one_core_GBps": one_core,

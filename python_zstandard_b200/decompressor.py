@@ -186,20 +186,8 @@ class ZstdDecompressor:
 
     @staticmethod
     def _split(self, lengths, parts):
-        """Contiguous ranges balanced by input bytes -- the reference's static partition of the
-        batch over its workers (c-ext/decompressor.c:1237,1290-1305), here over devices."""
-        n = len(lengths)
-        if parts <= 1 or n < 2:
-            return [(0, n)]
-        cum = np.cumsum(lengths)
-        total = int(cum[-1])
-        cuts = [0]
-        for p in range(1, parts):
-            k = int(np.searchsorted(cum, total * p // parts, side="left")) + 1
-            k = min(max(k, cuts[-1] + 1), n - (parts - p))
-            cuts.append(k)
-        cuts.append(n)
-        return [(cuts[i], cuts[i + 1]) for i in range(parts) if cuts[i] < cuts[i + 1]]
+        from .sharding import split_ranges
+        return split_ranges(lengths, parts)
 
     def _launch(self, ctx, base_ptr, segs, n, sizes_arr, flags=0):
         L = ctx.L
