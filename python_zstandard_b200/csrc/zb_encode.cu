@@ -80,6 +80,22 @@ __device__ __forceinline__ u32 ze_ld32(const u8* p)     // unaligned little-endi
     if (sh == 0) return lo;
     return __funnelshift_r(lo, w[1], sh);
 }
+// unaligned little-endian 64-bit load built from three aligned 32-bit loads (reads up to 11 bytes past p)
+__device__ __forceinline__ u64 ze_ld64(const u8* p)
+{
+    uintptr_t const a = (uintptr_t)p; const u32* w = (const u32*)(a & ~(uintptr_t)3);
+    u32 const sh = (u32)(a & 3) * 8;
+    u32 const w0 = w[0], w1 = w[1], w2 = w[2];
+    return (u64)__funnelshift_r(w0, w1, sh) | ((u64)__funnelshift_r(w1, w2, sh) << 32);
+}
+// number of equal leading (little-endian) bytes of two 64-bit words, 0..8
+__device__ __forceinline__ u32 ze_common8(u64 a, u64 b)
+{
+    u64 const x = a ^ b; u32 const lo = (u32)x, hi = (u32)(x >> 32);
+    if (lo) return ((u32)__ffs((int)lo) - 1) >> 3;
+    if (hi) return 4 + (((u32)__ffs((int)hi) - 1) >> 3);
+    return 8;
+}
 __device__ __forceinline__ u32 ze_hash4(u32 v) { return (v * 2654435761u) >> (32 - ZE_HLOG); }
 // length of the common prefix of a[0..) and b[0..), at most `limit` bytes
 __device__ __forceinline__ u32 ze_count(const u8* a, const u8* b, u32 limit)
@@ -407,6 +423,8 @@ __device__ static u32 ze_huf_write_table(u8* out, const ZeHuf& H, ZeCTable& ct, 
 // ---------------------------------------------------------------------------
 // the block kernel
 // ---------------------------------------------------------------------------
+__device__ unsigned long long g_ze_phase[16];     // summed clock cycles per phase (thread 0 of every CTA), for tuning
+#define ZE_MARK(k) do { if (tid == 0) { long long const t_ = clock64(); atomicAdd(&g_ze_phase[k], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
 struct ZeShared {
     u16 head[1 << ZE_HLOG];           // A: hash heads.  E: reused as u32 staging by the packers
     u32 hist[256];
@@ -416,6 +434,7 @@ struct ZeShared {
     u32 wk[1600];
     u8 tmp_sym[3][512];
     u32 s_warp[8];
+    __align__(16) u32 ring[256];      // A: 2 x 512 B input ring
     u16 ucnt[128]; u16 utail[128];
     u32 uoff[128]; u32 ucarry[128];
     u32 nseq, nlit, tail_lit, all_same, lit_mode, lit_hdr, lit_bytes, seq_bytes, stream_bits[4], huf_tbl_bytes, seq_hdr_bytes, use_raw, body;
@@ -459,6 +478,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         u32 const j = s_job;
         if (j >= n_jobs) return;
         ZeBlockJob const job = jobs[j];
+        long long t_phase = clock64();
         const u8* const in = src + job.src_pos;
         u32 const n = job.size;
         u8* const out = slots + (u64)j * slot_bytes;       // block header (3 bytes) + payload
@@ -486,6 +506,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             continue;
         }
 
+        ZE_MARK(0);
         // ---------------- A: hash links (warp 0); the other warps clear the histograms meanwhile
         for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = 0xFFFFFFFFu;
         for (u32 i = tid; i < 256; i += ZE_THREADS) S.hist[i] = 0;
@@ -493,74 +514,174 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         __syncthreads();
         if (warp == 0) {
             u32 const lt = (1u << lane) - 1;
-            for (u32 base = 0; base < n; base += 32) {
-                u32 const p = base + lane;
-                bool const valid = p + 4 <= n;
-                u32 const h = valid ? ze_hash4(ze_ld32(in + p)) : 0;
-                u32 const old = valid ? S.head[h] : 0xFFFFu;
-                u32 const m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
-                u32 const lower = m & lt;
-                int cand = -1;
-                if (lower) { cand = (int)(base + (31 - __clz(lower))); if (cand == 0 && job.first) cand = -1; }
-                else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= (int)p) cand -= 0x10000; }
-                u32 d = 0;
-                if (valid && cand >= 0 && p - (u32)cand <= 65535u) d = p - (u32)cand;
-                if (p < n) G.dist[p] = (u16)d;
-                if (valid && (m >> lane) == 1u && (p & 0xFFFFu) != 0xFFFFu && (p | (job.first ^ 1u))) S.head[h] = (u16)p;   // highest lane of its group; like the reference, the first position of a frame is never a match source (zstd/zstd.c:31075)
+            volatile u16* const vhead = S.head;      // one warp, converged at every match.any: table accesses stay in program order
+            // The block is streamed through a 2 x 512-byte shared-memory ring, filled with coalesced 128-bit
+            // loads that are issued a whole chunk (16 steps) before their data is needed.
+            const u8* const in_al = (const u8*)((uintptr_t)in & ~(uintptr_t)15);
+            u32 const skew = (u32)(in - in_al);
+            u32 const span = skew + n;                                   // bytes of the aligned stream that belong to the block
+            auto chunk_ld = [&](u32 c) { u32 const o = c * 512 + lane * 16; return o < span + 16 ? *(const uint4*)(in_al + o) : make_uint4(0, 0, 0, 0); };
+            uint4* const ring = (uint4*)S.ring;
+            ring[lane] = chunk_ld(0);
+            uint4 pend = chunk_ld(1);
+            u32 const nchunks = (span + 511) / 512;
+            for (u32 c = 0; c < nchunks; c++) {
+                ring[((c + 1) & 1) * 32 + lane] = pend;                  // chunk c+1 (requested a chunk ago)
+                pend = chunk_ld(c + 2);
                 __syncwarp();
+                #pragma unroll 4
+                for (u32 k = 0; k < 16; k++) {
+                    int const pp = (int)(c * 512 + k * 32 + lane) - (int)skew;   // block position of this lane
+                    if (__all_sync(0xFFFFFFFFu, pp < 0 || pp >= (int)n)) continue;
+                    u32 const p = (u32)pp;
+                    bool const valid = pp >= 0 && p + 4 <= n;
+                    u32 const bo = (c * 512 + k * 32 + lane) & 1023;     // byte offset in the ring
+                    u32 const w0 = S.ring[bo >> 2], w1 = S.ring[((bo >> 2) + 1) & 255];
+                    u32 const vcur = __funnelshift_r(w0, w1, (bo & 3) * 8);
+                    u32 const h = valid ? ze_hash4(vcur) : 0;
+                    u32 const old = valid ? vhead[h] : 0xFFFFu;
+                    // Two lanes of this step with the same hash are the exception; match.any costs one round per
+                    // distinct value, so it only runs when the table itself shows a collision (a lane reads back
+                    // somebody else's position from the slot it just wrote).
+                    bool const ins = valid && (p & 0xFFFFu) != 0xFFFFu && (p | (job.first ^ 1u));
+                    if (ins) vhead[h] = (u16)p;
+                    bool const lost = ins && vhead[h] != (u16)p;
+                    int cand = -1;
+                    if (__any_sync(0xFFFFFFFFu, lost)) {
+                        u32 const m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
+                        u32 const lower = m & lt;
+                        if (lower) { int const lsrc = 31 - __clz(lower); cand = pp - ((int)lane - lsrc); if (cand == 0 && job.first) cand = -1; }
+                        else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= pp) cand -= 0x10000; }
+                        if (ins && (m >> lane) == 1u) vhead[h] = (u16)p;          // the highest lane of a group owns the slot
+                    } else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= pp) cand -= 0x10000; }
+                    u32 d = 0;
+                    if (valid && cand >= 0 && p - (u32)cand <= 65535u) d = p - (u32)cand;
+                    if (pp >= 0 && p < n) G.dist[p] = (u16)d;
+                }
             }
         }
         __syncthreads();
-
-        // ---------------- C: parse, one lane per 1 KiB unit
+        ZE_MARK(1);
+        // ---------------- C: parse, one lane per 1 KiB unit.
+        // A uniform state machine: every iteration issues ALL of a lane's loads together (current bytes,
+        // candidate bytes at ip and ip+1, both repcode candidates, the backward bytes, the next dist
+        // entry) and then decides, so a step costs one memory round trip for the whole warp instead of
+        // one per divergent path.  Long matches continue in EXTEND iterations, 8 bytes per step.
         {
             u32 const u0 = tid * ZE_UNIT;
             u32 cnt = 0, tail = 0;
-            if (u0 < n) {
-                u32 const end = min(u0 + ZE_UNIT, n);
-                u32 const ilimit = n >= 8 ? n - 8 : 0;
-                u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
-                uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
-                if (ip == 0 && job.first) ip = 1;                      // the reference starts its search at position 1 (zstd/zstd.c:31075)
-                while (ip + 4 <= end && ip < ilimit) {                 // ... and stops one short of ilimit (:31100-31180)
-                    u32 start = 0, ml = 0, off = 0;
-                    if (r0 && ip + 5 <= end && ip + 1 <= ilimit && ip + 1 >= r0 && ze_ld32(in + ip + 1) == ze_ld32(in + ip + 1 - r0)) {
-                        start = ip + 1; off = r0; ml = 4 + ze_count(in + start - off + 4, in + start + 4, end - start - 4);
-                    } else {
-                        u32 const d = G.dist[ip];
-                        if (d && ze_ld32(in + ip - d) == ze_ld32(in + ip)) {
-                            u32 m = 4 + ze_count(in + ip - d + 4, in + ip + 4, end - ip - 4);
-                            bool take = true;
-                            if (ip + 1 <= ilimit && ip + 5 <= end) {           // one-step lazy: is the match at ip+1 clearly better?
-                                u32 const d2 = G.dist[ip + 1];
-                                if (d2 && ze_ld32(in + ip + 1 - d2) == ze_ld32(in + ip + 1)) {
-                                    u32 const m2 = 4 + ze_count(in + ip + 1 - d2 + 4, in + ip + 5, end - ip - 5);
-                                    if (m2 > m + 1) take = false;
-                                }
+            bool alive = u0 < n;
+            u32 const end = alive ? min(u0 + ZE_UNIT, n) : 0;
+            u32 const ilimit = n >= 8 ? n - 8 : 0;
+            u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
+            if (alive && ip == 0 && job.first) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
+            uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
+            u32 mode = 0, m_start = 0, m_off = 0, m_len = 0;
+            u32 d0 = 0, d1 = 0;
+            if (alive) { d0 = G.dist[ip]; d1 = ip + 1 < n ? G.dist[ip + 1] : 0; }
+            for (;;) {
+                bool const searching = alive && mode == 0 && ip + 4 <= end && ip < ilimit;   // ... and stops one short of ilimit (:31100-31180)
+                bool const extending = alive && mode == 1;
+                if (!__any_sync(0xFFFFFFFFu, searching || extending)) break;
+                if (alive && !searching && !extending) alive = false;
+                // all loads of the step, unconditional (invalid ones alias the current position) and issued
+                // back to back as raw aligned words; the funnel shifts that consume them come afterwards
+                u64 A = 0, B = 0, C1 = 0, RP = 0, RQ = 0; u32 bka = 0, bkb = 1, d2 = 0, bk_max = 0;
+                bool has_c1 = false, has_rp = false, has_rq = false, has_bk = false;
+                {
+                    u32 const pa = extending ? m_start + m_len : ip;
+                    has_c1 = searching && d1 != 0 && ip + 5 <= end;
+                    has_rp = searching && r0 != 0 && ip + 1 >= r0 && ip + 5 <= end;
+                    has_rq = searching && anchor == ip && r1 != 0 && ip >= r1;
+                    u32 const em = (searching && d0) ? min(4u, min(ip - anchor, ip - d0)) : 0u;   // bytes that may extend the match backwards
+                    has_bk = em != 0; bk_max = em;
+                    u32 const pb = extending ? pa - m_off : (d0 ? ip - d0 : ip);
+                    u32 const pc = has_c1 ? ip + 1 - d1 : pa;
+                    u32 const pp = has_rp ? ip + 1 - r0 : pa;
+                    u32 const pq = has_rq ? ip - r1 : pa;
+                    u32 const pk = has_bk ? ip - em : pa;
+                    u32 const pl = has_bk ? ip - d0 - em : pa;
+                    bool const act = searching || extending;
+                    const u8* const qa = in + (act ? pa : 0); const u8* const qb = in + (act ? pb : 0); const u8* const qc = in + (act ? pc : 0);
+                    const u8* const qp = in + (act ? pp : 0); const u8* const qq = in + (act ? pq : 0);
+                    const u8* const qk = in + (act ? pk : 0); const u8* const ql = in + (act ? pl : 0);
+                    #define ZE_W(q) ((const u32*)((uintptr_t)(q) & ~(uintptr_t)3))
+                    #define ZE_S(q) ((u32)((uintptr_t)(q) & 3) * 8)
+                    const u32* const wa = ZE_W(qa); const u32* const wb = ZE_W(qb); const u32* const wc = ZE_W(qc);
+                    const u32* const wpp = ZE_W(qp); const u32* const wq = ZE_W(qq); const u32* const wk = ZE_W(qk); const u32* const wl = ZE_W(ql);
+                    // predicated (not branched) loads: a lane only spends load bandwidth on what it will look at.
+                    // A candidate that coincides with the main candidate (same distance) reuses its bytes.
+                    bool const ldb = extending || (searching && d0 != 0);
+                    bool const c_same = has_c1 && d0 != 0 && d1 == d0, p_same = has_rp && d0 != 0 && r0 == d0;
+                    bool const ldc = has_c1 && !c_same, ldp = has_rp && !p_same;
+                    u32 const a0 = act ? wa[0] : 0, a1 = act ? wa[1] : 0, a2 = act ? wa[2] : 0;
+                    u32 const b0 = ldb ? wb[0] : 0, b1 = ldb ? wb[1] : 0, b2 = ldb ? wb[2] : 0;
+                    u32 const c0 = ldc ? wc[0] : 0, c1 = ldc ? wc[1] : 0, c2 = ldc ? wc[2] : 0;
+                    u32 const p0 = ldp ? wpp[0] : 0, p1 = ldp ? wpp[1] : 0, p2 = ldp ? wpp[2] : 0;
+                    u32 const q0 = has_rq ? wq[0] : 0, q1 = has_rq ? wq[1] : 0, q2 = has_rq ? wq[2] : 0;
+                    u32 const k0 = has_bk ? wk[0] : 0, k1 = has_bk ? wk[1] : 0, l0 = has_bk ? wl[0] : 0, l1 = has_bk ? wl[1] : 0;
+                    u32 const dn = (searching && ip + 2 < n) ? G.dist[ip + 2] : 0;
+                    #define ZE_J(x0, x1, x2, q) ((u64)__funnelshift_r(x0, x1, ZE_S(q)) | ((u64)__funnelshift_r(x1, x2, ZE_S(q)) << 32))
+                    A = ZE_J(a0, a1, a2, qa); B = ZE_J(b0, b1, b2, qb); C1 = ZE_J(c0, c1, c2, qc); RP = ZE_J(p0, p1, p2, qp); RQ = ZE_J(q0, q1, q2, qq);
+                    if (c_same) C1 = B >> 8;
+                    if (p_same) RP = B >> 8;
+                    bka = __funnelshift_r(k0, k1, ZE_S(qk)) << ((4 - em) * 8 & 31); bkb = __funnelshift_r(l0, l1, ZE_S(ql)) << ((4 - em) * 8 & 31);
+                    d2 = dn;
+                    if (searching && !d0) B = ~A;
+                }
+                bool fin = false; u32 f_start = 0, f_off = 0, f_len = 0;
+                if (searching) {
+                    u32 const room = end - ip;
+                    bool found = false, sat = false; u32 start = 0, off = 0, len = 0;
+                    if (has_rq && (u32)A == (u32)RQ) {                       // immediate repcode match (ll == 0)
+                        u32 const c = ze_common8(A, RQ); start = ip; off = r1; len = min(c, room); sat = c == 8; found = true;
+                    } else if (has_rp && (u32)(A >> 8) == (u32)RP) {         // repcode match at ip + 1
+                        u32 const c = min(ze_common8(A >> 8, RP & 0x00FFFFFFFFFFFFFFull), 7u);
+                        start = ip + 1; off = r0; len = min(c, room - 1); sat = c == 7; found = true;
+                    } else if (d0 && (u32)A == (u32)B) {
+                        u32 const m0 = ze_common8(A, B);
+                        bool skip = false;
+                        if (m0 < 8 && has_c1 && (u32)(A >> 8) == (u32)C1) {  // one-step lazy: clearly longer one byte later?
+                            u32 const m1 = min(ze_common8(A >> 8, C1 & 0x00FFFFFFFFFFFFFFull), 7u);
+                            skip = m1 > m0 + 1;
+                        }
+                        if (!skip) {
+                            start = ip; off = d0; len = min(m0, room); sat = m0 == 8; found = true;
+                            if (has_bk) {                                    // backward extension, up to 4 bytes
+                                u32 const x = bka ^ bkb; u32 e = x ? ((u32)__clz((int)x) >> 3) : 4u;
+                                e = min(e, bk_max);
+                                start -= e; len += e;
                             }
-                            if (take) {
-                                start = ip; off = d; ml = m;
-                                while (start > anchor && start > off && in[start - 1] == in[start - off - 1]) { start--; ml++; }
-                            } else { ip++; continue; }
                         }
                     }
-                    if (ml < 4) { ip += 1 + ((ip - anchor) >> 8); continue; }
-                    u32 ll = start - anchor;
-                    rec[cnt++] = make_uint2(ll | (ml << 16), ze_off_code(off, ll, r0, r1, r2));
-                    ip = start + ml; anchor = ip;
-                    // immediate repcode matches (ll == 0: code 1 means the second most recent offset)
-                    while (r1 && ip <= ilimit && ip + 4 <= end && ip >= r1 && ze_ld32(in + ip) == ze_ld32(in + ip - r1)) {
-                        u32 const o = r1, m = 4 + ze_count(in + ip - o + 4, in + ip + 4, end - ip - 4);
-                        rec[cnt++] = make_uint2(0u | (m << 16), ze_off_code(o, 0, r0, r1, r2));
-                        ip += m; anchor = ip;
+                    if (found) {
+                        if (sat && start + len < end) { mode = 1; m_start = start; m_off = off; m_len = len; }
+                        else { fin = true; f_start = start; f_off = off; f_len = len; }
+                    } else {
+                        u32 const step = 1 + ((ip - anchor) >> 8);
+                        ip += step;
+                        if (step == 1) { d0 = d1; d1 = d2; }
+                        else { d0 = ip < n ? G.dist[ip] : 0; d1 = ip + 1 < n ? G.dist[ip + 1] : 0; }
                     }
+                } else if (extending) {
+                    u32 const room = end - (m_start + m_len);
+                    u32 const c = ze_common8(A, B); u32 const k = min(c, room);
+                    m_len += k;
+                    if (!(c == 8 && m_start + m_len < end)) { fin = true; f_start = m_start; f_off = m_off; f_len = m_len; }
                 }
-                tail = end - anchor;
+                if (fin) {
+                    u32 const ll = f_start - anchor;
+                    rec[cnt++] = make_uint2(ll | (f_len << 16), ze_off_code(f_off, ll, r0, r1, r2));
+                    ip = f_start + f_len; anchor = ip; mode = 0;
+                    d0 = ip < n ? G.dist[ip] : 0; d1 = ip + 1 < n ? G.dist[ip + 1] : 0;
+                }
             }
+            if (u0 < n) tail = end - anchor;
             S.ucnt[tid] = (u16)cnt; S.utail[tid] = (u16)tail;
         }
         __syncthreads();
 
+        ZE_MARK(2);
         // ---------------- D: compaction of the units' sequences + literal gather
         if (tid == 0) {
             u32 off = 0, carry = 0; u32 const units = (n + ZE_UNIT - 1) / ZE_UNIT;
@@ -610,6 +731,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         __syncthreads();
         u32 const nlit = S.nlit;
 
+        ZE_MARK(3);
         // ---------------- E: entropy tables.  thread 0: LL, 32: OF, 64: ML (own scratch each), 96: literals mode + Huffman code
         if (nseq) {
             if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0]);
@@ -629,6 +751,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         }
         __syncthreads();
 
+        ZE_MARK(4);
         // ---------------- E: literals section payload into tmp_lit
         u32 lit_payload = 0;        // bytes in tmp_lit (Huffman: table + jump table + streams)
         bool const four = nlit >= 256;
@@ -682,30 +805,50 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             __syncthreads();
         }
 
+        ZE_MARK(5);
         // ---------------- E: sequences -> tmp_seq
         u32 seq_payload = 0;
         if (nseq) {
             // three state chains, last sequence to first (warps 0..2, lane 0)
-            if (lane == 0 && warp < 3) {
-                ZeCTable const& ct = S.ct[warp == 0 ? 0 : (warp == 1 ? 1 : 2)];
-                const u8* const codes = warp == 0 ? G.llc : (warp == 1 ? G.ofc : G.mlc);
-                u16* const sb = G.sbits[warp];
+            if (warp == 0 && lane < 3) {                                  // lanes 0,1,2 of one warp: LL, OF, ML
+                ZeCTable const& ct = S.ct[lane];
+                const u8* const codes = lane == 0 ? G.llc : (lane == 1 ? G.ofc : G.mlc);
+                u16* const sb = G.sbits[lane];
                 if (ct.mode == 1) { for (u32 i = 0; i < nseq; i++) sb[i] = 0; sb[nseq] = 0; }
                 else {
                     u32 s = codes[nseq - 1];
                     u32 const nbo = (u32)(ct.dnb[s] + (1 << 15)) >> 16; u32 const v0 = (nbo << 16) - (u32)ct.dnb[s];
                     u32 st = ct.state[(v0 >> nbo) + ct.dfs[s]];
                     sb[nseq - 1] = 0;
-                    for (int i = (int)nseq - 2; i >= 0; i--) {
+                    // The chain st -> st' is serial; everything that does not depend on st (the symbol codes and
+                    // their deltaNbBits / deltaFindState) is fetched a group of four ahead of it.
+                    int i = (int)nseq - 2;
+                    for (; i >= 0 && ((i & 3) != 3); i--) {
                         s = codes[i];
                         u32 const nb = (st + (u32)ct.dnb[s]) >> 16;
                         sb[i] = (u16)((st & ((1u << nb) - 1)) | (nb << 12));
                         st = ct.state[(st >> nb) + ct.dfs[s]];
                     }
+                    if (i >= 3) {
+                        u32 grp = *(const u32*)(codes + i - 3);                 // codes[i-3..i], 4-byte aligned
+                        for (; i >= 3; i -= 4) {
+                            u32 const g = grp;
+                            if (i >= 7) grp = *(const u32*)(codes + i - 7);     // next group, needed four steps from now
+                            u32 const s3 = g >> 24, s2 = (g >> 16) & 255, s1 = (g >> 8) & 255, s0 = g & 255;
+                            int const n3 = ct.dnb[s3], f3 = ct.dfs[s3], n2 = ct.dnb[s2], f2 = ct.dfs[s2];
+                            int const n1 = ct.dnb[s1], f1 = ct.dfs[s1], n0 = ct.dnb[s0], f0 = ct.dfs[s0];
+                            u32 nb;
+                            nb = (st + (u32)n3) >> 16; sb[i]     = (u16)((st & ((1u << nb) - 1)) | (nb << 12)); st = ct.state[(st >> nb) + f3];
+                            nb = (st + (u32)n2) >> 16; sb[i - 1] = (u16)((st & ((1u << nb) - 1)) | (nb << 12)); st = ct.state[(st >> nb) + f2];
+                            nb = (st + (u32)n1) >> 16; sb[i - 2] = (u16)((st & ((1u << nb) - 1)) | (nb << 12)); st = ct.state[(st >> nb) + f1];
+                            nb = (st + (u32)n0) >> 16; sb[i - 3] = (u16)((st & ((1u << nb) - 1)) | (nb << 12)); st = ct.state[(st >> nb) + f0];
+                        }
+                    }
                     sb[nseq] = (u16)((st & ((1u << ct.log) - 1)));      // final state (flushed with `log` bits)
                 }
             }
             __syncthreads();
+            ZE_MARK(6);
             // bit count per sequence; chunks are written last sequence first
             u32 const logLL = S.ct[0].mode == 1 ? 0 : S.ct[0].log, logOF = S.ct[1].mode == 1 ? 0 : S.ct[1].log, logML = S.ct[2].mode == 1 ? 0 : S.ct[2].log;
             u32 run = 0;
@@ -745,6 +888,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             __syncthreads();
         }
 
+        ZE_MARK(7);
         // ---------------- F: assemble the block in its slot
         if (tid == 0) {
             u8* o = S.lit_hdr_buf; u32 p = 0;
@@ -798,6 +942,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 if (nseq) { const u8* ps = (const u8*)G.tmp_seq; for (u32 i = tid; i < seq_payload; i += ZE_THREADS) o[p + i] = ps[i]; }
             }
         }
+        ZE_MARK(8);
         __syncthreads();
     }
 }
@@ -957,5 +1102,11 @@ void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* se
 }
 
 u32 zb_encode_smem_bytes() { return (u32)sizeof(ZeShared); }
+
+void zb_encode_phase_read(unsigned long long* out16, int reset)
+{
+    cudaMemcpyFromSymbol(out16, g_ze_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_ze_phase, z, sizeof z); }
+}
 
 }  // extern "C"

@@ -1,0 +1,24 @@
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, corpus
+import python_zstandard_b200 as zb
+from python_zstandard_b200 import _native
+n = int(os.environ.get("N", "592")); size = int(os.environ.get("SIZE", "131072"))
+blob, off, ln = corpus.text_segments(n, size)
+segs = np.stack([off, ln], axis=1).astype(np.uint64)
+bws = zb.BufferWithSegments(blob, segs.tobytes())
+c = zb.ZstdCompressor()
+L = _native.lib()
+L.zb_encode_phase_read.argtypes = [C.c_void_p, C.c_int]
+buf = (C.c_uint64 * 16)()
+c.multi_compress_to_buffer(bws)
+L.zb_encode_phase_read(buf, 1)
+ctx = _native.Context.get(0); ctx.profile(True)
+res = c.multi_compress_to_buffer(bws)
+print(ctx.profile_read())
+L.zb_encode_phase_read(buf, 1)
+names = ["setup/rle", "A hash links", "C parse", "D compaction+gather", "E tables", "E literals", "E chains", "E seq pack", "F assemble"]
+tot = sum(buf[i] for i in range(9))
+for i, nm in enumerate(names):
+    print("%-22s %10.0f cycles/block  %5.1f%%" % (nm, buf[i] / n, 100.0 * buf[i] / tot))
+print("total cycles/block", tot / n)
