@@ -230,7 +230,8 @@ def main():
     cn = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "2048"))
     cblob_in, coff_in, cln_in = corpus.silesia_mix(cn, 131072)
     csegs = np.stack([coff_in, cln_in], axis=1).astype(np.uint64)
-    d_cin = torch.from_numpy(cblob_in).cuda()
+    d_cin = torch.empty(len(cblob_in) + 256, dtype=torch.uint8, device="cuda")
+    d_cin[:len(cblob_in)].copy_(torch.from_numpy(cblob_in))
     d_csegs = torch.from_numpy(csegs.view(np.int64).copy()).cuda()
     cparams = zstd.compressor.CParams(3, 0, 1, 0)
 

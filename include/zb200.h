@@ -133,6 +133,7 @@ int zb200_frame_info(const void* src, size_t size, zb200_frame_info_t* out);
 #define ZB200_K_COMPRESS 5
 #define ZB200_K_LAYOUT   6
 #define ZB200_K_FRAMES   7
+#define ZB200_K_VERIFY   8
 #define ZB200_K_COUNT    16
 void zb200_profile_enable(zb200_ctx* ctx, int on);
 void zb200_profile_reset(zb200_ctx* ctx);

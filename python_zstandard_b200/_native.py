@@ -111,12 +111,15 @@ class Context:
         self.lock = threading.Lock()
 
     @classmethod
-    def get(cls, device=0):
+    def get(cls, device=0, slot=0):
+        """Context `slot` of `device`.  Slot 0 is the default; slots 1.. are extra contexts (own stream,
+        scratch and pinned pool) used to keep several sub-batches in flight so that host->device copies,
+        kernels and device->host copies of different sub-batches overlap."""
         with cls._guard:
-            c = cls._by_device.get(device)
+            c = cls._by_device.get((device, slot))
             if c is None:
                 c = cls(device)
-                cls._by_device[device] = c
+                cls._by_device[(device, slot)] = c
             return c
 
     def last_error(self):

@@ -21,9 +21,11 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
                      u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st);
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, cudaStream_t st);
+void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_sizes, const ZbFrameInfo* info, const u32* ck_expect,
+                      u32 first, u32 end, u32* status, cudaStream_t st);
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
-                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st);
+                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st);
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,
                       u32* first_error, cudaStream_t st);
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
@@ -61,11 +63,13 @@ struct PinnedBlock { void* p; size_t cap; bool busy; };
 struct zb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // device->host copies of finished chunks, overlapping later chunks' kernels
+    cudaEvent_t chunk_ev[64] = {nullptr};
     std::string last_error;
     int sm_count = 148;
     // device arenas (grow-only)
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
-    DevBuf jobs, seginfo, slots, bouts, escratch, fsizes;
+    DevBuf jobs, seginfo, slots, bouts, escratch, fsizes, ck;
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -120,17 +124,24 @@ void fold_spans(zb200_ctx* c)
 
 void* pinned_get(zb200_ctx* c, size_t bytes)
 {
+    // size classes (powers of two up to 64 MiB, then multiples of 64 MiB) so that batches of slightly different
+    // sizes reuse the same blocks; blocks are kept for the life of the context (page-locking is slow)
+    size_t cls = 1 << 16;
+    while (cls < bytes && cls < ((size_t)64 << 20)) cls <<= 1;
+    if (cls < bytes) cls = (bytes + ((size_t)64 << 20) - 1) & ~(((size_t)64 << 20) - 1);
     std::lock_guard<std::mutex> g(c->mu);
     PinnedBlock* best = nullptr;
-    for (auto& b : c->pinned) if (!b.busy && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+    for (auto& b : c->pinned) if (!b.busy && b.cap >= cls && (!best || b.cap < best->cap)) best = &b;
     if (best) { best->busy = true; return best->p; }
-    // drop idle blocks that are too small before growing
-    for (size_t i = 0; i < c->pinned.size();) {
-        if (!c->pinned[i].busy) { cudaFreeHost(c->pinned[i].p); c->pinned.erase(c->pinned.begin() + (long)i); } else i++;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) {
+        // out of pinned memory: release idle blocks and retry once
+        for (size_t i = 0; i < c->pinned.size();) {
+            if (!c->pinned[i].busy) { cudaFreeHost(c->pinned[i].p); c->pinned.erase(c->pinned.begin() + (long)i); } else i++;
+        }
+        if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     }
-    void* p = nullptr; size_t cap = bytes + bytes / 16 + 4096;
-    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    c->pinned.push_back({p, cap, true});
+    c->pinned.push_back({p, cls, true});
     return p;
 }
 void pinned_put(zb200_ctx* c, void* p)
@@ -146,6 +157,10 @@ bool is_pinned_pool(zb200_ctx* c, const void* p)
 }
 
 ZbDictDev no_dict() { ZbDictDev d; memset(&d, 0, sizeof d); return d; }
+
+// One upload at a time per device: when several contexts work on sub-batches of one call, this staggers
+// them (A computes and downloads while B uploads) instead of letting them share every stage in lock-step.
+std::mutex g_upload_mu[16];
 
 }  // namespace
 
@@ -164,6 +179,8 @@ int zb200_ctx_create(int device, zb200_ctx** out)
         delete ctx; return -1;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     zb_launch_default_tables(ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -1; }
     *out = ctx;
@@ -177,10 +194,12 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
                      &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial,
-                     &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes};
+                     &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes, &ctx->ck};
     for (auto* b : all) b->release();
     for (auto& b : ctx->pinned) cudaFreeHost(b.p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -292,19 +311,21 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(ctx->status.ensure(n * sizeof(u32)));
     CK(ctx->out_sizes.ensure(n * sizeof(u64)));
     CK(ctx->out_segs.ensure(n * sizeof(ZbSegment)));
-    CK(ctx->small.ensure(256));
+    CK(ctx->small.ensure(512));
     CK(ctx->partial.ensure(((n + 1023) / 1024 + 1) * 4 * sizeof(u64)));
     u64* d_totals = ctx->small.as<u64>();                 // [0..3] totals
     u32* d_counter = (u32*)(d_totals + 8);                // work counter
     u32* d_first_err = d_counter + 1;
     u32 init[2] = {0, 0xFFFFFFFFu};
     CK(cudaMemcpyAsync(d_counter, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_totals, 0, 8 * sizeof(u64), ctx->stream));
+    CK(ctx->ck.ensure(n * sizeof(u32)));
 
     { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), ctx->stream); }
     { KSpan s(ctx, ZB200_K_PLACE);
       zb_launch_place(ctx->info.as<ZbFrameInfo>(), d_dst_sizes, nf, ctx->place.as<ZbFramePlace>(), d_totals,
                       ctx->status.as<u32>(), ctx->partial.as<u64>(), ctx->stream); }
-    u64 totals[4];
+    u64 totals[5];
     CK(cudaMemcpyAsync(totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
@@ -318,29 +339,55 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(ctx->dst.ensure(totals[0] + 64));
     ctx->last_scratch = (totals[1] + 1) * sizeof(ZbBlock) + (totals[2] + 1) * sizeof(ZbSeq) + totals[3];
 
-    { KSpan s(ctx, ZB200_K_ENTROPY);
-      zb_launch_entropy(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
-                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctas, d_counter, dd,
-                        ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->stream); }
-    { KSpan s(ctx, ZB200_K_EXECUTE);
-      zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
-                        ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), nf, dd, ctx->stream); }
-    { KSpan s(ctx, ZB200_K_FINISH);
-      zb_launch_finish(ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->status.as<u32>(), nf,
-                       ctx->out_segs.as<ZbSegment>(), d_first_err, ctx->stream); }
-
+    // ---- chunks of frames: the device->host copy of chunk k overlaps the kernels of chunk k+1
+    u32 n_chunks = 1;
+    if (copy_back) { u64 c = totals[0] / (48ull << 20); n_chunks = (u32)(c < 1 ? 1 : (c > 32 ? 32 : c)); if (n_chunks > nf) n_chunks = nf; }
+    std::vector<u32> cut(n_chunks + 1); for (u32 k = 0; k <= n_chunks; k++) cut[k] = (u32)((u64)nf * k / n_chunks);
+    std::vector<ZbFramePlace> cpl(n_chunks + 1);
+    if (n_chunks > 1) {
+        for (u32 k = 0; k <= n_chunks; k++)
+            CK(cudaMemcpyAsync(&cpl[k], ctx->place.as<ZbFramePlace>() + cut[k], sizeof(ZbFramePlace), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<u32> cinit(n_chunks); for (u32 k = 0; k < n_chunks; k++) cinit[k] = cut[k];
+        CK(cudaMemcpyAsync(d_counter + 8, cinit.data(), n_chunks * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     res->n = n; res->size = totals[0];
     res->segs.resize(n);
-    u32 first_err = 0xFFFFFFFFu;
-    CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&first_err, d_first_err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     if (copy_back) {
         res->data = pinned_get(ctx, totals[0] ? totals[0] : 1);
         if (!res->data) return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation);
         res->data_pinned_pool = true;
-        CK(cudaMemcpyAsync(res->data, ctx->dst.p, totals[0], cudaMemcpyDeviceToHost, ctx->stream));
     } else { res->data = ctx->dst.p; res->data_on_device = true; }
+    for (u32 k = 0; k < n_chunks; k++) {
+        u32 const f0 = cut[k], f1 = cut[k + 1];
+        u32* const counter = n_chunks > 1 ? d_counter + 8 + k : d_counter;
+        u32 cc = ctas; { u32 const need = (f1 - f0 + 255) / 256; if (cc > need) cc = need; if (cc == 0) cc = 1; }
+        { KSpan s(ctx, ZB200_K_ENTROPY);
+          zb_launch_entropy(d_src, d_segs, f1, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
+                            ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
+                            ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), ctx->stream); }
+        { KSpan s(ctx, ZB200_K_EXECUTE);
+          zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
+                            ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), f0, f1, dd, ctx->stream); }
+        if (totals[4]) { KSpan s(ctx, ZB200_K_VERIFY);
+          zb_launch_verify(ctx->dst.as<u8>(), ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->info.as<ZbFrameInfo>(),
+                           ctx->ck.as<u32>(), f0, f1, ctx->status.as<u32>(), ctx->stream); }
+        if (copy_back && n_chunks > 1) {
+            CK(cudaEventRecord(ctx->chunk_ev[k], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[k], 0));
+            u64 const o0 = cpl[k].dst_off, o1 = cpl[k + 1].dst_off;
+            if (o1 > o0) CK(cudaMemcpyAsync((u8*)res->data + o0, ctx->dst.as<u8>() + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    { KSpan s(ctx, ZB200_K_FINISH);
+      zb_launch_finish(ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->status.as<u32>(), nf,
+                       ctx->out_segs.as<ZbSegment>(), d_first_err, ctx->stream); }
+    u32 first_err = 0xFFFFFFFFu;
+    CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&first_err, d_first_err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (copy_back && n_chunks == 1) CK(cudaMemcpyAsync(res->data, ctx->dst.p, totals[0], cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (copy_back && n_chunks > 1) CK(cudaStreamSynchronize(ctx->copy_stream));
     if (ctx->prof) fold_spans(ctx);
     if (first_err != 0xFFFFFFFFu) {
         u32 code = 0; u64 got = 0; ZbFramePlace pl;
@@ -367,20 +414,22 @@ static int decompress_common(zb200_ctx* ctx, const void* src_base, const zb200_s
         if (hi < lo) { lo = hi = 0; }
         CK(ctx->src.ensure(hi - lo + 64));
         CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
-        CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-        if (lo == 0) CK(cudaMemcpyAsync(ctx->segs.p, segs, n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
-        else {
-            std::vector<zb200_segment> tmp(segs, segs + n);
-            for (auto& s : tmp) s.offset -= lo;
-            CK(cudaMemcpyAsync(ctx->segs.p, tmp.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        if (dst_sizes) CK(ctx->dst_sizes.ensure(n * sizeof(u64)));
+        std::vector<zb200_segment> tmp;
+        {
+            std::lock_guard<std::mutex> up(g_upload_mu[ctx->device & 15]);
+            CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+            if (lo == 0) CK(cudaMemcpyAsync(ctx->segs.p, segs, n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+            else {
+                tmp.assign(segs, segs + n);
+                for (auto& s : tmp) s.offset -= lo;
+                CK(cudaMemcpyAsync(ctx->segs.p, tmp.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+            }
+            if (dst_sizes) CK(cudaMemcpyAsync(ctx->dst_sizes.p, dst_sizes, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
         }
         d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
-        if (dst_sizes) {
-            CK(ctx->dst_sizes.ensure(n * sizeof(u64)));
-            CK(cudaMemcpyAsync(ctx->dst_sizes.p, dst_sizes, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-            d_dst_sizes = ctx->dst_sizes.as<u64>();
-        }
+        if (dst_sizes) d_dst_sizes = ctx->dst_sizes.as<u64>();
     }
     zb200_result* res = new zb200_result(); res->ctx = ctx;
     int rc = run_decompress(ctx, d_src, d_segs, n, d_dst_sizes, dict, res, !(flags & ZB200_DST_DEVICE),
@@ -585,7 +634,7 @@ int zb200_profile_read(zb200_ctx* ctx, float ms[ZB200_K_COUNT], uint32_t launche
 const char* zb200_kernel_name(int k)
 {
     static const char* names[ZB200_K_COUNT] = {"zb_scan_frames", "zb_place_frames", "zb_entropy_decode", "zb_execute", "zb_finish",
-                                                "zb_compress_blocks", "zb_frame_layout", "zb_write_frames"};
+                                                "zb_compress_blocks", "zb_frame_layout", "zb_write_frames", "zb_verify_checksums"};
     return (k >= 0 && k < ZB200_K_COUNT && names[k]) ? names[k] : "";
 }
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }

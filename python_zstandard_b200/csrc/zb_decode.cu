@@ -236,7 +236,7 @@ zb_place_scan(const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_
     }
     u32 const f = blockIdx.x * ZB_PLACE_CTA + tid;
     u64 v[4] = {0, 0, 0, 0}; u64 cap = 0; u32 st = ZB_OK;
-    if (f < n_frames) { zb_place_values(info[f], dst_sizes, f, v, cap, st); status[f] = st; }
+    if (f < n_frames) { ZbFrameInfo const fi = info[f]; zb_place_values(fi, dst_sizes, f, v, cap, st); status[f] = st; if ((fi.flags & 1) && st == ZB_OK) totals[4] = 1; }
     u64 incl[4];
     #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -417,10 +417,10 @@ __device__ __forceinline__ void zb_warp_copy(u8* dst, const u8* src, u32 n, u32 
 __global__ void __launch_bounds__(256)
 zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
            const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
-           u8* dst, u32 n_frames, ZbDictDev dict, u64 min_cap)
+           u8* dst, u32 first, u32 n_frames, ZbDictDev dict, u64 min_cap)
 {
     u32 const lane = threadIdx.x & 31;
-    u32 const f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u32 const f = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);      // frames [first, n_frames)
     if (f >= n_frames) return;
     if (status[f] != ZB_OK) return;
     ZbFramePlace const pl = place[f];
@@ -529,11 +529,11 @@ zb_execute(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, c
 __global__ void __launch_bounds__(ZB_TILE_WARPS * 32)
 zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
                 const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
-                u8* __restrict__ dst, u32 n_frames, ZbDictDev dict)
+                u8* __restrict__ dst, u32 first, u32 n_frames, ZbDictDev dict)
 {
     extern __shared__ __align__(16) u8 zb_tile[];
     u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 const f = blockIdx.x * ZB_TILE_WARPS + warp;
+    u32 const f = first + blockIdx.x * ZB_TILE_WARPS + warp;                    // frames [first, n_frames)
     if (f >= n_frames) return;
     if (status[f] != ZB_OK) return;
     ZbFramePlace const pl = place[f];
@@ -639,6 +639,42 @@ zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ pla
     }
 }
 
+
+// ===========================================================================
+// content checksum: low 32 bits of XXH64(seed 0) over the regenerated frame (zstd/zstd.c:44260-44277).
+// One lane per checksummed frame (the four accumulators are a serial chain over 32-byte stripes).
+// ===========================================================================
+__device__ static u64 zb_xxh64(const u8* p, u64 len)
+{
+    u64 const P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    auto rotl = [](u64 x, int r) { return (x << r) | (x >> (64 - r)); };
+    auto round = [&](u64 acc, u64 in) { return rotl(acc + in * P2, 31) * P1; };
+    const u8* const end = p + len; u64 h;
+    if (len >= 32) {
+        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        do { v1 = round(v1, zb_rd64(p)); v2 = round(v2, zb_rd64(p + 8)); v3 = round(v3, zb_rd64(p + 16)); v4 = round(v4, zb_rd64(p + 24)); p += 32; } while (p + 32 <= end);
+        h = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+        h = (h ^ round(0, v1)) * P1 + P4; h = (h ^ round(0, v2)) * P1 + P4; h = (h ^ round(0, v3)) * P1 + P4; h = (h ^ round(0, v4)) * P1 + P4;
+    } else h = P5;
+    h += len;
+    while (p + 8 <= end) { h ^= round(0, zb_rd64(p)); h = rotl(h, 27) * P1 + P4; p += 8; }
+    if (p + 4 <= end) { h ^= (u64)zb_rd32(p) * P1; h = rotl(h, 23) * P2 + P3; p += 4; }
+    while (p < end) { h ^= (*p++) * P5; h = rotl(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+__global__ void zb_verify_checksums(const u8* __restrict__ dst, const ZbFramePlace* __restrict__ place, const u64* __restrict__ out_sizes,
+                                    const ZbFrameInfo* __restrict__ info, const u32* __restrict__ ck_expect, u32 first, u32 n_frames,
+                                    u32* __restrict__ status)
+{
+    u32 const f = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    if (status[f] != ZB_OK || !(info[f].flags & 1)) return;
+    u64 const h = zb_xxh64(dst + place[f].dst_off, out_sizes[f]);
+    if ((u32)h != ck_expect[f]) status[f] = ZB_E_CHECKSUM_WRONG;
+}
+
 // ===========================================================================
 // K5: finish -- output segment table + lowest failing frame
 // ===========================================================================
@@ -714,26 +750,34 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
 
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, cudaStream_t st)
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, cudaStream_t st)
 {
     // persistent grid: one CTA of ZB_ENT_WARPS warps per SM, each warp with its own shared-memory table pool
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM); attr_set = true; }
     zb_entropy_decode<<<n_ctas, ZB_ENT_WARPS * 32, ZB_ENT_SMEM, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
-                                                                     work_counter, dict, status, out_sizes);
+                                                                     work_counter, dict, status, out_sizes, ck_expect);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
-                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 n, ZbDictDev dict, cudaStream_t st)
+                       const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st)
 {
-    // frames <= ZB_TILE_CAP bytes are regenerated in shared memory, larger ones straight in HBM/L2
+    // frames [first, end).  Frames <= ZB_TILE_CAP bytes are regenerated in shared memory, larger ones straight in HBM/L2
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM); attr_set = true; }
+    u32 const n = end - first;
     zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
-                                                                                                 seqs, lits, dst, n, dict);
+                                                                                                 seqs, lits, dst, first, end, dict);
     u32 const warps_per_cta = 8;
     zb_execute<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(src, place, status, blocks, seqs,
-                                                                                       lits, dst, n, dict, (u64)ZB_TILE_CAP + 1);
+                                                                                       lits, dst, first, end, dict, (u64)ZB_TILE_CAP + 1);
+}
+
+void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_sizes, const ZbFrameInfo* info, const u32* ck_expect,
+                      u32 first, u32 end, u32* status, cudaStream_t st)
+{
+    u32 const n = end - first;
+    zb_verify_checksums<<<(n + 127) / 128, 128, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
 }
 
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,

@@ -520,7 +520,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             const u8* const in_al = (const u8*)((uintptr_t)in & ~(uintptr_t)15);
             u32 const skew = (u32)(in - in_al);
             u32 const span = skew + n;                                   // bytes of the aligned stream that belong to the block
-            auto chunk_ld = [&](u32 c) { u32 const o = c * 512 + lane * 16; return o < span + 16 ? *(const uint4*)(in_al + o) : make_uint4(0, 0, 0, 0); };
+            auto chunk_ld = [&](u32 c) { u32 const o = c * 512 + lane * 16; return o < span ? *(const uint4*)(in_al + o) : make_uint4(0, 0, 0, 0); };   // aligned 16-byte loads never leave the allocation
             uint4* const ring = (uint4*)S.ring;
             ring[lane] = chunk_ld(0);
             uint4 pend = chunk_ld(1);
@@ -580,6 +580,13 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             u32 d0 = 0, d1 = 0;
             if (alive) { d0 = G.dist[ip]; d1 = ip + 1 < n ? G.dist[ip + 1] : 0; }
             for (;;) {
+                if (alive && mode == 1 && m_start + m_len + 8 > n) {        // the last bytes of a block: finish the match bytewise (no wide reads past the input)
+                    while (m_start + m_len < end && in[m_start + m_len] == in[m_start + m_len - m_off]) m_len++;
+                    u32 const ll = m_start - anchor;
+                    rec[cnt++] = make_uint2(ll | (m_len << 16), ze_off_code(m_off, ll, r0, r1, r2));
+                    ip = m_start + m_len; anchor = ip; mode = 0;
+                    d0 = ip < n ? G.dist[ip] : 0; d1 = ip + 1 < n ? G.dist[ip + 1] : 0;
+                }
                 bool const searching = alive && mode == 0 && ip + 4 <= end && ip < ilimit;   // ... and stops one short of ilimit (:31100-31180)
                 bool const extending = alive && mode == 1;
                 if (!__any_sync(0xFFFFFFFFu, searching || extending)) break;

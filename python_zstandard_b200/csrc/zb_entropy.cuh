@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(ZB_ENT_WARPS * 32)
 zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
                   const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
                   ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
-                  u32* __restrict__ work_counter, ZbDictDev dict, u32* status, u64* __restrict__ out_sizes)
+                  u32* __restrict__ work_counter, ZbDictDev dict, u32* status, u64* __restrict__ out_sizes,
+                  u32* __restrict__ ck_expect)
 {
     extern __shared__ __align__(16) u8 zb_smem[];
     u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -425,6 +426,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                     if (last) {
                         if (h.content_size != ZB_CONTENT_UNKNOWN && out_pos != h.content_size) err = ZB_E_CORRUPTION;
                         else if (h.checksum && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
+                        else if (h.checksum) ck_expect[f] = zb_rd32(s + pos);     // compared with XXH64 of the output by zb_verify_checksums
                         else if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;   // c-ext/decompressor.c:1151-1162
                         done = true;
                     }

@@ -20,6 +20,18 @@ _UNKNOWN = (1 << 64) - 1
 _SIZES_ARE_CAPACITY = 4
 
 
+_EXECUTORS = {}
+
+
+def _executor(workers):
+    """Persistent worker threads (ctypes calls release the GIL, so sub-batches overlap on the device)."""
+    ex = _EXECUTORS.get(workers)
+    if ex is None:
+        from concurrent.futures import ThreadPoolExecutor
+        ex = _EXECUTORS[workers] = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="zb200")
+    return ex
+
+
 def _devices(threads):
     """`threads` of the reference becomes a hint for how many GPUs to spread a batch over:
     <= 1 -> the current device only; -1 -> every visible device (cpu_count() in the reference)."""
@@ -200,6 +212,11 @@ class ZstdDecompressor:
         ctx.check(rc, "zb200_decompress_batch")
         return res
 
+    # sub-batches in flight per device: while one copies its output to the host, the next runs its kernels
+    # and a third uploads its input (PCIe is full duplex; the copies dominate the end-to-end time)
+    PIPELINE_DEPTH = 3
+    SUB_BATCH_INPUT_BYTES = 24 << 20
+
     def _run_contiguous(self, b, n, sizes_bytes, first_index, threads):
         if n == 0:
             return []
@@ -208,16 +225,40 @@ class ZstdDecompressor:
         data = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
         sizes_arr = np.frombuffer(sizes_bytes, dtype=np.uint64) if sizes_bytes is not None else None
         parts = self._split(None, segs[:, 1], _devices(threads))
-        handles = []
+        jobs = []           # (device, slot, lo, hi) in output order
         for dev, (lo, hi) in enumerate(parts):
-            ctx = self._context(dev)
+            nbytes = int(segs[lo:hi, 1].sum())
+            k = max(1, min((hi - lo) // 256 or 1, nbytes // self.SUB_BATCH_INPUT_BYTES))
+            if k < 2:
+                jobs.append((dev, 0, lo, hi))
+                continue
+            for i, (a, c) in enumerate(self._split(None, segs[lo:hi, 1], k)):
+                jobs.append((dev, i % self.PIPELINE_DEPTH, lo + a, lo + c))
+
+        def run(job):
+            dev, slot, lo, hi = job
+            ctx = _native.Context.get(dev, slot)
             sub = np.ascontiguousarray(segs[lo:hi])
             ssz = np.ascontiguousarray(sizes_arr[lo:hi]) if sizes_arr is not None else None
-            handles.append((ctx, lo, self._launch(ctx, data.ctypes.data, sub, hi - lo, ssz)))
+            return ctx, lo, self._launch(ctx, data.ctypes.data, sub, hi - lo, ssz)
+
+        if len(jobs) == 1:
+            handles = [run(jobs[0])]
+        else:
+            handles = list(_executor(self.PIPELINE_DEPTH * len(parts)).map(run, jobs))
         out = []
+        err = None
         for ctx, lo, res in handles:
-            self._raise_item_error(L, res, first_index + lo)
-            out.append(BufferWithSegments._from_result(ctx, res))
+            if err is None:
+                try:
+                    self._raise_item_error(L, res, first_index + lo)
+                    out.append(BufferWithSegments._from_result(ctx, res))
+                except Exception as e:      # lowest failing item wins; free the rest
+                    err = e
+            else:
+                L.zb200_result_free(res)
+        if err is not None:
+            raise err
         return out
 
     def _run_list(self, views, sizes, threads):

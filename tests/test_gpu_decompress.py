@@ -191,3 +191,21 @@ def test_mixed_128k_segments(ref):
     out = zstd.ZstdDecompressor().multi_decompress_to_buffer(zstd.BufferWithSegments(cblob, segs.tobytes()))
     got = np.frombuffer(out._buffers[0]._data, dtype=np.uint8)
     assert np.array_equal(got, blob)
+
+
+def test_content_checksum_is_verified(oracle):
+    """A frame whose stored XXH64 does not match its content is rejected (zstd/zstd.c:44271-44277)."""
+    vec = [v for v in helpers.golden_vectors() if v[0] == "text4k_l3_ck"][0]
+    frame, raw = vec[1], vec[2]
+    d = zstd.ZstdDecompressor()
+    assert d.multi_decompress_to_buffer([frame])[0].tobytes() == raw
+    bad = frame[:-1] + bytes([frame[-1] ^ 0x40])
+    with pytest.raises(zstd.ZstdError, match="error decompressing item 1: Restored data doesn't match checksum"):
+        d.multi_decompress_to_buffer([frame, bad])
+    with pytest.raises(zstd.ZstdError, match="decompression error: Restored data doesn't match checksum"):
+        d.decompress(bad)
+    with pytest.raises(Oracle.Error, match="checksum"):
+        oracle.decompress(bad, len(raw))
+    # a multi-block checksummed frame still verifies
+    big = [v for v in helpers.golden_vectors() if v[0] == "text150k_l3_multiblock"][0]
+    assert d.decompress(big[1]) == big[2]
