@@ -37,6 +37,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to fd 1 from C, so
+# fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def make_batch(n_frames, threads):
     """Synthetic input: n frames of S-text compressed by the UNMODIFIED reference codec at level 3
     (this is the workload generator, outside every timed region)."""
@@ -114,7 +124,7 @@ def run_reference(args, rank, world):
         ref.batch(False, cblob, coff, clens, dst_len=sizes, threads=threads, gather=False)
     dt = (time.perf_counter() - t0) / args.steps
     gbs = len(blob) / dt / 1e9
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -123,7 +133,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "reference",
                          "sample": "the full %d-frame batch per step (oracle/_ref libzstd 1.5.7 -O3, reference batch orchestration)" % N_FRAMES},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -149,6 +159,7 @@ def main():
     from python_zstandard_b200 import _native
 
     torch.cuda.set_device(local)
+    zstd.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_frames = args.frames
@@ -336,7 +347,7 @@ def main():
         "roundtrip": "reference decoder regenerates the input bit-exact",
         "cpu_baseline": {"value": len(cblob_in) / tcb / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference"},
     }
-    print(json.dumps({
+    emit({
         "metric": METRIC, "value": world * U / (dev_ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -361,7 +372,7 @@ def main():
                          "sample": "the same %d-frame batch, best of 3 (oracle/_ref libzstd 1.5.7 -O3 via the "
                                    "reference batch orchestration restated in oracle/ref_batch.c)" % n_frames},
         "clocks": clk.summary(),
-    }))
+    })
     if world > 1:
         dist.destroy_process_group()
 

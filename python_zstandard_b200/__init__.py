@@ -17,6 +17,7 @@ from .dictionary import (ZstdCompressionDict, DICT_TYPE_AUTO, DICT_TYPE_RAWCONTE
                          DICT_TYPE_FULLDICT)
 from .decompressor import ZstdDecompressor, FORMAT_ZSTD1, FORMAT_ZSTD1_MAGICLESS  # noqa: F401
 from .compressor import ZstdCompressor, ZstdCompressionParameters  # noqa: F401
+from ._native import set_device, default_device  # noqa: F401
 
 __version__ = "0.25.0+b200"
 backend = "b200"
@@ -65,10 +66,10 @@ class PinnedBuffer:
     """Page-locked host memory from the codec context's pool.  Data placed here (e.g. the `data`
     of a BufferWithSegments) is DMA-copied to the device at full PCIe rate instead of being staged."""
 
-    def __init__(self, nbytes, device=0):
+    def __init__(self, nbytes, device=None):
         import ctypes as C
         from . import _native
-        self._ctx = _native.Context.get(device)
+        self._ctx = _native.Context.get(_native.default_device() if device is None else device)
         self._ptr = self._ctx.L.zb200_host_alloc(self._ctx.h, nbytes)
         if not self._ptr:
             raise MemoryError("pinned allocation of %d bytes failed" % nbytes)

@@ -148,3 +148,18 @@ class Context:
 
 def device_count():
     return lib().zb200_device_count()
+
+
+_default_device = 0
+
+
+def set_device(index):
+    """Device that single-device calls use (one process per GPU: set it to LOCAL_RANK)."""
+    global _default_device
+    if index < 0 or index >= device_count():
+        raise ValueError("invalid device index %d" % index)
+    _default_device = index
+
+
+def default_device():
+    return _default_device

@@ -102,7 +102,7 @@ class ZstdCompressor:
     def compress(self, data):
         view = memoryview(data)
         buf = np.frombuffer(view, dtype=np.uint8) if view.nbytes else np.zeros(0, dtype=np.uint8)
-        ctx = _native.Context.get(0)
+        ctx = _native.Context.get(_native.default_device())
         L = ctx.L
         seg = np.array([[0, len(buf)]], dtype=np.uint64)
         res = C.c_void_p()
@@ -161,10 +161,11 @@ class ZstdCompressor:
             raise ValueError("source elements are empty")
         lengths = np.array([v.nbytes for v in views], dtype=np.uint64)
         from .decompressor import ZstdDecompressor
-        parts = ZstdDecompressor._split(None, lengths, _devices(threads))
+        devs = _devices(threads)
+        parts = ZstdDecompressor._split(None, lengths, len(devs))
         p = self._params()
-        for dev, (lo, hi) in enumerate(parts):
-            ctx = _native.Context.get(dev)
+        for di, (lo, hi) in enumerate(parts):
+            ctx = _native.Context.get(devs[di])
             k = hi - lo
             arrs = [np.frombuffer(v, dtype=np.uint8) if v.nbytes else np.zeros(0, dtype=np.uint8) for v in views[lo:hi]]
             ptrs = (C.c_void_p * k)(*[a.ctypes.data if len(a) else None for a in arrs])
@@ -179,11 +180,12 @@ class ZstdCompressor:
     def _run(self, base_ptr, segs, threads, keep=()):
         from .decompressor import ZstdDecompressor
         L = _native.lib()
-        parts = ZstdDecompressor._split(None, segs[:, 1], _devices(threads))
+        devs = _devices(threads)
+        parts = ZstdDecompressor._split(None, segs[:, 1], len(devs))
         p = self._params()
         out = []
-        for dev, (lo, hi) in enumerate(parts):
-            ctx = _native.Context.get(dev)
+        for di, (lo, hi) in enumerate(parts):
+            ctx = _native.Context.get(devs[di])
             sub = np.ascontiguousarray(segs[lo:hi])
             res = C.c_void_p()
             with ctx.lock:

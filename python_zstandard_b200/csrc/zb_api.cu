@@ -134,12 +134,12 @@ void* pinned_get(zb200_ctx* c, size_t bytes)
     for (auto& b : c->pinned) if (!b.busy && b.cap >= cls && (!best || b.cap < best->cap)) best = &b;
     if (best) { best->busy = true; return best->p; }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
         // out of pinned memory: release idle blocks and retry once
         for (size_t i = 0; i < c->pinned.size();) {
             if (!c->pinned[i].busy) { cudaFreeHost(c->pinned[i].p); c->pinned.erase(c->pinned.begin() + (long)i); } else i++;
         }
-        if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     }
     c->pinned.push_back({p, cls, true});
     return p;

@@ -753,8 +753,7 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
                        ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, cudaStream_t st)
 {
     // persistent grid: one CTA of ZB_ENT_WARPS warps per SM, each warp with its own shared-memory table pool
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM); attr_set = true; }
+    cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM);      // per device: cheap, so set on every launch
     zb_entropy_decode<<<n_ctas, ZB_ENT_WARPS * 32, ZB_ENT_SMEM, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
                                                                      work_counter, dict, status, out_sizes, ck_expect);
 }
@@ -763,8 +762,7 @@ void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* stat
                        const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st)
 {
     // frames [first, end).  Frames <= ZB_TILE_CAP bytes are regenerated in shared memory, larger ones straight in HBM/L2
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM); attr_set = true; }
+    cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM);      // per device: cheap, so set on every launch
     u32 const n = end - first;
     zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
                                                                                                  seqs, lits, dst, first, end, dict);

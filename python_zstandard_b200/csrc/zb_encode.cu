@@ -1086,8 +1086,7 @@ size_t zb_encode_scratch_bytes() { return sizeof(ZeScratch); }
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
                                void* outs, u32* work_counter, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(zb_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared)); attr_set = true; }
+    cudaFuncSetAttribute(zb_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));      // per device: cheap, so set on every launch
     zb_compress_blocks<<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
                                                                      (ZeBlockOut*)outs, work_counter);
 }

@@ -34,13 +34,14 @@ def _executor(workers):
 
 def _devices(threads):
     """`threads` of the reference becomes a hint for how many GPUs to spread a batch over:
-    <= 1 -> the current device only; -1 -> every visible device (cpu_count() in the reference)."""
+    <= 1 -> the default device only (see set_device); -1 -> every visible device (cpu_count() in the
+    reference).  Returns the list of device indices to use."""
     n = _native.device_count()
+    base = _native.default_device()
     if threads is None or threads == 0 or threads == 1:
-        return 1
-    if threads < 0:
-        return max(1, n)
-    return max(1, min(threads, n))
+        return [base]
+    k = max(1, n) if threads < 0 else max(1, min(threads, n))
+    return [(base + i) % max(n, 1) for i in range(k)]
 
 
 class ZstdDecompressor:
@@ -56,8 +57,8 @@ class ZstdDecompressor:
         self._format = format
         self._ctx = None
 
-    def _context(self, device=0):
-        return _native.Context.get(device)
+    def _context(self, device=None):
+        return _native.Context.get(_native.default_device() if device is None else device)
 
     def memory_size(self):
         return 0
@@ -224,9 +225,11 @@ class ZstdDecompressor:
         segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
         data = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
         sizes_arr = np.frombuffer(sizes_bytes, dtype=np.uint64) if sizes_bytes is not None else None
-        parts = self._split(None, segs[:, 1], _devices(threads))
+        devs = _devices(threads)
+        parts = self._split(None, segs[:, 1], len(devs))
         jobs = []           # (device, slot, lo, hi) in output order
-        for dev, (lo, hi) in enumerate(parts):
+        for di, (lo, hi) in enumerate(parts):
+            dev = devs[di]
             nbytes = int(segs[lo:hi, 1].sum())
             k = max(1, min((hi - lo) // 256 or 1, nbytes // self.SUB_BATCH_INPUT_BYTES))
             if k < 2:
@@ -266,10 +269,11 @@ class ZstdDecompressor:
         n = len(views)
         lengths = np.array([v.nbytes for v in views], dtype=np.uint64)
         sizes_arr = np.frombuffer(sizes, dtype=np.uint64) if sizes is not None else None
-        parts = self._split(None, lengths, _devices(threads))
+        devs = _devices(threads)
+        parts = self._split(None, lengths, len(devs))
         out = []
-        for dev, (lo, hi) in enumerate(parts):
-            ctx = self._context(dev)
+        for di, (lo, hi) in enumerate(parts):
+            ctx = self._context(devs[di])
             k = hi - lo
             arrs = [np.frombuffer(v, dtype=np.uint8) if v.nbytes else np.zeros(0, dtype=np.uint8) for v in views[lo:hi]]
             ptrs = (C.c_void_p * k)(*[a.ctypes.data if len(a) else None for a in arrs])
