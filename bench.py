@@ -248,7 +248,7 @@ def main():
 
     def step_compress():
         r_ = C.c_void_p()
-        rc_ = L.zb200_compress_batch(ctx.h, d_cin.data_ptr(), d_csegs.data_ptr(), cn, C.byref(cparams),
+        rc_ = L.zb200_compress_batch(ctx.h, d_cin.data_ptr(), d_csegs.data_ptr(), cn, C.byref(cparams), None,
                                      _native.SRC_DEVICE | _native.DST_DEVICE, C.byref(r_))
         ctx.check(rc_, "zb200_compress_batch")
         return r_

@@ -102,11 +102,13 @@ typedef struct {
     uint32_t write_content_size;  /* frame content size in header   (ZSTD_c_contentSizeFlag) */
     uint32_t dict_id;             /* dictionary id to record, 0 = none (ZSTD_c_dictIDFlag)   */
 } zb200_cparams;
+/* dict: optional dictionary (the same handle decompression uses; compression sees its last <= 32 KiB of
+ * content as history before every frame, ZSTD_CCtx_refCDict / loadDictionary_byReference, c-ext/compressor.c:1146-1168) */
 int zb200_compress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
-                         const zb200_cparams* params, uint32_t flags, zb200_result** out);
+                         const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out);
 /* same, from an array of independent host buffers (list input, c-ext/compressor.c:1434-1466) */
 int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
-                              const zb200_cparams* params, uint32_t flags, zb200_result** out);
+                              const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out);
 /* ZSTD_compressBound (zstd/zstd.c:4547) */
 uint64_t zb200_compress_bound(uint64_t src_size);
 

@@ -4,7 +4,8 @@ Mirrors c-ext/compressor.c: constructor :88-261 (same keyword arguments, default
 texts), compress() :509-574 and multi_compress_to_buffer() :1341-1504.  The frames come from the
 CUDA block compressor in libzb200 (zb_encode.cu); they are RFC 8878 zstd and decode with any zstd
 decoder, but they are not byte-identical to CPU zstd's -- the parse is this project's own.
-Dictionary *compression* (config 4) is not implemented yet: a dict_data argument raises.
+With dict_data, the last 32 KiB of the dictionary content act as match history in front of every frame
+(the dictionary's entropy tables are not reused; frames stay self-describing).
 """
 import ctypes as C
 
@@ -84,13 +85,15 @@ class ZstdCompressor:
             self._checksum = bool(write_checksum) if write_checksum is not None else False
             self._content_size = bool(write_content_size) if write_content_size is not None else True
             self._write_dict_id = bool(write_dict_id) if write_dict_id is not None else True
-        if dict_data is not None:
-            raise ZstdError("dictionary compression is not implemented by the B200 backend yet")
         self._dict_data = dict_data
         self._threads = threads
 
     def _params(self):
-        return CParams(self._level, int(self._checksum), int(self._content_size), 0)
+        did = self._dict_data.dict_id() if (self._dict_data is not None and self._write_dict_id) else 0
+        return CParams(self._level, int(self._checksum), int(self._content_size), did)
+
+    def _dict(self, ctx):
+        return self._dict_data._ddict(ctx) if self._dict_data is not None else None
 
     def memory_size(self):
         return 0
@@ -108,8 +111,8 @@ class ZstdCompressor:
         res = C.c_void_p()
         p = self._params()
         with ctx.lock:
-            rc = L.zb200_compress_batch(ctx.h, buf.ctypes.data if len(buf) else None, seg.ctypes.data, 1, C.byref(p), 0,
-                                        C.byref(res))
+            rc = L.zb200_compress_batch(ctx.h, buf.ctypes.data if len(buf) else None, seg.ctypes.data, 1, C.byref(p),
+                                        self._dict(ctx), 0, C.byref(res))
         ctx.check(rc, "zb200_compress_batch")
         try:
             n = L.zb200_result_size(res)
@@ -172,7 +175,7 @@ class ZstdCompressor:
             lens = (C.c_size_t * k)(*[len(a) for a in arrs])
             res = C.c_void_p()
             with ctx.lock:
-                rc = L.zb200_compress_batch_ptrs(ctx.h, ptrs, lens, k, C.byref(p), 0, C.byref(res))
+                rc = L.zb200_compress_batch_ptrs(ctx.h, ptrs, lens, k, C.byref(p), self._dict(ctx), 0, C.byref(res))
             ctx.check(rc, "zb200_compress_batch_ptrs")
             results.append(BufferWithSegments._from_result(ctx, res))
         return BufferWithSegmentsCollection(*results)
@@ -189,7 +192,7 @@ class ZstdCompressor:
             sub = np.ascontiguousarray(segs[lo:hi])
             res = C.c_void_p()
             with ctx.lock:
-                rc = L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, hi - lo, C.byref(p), 0, C.byref(res))
+                rc = L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, hi - lo, C.byref(p), self._dict(ctx), 0, C.byref(res))
             ctx.check(rc, "zb200_compress_batch")
             out.append(BufferWithSegments._from_result(ctx, res))
         return out

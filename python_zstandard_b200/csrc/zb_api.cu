@@ -31,7 +31,8 @@ void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
 size_t zb_encode_scratch_bytes();
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, cudaStream_t st);
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, cudaStream_t st);
+void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st);
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
                             u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
 void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
@@ -86,6 +87,7 @@ struct zb200_ctx {
 
 struct zb200_ddict {
     zb200_ctx* ctx; void* d_raw = nullptr; ZbDictDigest* d_digest = nullptr; ZbDictDev dev; size_t size = 0;
+    u16* d_ctable = nullptr; const u8* c_tail = nullptr; u32 c_D = 0;      // compression view: last <= 32 KiB of the content + its hash table
 };
 
 struct zb200_result {
@@ -285,6 +287,13 @@ int zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddic
     v.ll_log = h->ll_log; v.of_log = h->of_log; v.ml_log = h->ml_log;
     v.rep[0] = h->rep[0]; v.rep[1] = h->rep[1]; v.rep[2] = h->rep[2];
     free(h);
+    // compression view (built now, it is one tiny launch)
+    d->c_D = v.content_size < 32768u ? v.content_size : 32768u;
+    d->c_tail = v.content + (v.content_size - d->c_D);
+    if (d->c_D >= 8 && cudaMalloc((void**)&d->d_ctable, 16384 * sizeof(u16)) == cudaSuccess) {
+        zb_launch_dict_table(d->c_tail, d->c_D, d->d_ctable, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    } else d->c_D = 0;
     *out = d;
     return 0;
 }
@@ -294,6 +303,7 @@ void zb200_ddict_free(zb200_ddict* d)
     cudaSetDevice(d->ctx->device);
     if (d->d_raw) cudaFree(d->d_raw);
     if (d->d_digest) cudaFree(d->d_digest);
+    if (d->d_ctable) cudaFree(d->d_ctable);
     delete d;
 }
 uint32_t zb200_ddict_id(const zb200_ddict* d) { return d ? d->dev.dict_id : 0; }
@@ -470,7 +480,7 @@ struct HostSegInfo { u64 first_job; u32 n_jobs, pad; };
 }
 
 static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
-                           const zb200_cparams* params, uint32_t flags, zb200_result** out)
+                           const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
 {
     *out = nullptr;
     if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_compress_batch: bad arguments", cudaSuccess);
@@ -529,7 +539,8 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     CK(cudaMemcpyAsync(ctx->seginfo.p, sinfo.data(), n * sizeof(HostSegInfo), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_counter, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
     if (nj) { KSpan s(ctx, ZB200_K_COMPRESS);
-      zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter, ctx->stream); }
+      zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
+                                dict ? dict->c_tail : nullptr, dict ? dict->c_D : 0, dict ? dict->d_ctable : nullptr, ctx->stream); }
     { KSpan s(ctx, ZB200_K_LAYOUT);
       zb_launch_frame_layout(d_segs, ctx->seginfo.p, ctx->bouts.p, (u32)n, P.write_checksum ? 1 : 0, P.write_content_size ? 1 : 0, P.dict_id,
                              ctx->fsizes.as<u64>(), ctx->out_segs.as<ZbSegment>(), d_total, ctx->stream); }
@@ -556,13 +567,13 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
 }
 
 int zb200_compress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
-                         const zb200_cparams* params, uint32_t flags, zb200_result** out)
+                         const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
 {
-    return compress_common(ctx, src_base, segs, n, params, flags, out);
+    return compress_common(ctx, src_base, segs, n, params, dict, flags, out);
 }
 
 int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
-                              const zb200_cparams* params, uint32_t flags, zb200_result** out)
+                              const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
 {
     *out = nullptr;
     if (!ctx || !srcs || !sizes || n == 0) return fail(ctx, "zb200_compress_batch_ptrs: bad arguments", cudaSuccess);
@@ -572,7 +583,7 @@ int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const siz
     if (!stage) return fail(ctx, "pinned staging allocation", cudaErrorMemoryAllocation);
     std::vector<zb200_segment> segs(n); u64 pos = 0;
     for (size_t i = 0; i < n; i++) { if (sizes[i]) memcpy(stage + pos, srcs[i], sizes[i]); segs[i].offset = pos; segs[i].length = sizes[i]; pos += sizes[i]; }
-    int rc = compress_common(ctx, stage, segs.data(), n, params, flags & ~ZB200_SRC_DEVICE, out);
+    int rc = compress_common(ctx, stage, segs.data(), n, params, dict, flags & ~ZB200_SRC_DEVICE, out);
     pinned_put(ctx, stage);
     return rc;
 }

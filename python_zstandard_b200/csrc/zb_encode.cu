@@ -56,6 +56,10 @@ struct ZeBlockOut { u32 csize; u32 pad; };     // compressed block bytes (header
 
 struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };
 
+// dictionary as the block compressor sees it: the last <= 32 KiB of the dictionary content act as history
+// right before the first block of every frame (restates the "attach dictionary" mode, zstd/zstd.c:25263-25277)
+struct ZeDict { const u8* tail; u32 D; u32 pad; const u16* table; };
+
 // per-CTA scratch in global memory (L2 resident: reused for every block the CTA processes)
 struct ZeScratch {
     u16 dist[ZE_BLOCK + 64];
@@ -464,7 +468,7 @@ __device__ __forceinline__ u32 ze_off_code(u32 off, u32 ll, u32& r0, u32& r1, u3
 __global__ void __launch_bounds__(ZE_THREADS)
 zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs, u32 n_jobs,
                    ZeScratch* __restrict__ scratch, u8* __restrict__ slots, u64 slot_bytes,
-                   ZeBlockOut* __restrict__ outs, u32* __restrict__ work_counter)
+                   ZeBlockOut* __restrict__ outs, u32* __restrict__ work_counter, ZeDict dict)
 {
     extern __shared__ __align__(16) u8 ze_smem_raw[];
     ZeShared& S = *(ZeShared*)ze_smem_raw;
@@ -480,6 +484,9 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         ZeBlockJob const job = jobs[j];
         long long t_phase = clock64();
         const u8* const in = src + job.src_pos;
+        u32 const D = job.first ? dict.D : 0;                       // dictionary bytes that precede this block as history
+        const u8* const dict_end = dict.tail + dict.D;
+        bool const skip0 = job.first && D == 0;                    // without a dictionary the reference never uses position 0 as a match source
         u32 const n = job.size;
         u8* const out = slots + (u64)j * slot_bytes;       // block header (3 bytes) + payload
         __syncthreads();
@@ -508,7 +515,8 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
 
         ZE_MARK(0);
         // ---------------- A: hash links (warp 0); the other warps clear the histograms meanwhile
-        for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = 0xFFFFFFFFu;
+        if (D) { const u32* t32 = (const u32*)dict.table; for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = t32[i]; }
+        else for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = 0xFFFFFFFFu;
         for (u32 i = tid; i < 256; i += ZE_THREADS) S.hist[i] = 0;
         if (tid < 36) S.hLL[tid] = 0; if (tid < 32) S.hOF[tid] = 0; if (tid < 56) S.hML[tid] = 0;
         __syncthreads();
@@ -543,19 +551,20 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     // Two lanes of this step with the same hash are the exception; match.any costs one round per
                     // distinct value, so it only runs when the table itself shows a collision (a lane reads back
                     // somebody else's position from the slot it just wrote).
-                    bool const ins = valid && (p & 0xFFFFu) != 0xFFFFu && (p | (job.first ^ 1u));
-                    if (ins) vhead[h] = (u16)p;
-                    bool const lost = ins && vhead[h] != (u16)p;
-                    int cand = -1;
+                    u32 const pv = p + D;                                        // position in (dictionary tail + block) space
+                    bool const ins = valid && (pv & 0xFFFFu) != 0xFFFFu && !(skip0 && p == 0);
+                    if (ins) vhead[h] = (u16)pv;
+                    bool const lost = ins && vhead[h] != (u16)pv;
+                    int cand = -1;                                                // candidate, in the same space
                     if (__any_sync(0xFFFFFFFFu, lost)) {
                         u32 const m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
                         u32 const lower = m & lt;
-                        if (lower) { int const lsrc = 31 - __clz(lower); cand = pp - ((int)lane - lsrc); if (cand == 0 && job.first) cand = -1; }
-                        else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= pp) cand -= 0x10000; }
-                        if (ins && (m >> lane) == 1u) vhead[h] = (u16)p;          // the highest lane of a group owns the slot
-                    } else if (old != 0xFFFFu) { cand = (int)((p & ~0xFFFFu) | old); if (cand >= pp) cand -= 0x10000; }
+                        if (lower) { int const lsrc = 31 - __clz(lower); cand = (int)pv - ((int)lane - lsrc); if (skip0 && cand == 0) cand = -1; }
+                        else if (old != 0xFFFFu) { cand = (int)((pv & ~0xFFFFu) | old); if (cand >= (int)pv) cand -= 0x10000; }
+                        if (ins && (m >> lane) == 1u) vhead[h] = (u16)pv;         // the highest lane of a group owns the slot
+                    } else if (old != 0xFFFFu) { cand = (int)((pv & ~0xFFFFu) | old); if (cand >= (int)pv) cand -= 0x10000; }
                     u32 d = 0;
-                    if (valid && cand >= 0 && p - (u32)cand <= 65535u) d = p - (u32)cand;
+                    if (valid && cand >= 0 && pv - (u32)cand <= 65535u) d = pv - (u32)cand;
                     if (pp >= 0 && p < n) G.dist[p] = (u16)d;
                 }
             }
@@ -574,14 +583,19 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             u32 const end = alive ? min(u0 + ZE_UNIT, n) : 0;
             u32 const ilimit = n >= 8 ? n - 8 : 0;
             u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
-            if (alive && ip == 0 && job.first) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
+            if (alive && ip == 0 && skip0) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
             uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
             u32 mode = 0, m_start = 0, m_off = 0, m_len = 0;
             u32 d0 = 0, d1 = 0;
             if (alive) { d0 = G.dist[ip]; d1 = ip + 1 < n ? G.dist[ip + 1] : 0; }
             for (;;) {
                 if (alive && mode == 1 && m_start + m_len + 8 > n) {        // the last bytes of a block: finish the match bytewise (no wide reads past the input)
-                    while (m_start + m_len < end && in[m_start + m_len] == in[m_start + m_len - m_off]) m_len++;
+                    while (m_start + m_len < end) {
+                        int const q = (int)(m_start + m_len) - (int)m_off;          // source position (negative: dictionary)
+                        u8 const b = q >= 0 ? in[q] : dict_end[q];
+                        if (in[m_start + m_len] != b) break;
+                        m_len++;
+                    }
                     u32 const ll = m_start - anchor;
                     rec[cnt++] = make_uint2(ll | (m_len << 16), ze_off_code(m_off, ll, r0, r1, r2));
                     ip = m_start + m_len; anchor = ip; mode = 0;
@@ -594,24 +608,30 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 // all loads of the step, unconditional (invalid ones alias the current position) and issued
                 // back to back as raw aligned words; the funnel shifts that consume them come afterwards
                 u64 A = 0, B = 0, C1 = 0, RP = 0, RQ = 0; u32 bka = 0, bkb = 1, d2 = 0, bk_max = 0;
+                u32 capB = 64, capC = 64, capP = 64, capQ = 64;
                 bool has_c1 = false, has_rp = false, has_rq = false, has_bk = false;
                 {
                     u32 const pa = extending ? m_start + m_len : ip;
+                    // candidate positions are block-relative and may be negative: -k means k bytes before the
+                    // dictionary end.  cap* = bytes that may be compared before that region ends.
+                    int const pbi = extending ? (int)pa - (int)m_off : (d0 ? (int)ip - (int)d0 : (int)ip);
                     has_c1 = searching && d1 != 0 && ip + 5 <= end;
-                    has_rp = searching && r0 != 0 && ip + 1 >= r0 && ip + 5 <= end;
-                    has_rq = searching && anchor == ip && r1 != 0 && ip >= r1;
-                    u32 const em = (searching && d0) ? min(4u, min(ip - anchor, ip - d0)) : 0u;   // bytes that may extend the match backwards
+                    has_rp = searching && r0 != 0 && (int)ip + 1 - (int)r0 >= -(int)D && ip + 5 <= end;
+                    has_rq = searching && anchor == ip && r1 != 0 && (int)ip - (int)r1 >= -(int)D;
+                    int const pci = has_c1 ? (int)ip + 1 - (int)d1 : (int)pa;
+                    int const ppi = has_rp ? (int)ip + 1 - (int)r0 : (int)pa;
+                    int const pqi = has_rq ? (int)ip - (int)r1 : (int)pa;
+                    capB = pbi < 0 ? (u32)(-pbi) : 64u; capC = pci < 0 ? (u32)(-pci) : 64u; capP = ppi < 0 ? (u32)(-ppi) : 64u; capQ = pqi < 0 ? (u32)(-pqi) : 64u;
+                    u32 const back_room = pbi >= 0 ? (u32)pbi : D - (u32)(-pbi);          // bytes available before the candidate
+                    u32 const em = (searching && d0) ? min(4u, min(ip - anchor, back_room)) : 0u;   // bytes that may extend the match backwards
                     has_bk = em != 0; bk_max = em;
-                    u32 const pb = extending ? pa - m_off : (d0 ? ip - d0 : ip);
-                    u32 const pc = has_c1 ? ip + 1 - d1 : pa;
-                    u32 const pp = has_rp ? ip + 1 - r0 : pa;
-                    u32 const pq = has_rq ? ip - r1 : pa;
-                    u32 const pk = has_bk ? ip - em : pa;
-                    u32 const pl = has_bk ? ip - d0 - em : pa;
+                    int const pki = has_bk ? (int)ip - (int)em : (int)pa;
+                    int const pli = has_bk ? pbi - (int)em : (int)pa;
                     bool const act = searching || extending;
-                    const u8* const qa = in + (act ? pa : 0); const u8* const qb = in + (act ? pb : 0); const u8* const qc = in + (act ? pc : 0);
-                    const u8* const qp = in + (act ? pp : 0); const u8* const qq = in + (act ? pq : 0);
-                    const u8* const qk = in + (act ? pk : 0); const u8* const ql = in + (act ? pl : 0);
+                    #define ZE_P(x) ((x) >= 0 ? in + (x) : dict_end + (x))
+                    const u8* const qa = in + (act ? pa : 0); const u8* const qb = act ? ZE_P(pbi) : in; const u8* const qc = act ? ZE_P(pci) : in;
+                    const u8* const qp = act ? ZE_P(ppi) : in; const u8* const qq = act ? ZE_P(pqi) : in;
+                    const u8* const qk = act ? ZE_P(pki) : in; const u8* const ql = act ? ZE_P(pli) : in;
                     #define ZE_W(q) ((const u32*)((uintptr_t)(q) & ~(uintptr_t)3))
                     #define ZE_S(q) ((u32)((uintptr_t)(q) & 3) * 8)
                     const u32* const wa = ZE_W(qa); const u32* const wb = ZE_W(qb); const u32* const wc = ZE_W(qc);
@@ -630,8 +650,8 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     u32 const dn = (searching && ip + 2 < n) ? G.dist[ip + 2] : 0;
                     #define ZE_J(x0, x1, x2, q) ((u64)__funnelshift_r(x0, x1, ZE_S(q)) | ((u64)__funnelshift_r(x1, x2, ZE_S(q)) << 32))
                     A = ZE_J(a0, a1, a2, qa); B = ZE_J(b0, b1, b2, qb); C1 = ZE_J(c0, c1, c2, qc); RP = ZE_J(p0, p1, p2, qp); RQ = ZE_J(q0, q1, q2, qq);
-                    if (c_same) C1 = B >> 8;
-                    if (p_same) RP = B >> 8;
+                    if (c_same) { C1 = B >> 8; capC = capB > 0 ? capB - 1 : 0; }
+                    if (p_same) { RP = B >> 8; capP = capB > 0 ? capB - 1 : 0; }
                     bka = __funnelshift_r(k0, k1, ZE_S(qk)) << ((4 - em) * 8 & 31); bkb = __funnelshift_r(l0, l1, ZE_S(ql)) << ((4 - em) * 8 & 31);
                     d2 = dn;
                     if (searching && !d0) B = ~A;
@@ -640,20 +660,20 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 if (searching) {
                     u32 const room = end - ip;
                     bool found = false, sat = false; u32 start = 0, off = 0, len = 0;
-                    if (has_rq && (u32)A == (u32)RQ) {                       // immediate repcode match (ll == 0)
-                        u32 const c = ze_common8(A, RQ); start = ip; off = r1; len = min(c, room); sat = c == 8; found = true;
-                    } else if (has_rp && (u32)(A >> 8) == (u32)RP) {         // repcode match at ip + 1
-                        u32 const c = min(ze_common8(A >> 8, RP & 0x00FFFFFFFFFFFFFFull), 7u);
-                        start = ip + 1; off = r0; len = min(c, room - 1); sat = c == 7; found = true;
-                    } else if (d0 && (u32)A == (u32)B) {
-                        u32 const m0 = ze_common8(A, B);
+                    if (has_rq && capQ >= 4 && (u32)A == (u32)RQ) {          // immediate repcode match (ll == 0)
+                        u32 const c = min(ze_common8(A, RQ), capQ); start = ip; off = r1; len = min(c, room); sat = c == 8 && capQ > 8; found = true;
+                    } else if (has_rp && capP >= 4 && (u32)(A >> 8) == (u32)RP) {   // repcode match at ip + 1
+                        u32 const c = min(min(ze_common8(A >> 8, RP & 0x00FFFFFFFFFFFFFFull), 7u), capP);
+                        start = ip + 1; off = r0; len = min(c, room - 1); sat = c == 7 && capP > 7; found = true;
+                    } else if (d0 && capB >= 4 && (u32)A == (u32)B) {
+                        u32 const m0 = min(ze_common8(A, B), capB);
                         bool skip = false;
-                        if (m0 < 8 && has_c1 && (u32)(A >> 8) == (u32)C1) {  // one-step lazy: clearly longer one byte later?
-                            u32 const m1 = min(ze_common8(A >> 8, C1 & 0x00FFFFFFFFFFFFFFull), 7u);
+                        if (m0 < 8 && has_c1 && capC >= 4 && (u32)(A >> 8) == (u32)C1) {  // one-step lazy: clearly longer one byte later?
+                            u32 const m1 = min(min(ze_common8(A >> 8, C1 & 0x00FFFFFFFFFFFFFFull), 7u), capC);
                             skip = m1 > m0 + 1;
                         }
                         if (!skip) {
-                            start = ip; off = d0; len = min(m0, room); sat = m0 == 8; found = true;
+                            start = ip; off = d0; len = min(m0, room); sat = m0 == 8 && capB > 8; found = true;
                             if (has_bk) {                                    // backward extension, up to 4 bytes
                                 u32 const x = bka ^ bkb; u32 e = x ? ((u32)__clz((int)x) >> 3) : 4u;
                                 e = min(e, bk_max);
@@ -672,9 +692,9 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     }
                 } else if (extending) {
                     u32 const room = end - (m_start + m_len);
-                    u32 const c = ze_common8(A, B); u32 const k = min(c, room);
+                    u32 const c = min(ze_common8(A, B), capB); u32 const k = min(c, room);
                     m_len += k;
-                    if (!(c == 8 && m_start + m_len < end)) { fin = true; f_start = m_start; f_off = m_off; f_len = m_len; }
+                    if (!(c == 8 && capB > 8 && m_start + m_len < end)) { fin = true; f_start = m_start; f_off = m_off; f_len = m_len; }
                 }
                 if (fin) {
                     u32 const ll = f_start - anchor;
@@ -955,6 +975,24 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
 }
 
 // ===========================================================================
+// dictionary hash table: the block compressor's table state after "having seen" the dictionary tail
+// (restates what ZSTD_loadDictionaryContent leaves in the match-state tables, zstd/zstd.c:27900-27990)
+// ===========================================================================
+__global__ void zb_dict_table(const u8* __restrict__ tail, u32 D, u16* __restrict__ table)
+{
+    u32 const lane = threadIdx.x;
+    for (u32 i = lane; i < (1u << ZE_HLOG); i += 32) table[i] = 0xFFFFu;
+    __syncwarp();
+    for (u32 base = 0; base + 4 <= D; base += 32) {
+        u32 const p = base + lane; bool const valid = p + 4 <= D;
+        u32 const h = valid ? ze_hash4((u32)tail[p] | ((u32)tail[p + 1] << 8) | ((u32)tail[p + 2] << 16) | ((u32)tail[p + 3] << 24)) : 0;
+        u32 const m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + lane));
+        if (valid && (m >> lane) == 1u && (p & 0xFFFFu) != 0xFFFFu) table[h] = (u16)p;
+        __syncwarp();
+    }
+}
+
+// ===========================================================================
 // frame layout
 // ===========================================================================
 struct ZeSegInfo { u64 first_job; u32 n_jobs; u32 pad; };
@@ -1083,12 +1121,15 @@ extern "C" {
 
 size_t zb_encode_scratch_bytes() { return sizeof(ZeScratch); }
 
+void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st) { zb_dict_table<<<1, 32, 0, st>>>(tail, D, table); }
+
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, cudaStream_t st)
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, cudaStream_t st)
 {
+    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table;
     cudaFuncSetAttribute(zb_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));      // per device: cheap, so set on every launch
     zb_compress_blocks<<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
-                                                                     (ZeBlockOut*)outs, work_counter);
+                                                                     (ZeBlockOut*)outs, work_counter, dict);
 }
 
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,

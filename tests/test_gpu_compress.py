@@ -156,3 +156,39 @@ def test_ragged_sizes(ref, oracle):
     assert len(res) == len(items)
     for i, d in enumerate(items):
         assert oracle.decompress(res[i].tobytes(), len(d)) == d, i
+
+
+def test_dictionary_compression(ref, oracle):
+    """Config 4: records compressed against a trained dictionary.  The frames carry the dictionary id,
+    decode bit-exact through the reference decoder (with the dictionary) and are far smaller than without
+    it; the size margin against the reference's dictionary compression is stated (we use the dictionary as
+    match history only, not its entropy tables)."""
+    import os
+    from tests import helpers
+    dct = open(os.path.join(helpers.GOLDEN, "dict.bin"), "rb").read()
+    recs = corpus.json_records(700)[500:]
+    d = zstd.ZstdCompressionDict(dct)
+    cctx = zstd.ZstdCompressor(dict_data=d)
+    res = cctx.multi_compress_to_buffer(recs)
+    assert len(res) == len(recs)
+    ours = plain = refsz = 0
+    nodict = zstd.ZstdCompressor().multi_compress_to_buffer(recs)
+    for i, r in enumerate(recs):
+        f = res[i].tobytes()
+        assert ref.decompress(f, len(r), dct) == r, i
+        assert oracle.decompress(f, len(r), dct) == r, i
+        ours += len(f)
+        plain += len(nodict[i])
+        refsz += len(ref.compress(r, level=3, dict_data=dct))
+    assert ours < plain * 0.75                     # the dictionary must pay off
+    assert ours <= refsz * 1.35, (ours, refsz)     # stated margin vs the reference with the same dictionary
+    out = zstd.ZstdDecompressor(dict_data=d).multi_decompress_to_buffer(res)
+    assert [out[i].tobytes() for i in range(len(recs))] == recs
+    # dict id is recorded unless disabled
+    info_frame = res[0].tobytes()
+    assert zstd.ZstdCompressor(dict_data=d, write_dict_id=False).compress(recs[0])[4] & 3 == 0
+    assert info_frame[4] & 3 != 0
+    # a bigger input whose match crosses from the dictionary into the block
+    big = dct[-3000:] + recs[0] * 3
+    f = cctx.compress(big)
+    assert ref.decompress(f, len(big), dct) == big
