@@ -18,7 +18,7 @@
 
 #define ZB_ENT_WARPS      8                       // warps per CTA (one CTA per SM)
 #define ZB_ENT_WS_BYTES   256                     // per-lane workspace (weights / normalized counts)
-#define ZB_ENT_POOL_BYTES (27 * 1024 + 512)       // per-warp pool, workspace included
+#define ZB_ENT_POOL_BYTES (27 * 1024 + 512)       // per-warp pool, workspace included (4 / 6 warps with bigger pools measured slower: 7.1 / 6.3 vs 5.7 ms)
 #define ZB_ENT_LUT_BYTES  512                     // CTA-wide baseline tables (LL_base, ML_base)
 #define ZB_ENT_SMEM       (ZB_ENT_WARPS * ZB_ENT_POOL_BYTES + ZB_ENT_LUT_BYTES)
 
