@@ -180,22 +180,40 @@ class ZstdCompressor:
             results.append(BufferWithSegments._from_result(ctx, res))
         return BufferWithSegmentsCollection(*results)
 
+    PIPELINE_DEPTH = 3
+    SUB_BATCH_INPUT_BYTES = 64 << 20
+
     def _run(self, base_ptr, segs, threads, keep=()):
-        from .decompressor import ZstdDecompressor
+        """Device partition as in the reference (contiguous ranges by bytes), then sub-batches of each range
+        kept in flight on extra contexts so that uploads, kernels and downloads overlap."""
+        from .decompressor import ZstdDecompressor, _executor
         L = _native.lib()
         devs = _devices(threads)
         parts = ZstdDecompressor._split(None, segs[:, 1], len(devs))
         p = self._params()
-        out = []
+        jobs = []
         for di, (lo, hi) in enumerate(parts):
-            ctx = _native.Context.get(devs[di])
+            nbytes = int(segs[lo:hi, 1].sum())
+            k = max(1, min((hi - lo) // 64 or 1, nbytes // self.SUB_BATCH_INPUT_BYTES))
+            if k < 2:
+                jobs.append((devs[di], 0, lo, hi))
+                continue
+            for i, (a, c) in enumerate(ZstdDecompressor._split(None, segs[lo:hi, 1], k)):
+                jobs.append((devs[di], i % self.PIPELINE_DEPTH, lo + a, lo + c))
+
+        def run(job):
+            dev, slot, lo, hi = job
+            ctx = _native.Context.get(dev, slot)
             sub = np.ascontiguousarray(segs[lo:hi])
             res = C.c_void_p()
             with ctx.lock:
                 rc = L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, hi - lo, C.byref(p), self._dict(ctx), 0, C.byref(res))
             ctx.check(rc, "zb200_compress_batch")
-            out.append(BufferWithSegments._from_result(ctx, res))
-        return out
+            return BufferWithSegments._from_result(ctx, res)
+
+        if len(jobs) == 1:
+            return [run(jobs[0])]
+        return list(_executor(self.PIPELINE_DEPTH * len(parts)).map(run, jobs))
 
     # ------------------------------------------------------------------ out of scope (SURVEY.md section 2, row 15)
     def _unsupported(self, *a, **k):

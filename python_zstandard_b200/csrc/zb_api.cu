@@ -21,7 +21,7 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
                      u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, cudaStream_t st);
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, cudaStream_t st);
 void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_sizes, const ZbFrameInfo* info, const u32* ck_expect,
                       u32 first, u32 end, u32* status, cudaStream_t st);
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
@@ -339,10 +339,8 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(cudaMemcpyAsync(totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
-    // persistent entropy grid: one CTA per SM (its shared memory holds the decode tables), fewer if the batch is small
-    u32 ctas = (u32)ctx->sm_count;
-    u32 need_ctas = (nf + 255) / 256;
-    if (ctas > need_ctas) ctas = need_ctas;
+    // persistent entropy grid: one CTA per SM (its shared memory holds the decode tables); trimmed per chunk below
+    u32 const ctas = (u32)ctx->sm_count;
     CK(ctx->blocks.ensure((totals[1] + 1) * sizeof(ZbBlock)));
     CK(ctx->seqs.ensure((totals[2] + 1) * sizeof(ZbSeq)));
     CK(ctx->lits.ensure(totals[3] + 64));
@@ -371,11 +369,14 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     for (u32 k = 0; k < n_chunks; k++) {
         u32 const f0 = cut[k], f1 = cut[k + 1];
         u32* const counter = n_chunks > 1 ? d_counter + 8 + k : d_counter;
-        u32 cc = ctas; { u32 const need = (f1 - f0 + 255) / 256; if (cc > need) cc = need; if (cc == 0) cc = 1; }
+        // frames per warp: large frames carry large decode tables (a 128 KiB block: ~4 KB Huffman + ~5 KB FSE cells per lane)
+        u64 const avg_out = (cpl.size() > 1 && n_chunks > 1 ? (cpl[k + 1].dst_off - cpl[k].dst_off) : totals[0]) / (f1 - f0 ? f1 - f0 : 1);
+        u32 const take = avg_out <= (8u << 10) ? 32u : (avg_out <= (16u << 10) ? 16u : (avg_out <= (32u << 10) ? 8u : (avg_out <= (64u << 10) ? 4u : 3u)));
+        u32 cc = ctas; { u32 const need = (f1 - f0 + 8 * take - 1) / (8 * take); if (cc > need) cc = need; if (cc == 0) cc = 1; }
         { KSpan s(ctx, ZB200_K_ENTROPY);
           zb_launch_entropy(d_src, d_segs, f1, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
-                            ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), ctx->stream); }
+                            ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, ctx->stream); }
         { KSpan s(ctx, ZB200_K_EXECUTE);
           zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), f0, f1, dd, ctx->stream); }
@@ -501,8 +502,12 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
         for (auto& s : hsegs) s.offset -= lo;
         CK(ctx->src.ensure(hi - lo + 64));
         CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
-        CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->segs.p, hsegs.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            std::lock_guard<std::mutex> up(g_upload_mu[ctx->device & 15]);     // stagger sub-batches of different contexts
+            CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->segs.p, hsegs.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
     }
     // block jobs: every <=128 KiB slice of every segment (ZSTD_compress_frameChunk's block loop, zstd/zstd.c:27545)

@@ -750,12 +750,12 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
 
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, cudaStream_t st)
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, cudaStream_t st)
 {
     // persistent grid: one CTA of ZB_ENT_WARPS warps per SM, each warp with its own shared-memory table pool
     cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM);      // per device: cheap, so set on every launch
     zb_entropy_decode<<<n_ctas, ZB_ENT_WARPS * 32, ZB_ENT_SMEM, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
-                                                                     work_counter, dict, status, out_sizes, ck_expect);
+                                                                     work_counter, dict, status, out_sizes, ck_expect, take);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
@@ -782,6 +782,12 @@ void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32
                       u32* first_error, cudaStream_t st)
 {
     zb_finish<<<(n + 255) / 256, 256, 0, st>>>(place, out_sizes, status, n, out_segs, first_error);
+}
+
+void zb_entropy_phase_read(unsigned long long* out8, int reset)
+{
+    cudaMemcpyFromSymbol(out8, g_zb_ent_phase, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_zb_ent_phase, z, sizeof z); }
 }
 
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st)

@@ -143,7 +143,23 @@ __device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, co
     return b.left() == 0;
 }
 
-// all literal streams of a block
+// The four literal streams of a block, interleaved in ONE lane: four independent bit readers advance side by
+// side, so the dependent chain of one stream (table lookup -> bit count -> shift) fills the latency slots of the
+// other three (what HUF_decompress4X1_usingDTable_internal_body does with its four BIT_DStream_t, zstd/zstd.c:39868-39964).
+struct ZbHufLane { ZbBitR b; u8* out; u32 left; };
+
+__device__ __forceinline__ void zb_huf_one(ZbHufLane& h, const u16* cells, u32 log)
+{
+    u32 const c = cells[h.b.peek(log)]; *h.out++ = (u8)c; h.b.skip(c >> 8); h.b.refill(); h.left--;
+}
+// four symbols of one stream -> one aligned 32-bit store
+#define ZB_HUF4(h) do { \
+        u32 const c0_ = cells[h.b.peek(log)]; h.b.skip(c0_ >> 8); \
+        u32 const c1_ = cells[h.b.peek(log)]; h.b.skip(c1_ >> 8); h.b.refill(); \
+        u32 const c2_ = cells[h.b.peek(log)]; h.b.skip(c2_ >> 8); \
+        u32 const c3_ = cells[h.b.peek(log)]; h.b.skip(c3_ >> 8); h.b.refill(); \
+        *(u32*)h.out = (c0_ & 255) | ((c1_ & 255) << 8) | ((c2_ & 255) << 16) | (c3_ << 24); h.out += 4; h.left -= 4; } while (0)
+
 __device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, bool single, const u16* cells, u32 log)
 {
     if (single) return zb_huf_stream2(dstl, regen, p, left, cells, log);
@@ -151,10 +167,26 @@ __device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, 
     u32 const l1 = zb_rd16(p), l2 = zb_rd16(p + 2), l3 = zb_rd16(p + 4), seg = (regen + 3) / 4;
     if (6 + l1 + l2 + l3 > left || seg * 3 > regen) return false;
     u32 const l4 = left - 6 - l1 - l2 - l3;
-    return zb_huf_stream2(dstl, seg, p + 6, l1, cells, log)
-        && zb_huf_stream2(dstl + seg, seg, p + 6 + l1, l2, cells, log)
-        && zb_huf_stream2(dstl + 2 * seg, seg, p + 6 + l1 + l2, l3, cells, log)
-        && zb_huf_stream2(dstl + 3 * seg, regen - 3 * seg, p + 6 + l1 + l2 + l3, l4, cells, log);
+    ZbHufLane h0, h1, h2, h3;
+    if (!h0.b.init(p + 6, l1) || !h1.b.init(p + 6 + l1, l2) || !h2.b.init(p + 6 + l1 + l2, l3) || !h3.b.init(p + 6 + l1 + l2 + l3, l4)) return false;
+    h0.out = dstl; h1.out = dstl + seg; h2.out = dstl + 2 * seg; h3.out = dstl + 3 * seg;
+    h0.left = h1.left = h2.left = seg; h3.left = regen - 3 * seg;
+    // bring every stream's output pointer to a 4-byte boundary
+    while (h0.left && ((uintptr_t)h0.out & 3)) zb_huf_one(h0, cells, log);
+    while (h1.left && ((uintptr_t)h1.out & 3)) zb_huf_one(h1, cells, log);
+    while (h2.left && ((uintptr_t)h2.out & 3)) zb_huf_one(h2, cells, log);
+    while (h3.left && ((uintptr_t)h3.out & 3)) zb_huf_one(h3, cells, log);
+    // main loop: 4 symbols of each of the 4 streams per iteration
+    while (h0.left >= 4 && h1.left >= 4 && h2.left >= 4 && h3.left >= 4) { ZB_HUF4(h0); ZB_HUF4(h1); ZB_HUF4(h2); ZB_HUF4(h3); }
+    while (h0.left >= 4) ZB_HUF4(h0);
+    while (h1.left >= 4) ZB_HUF4(h1);
+    while (h2.left >= 4) ZB_HUF4(h2);
+    while (h3.left >= 4) ZB_HUF4(h3);
+    while (h0.left) zb_huf_one(h0, cells, log);
+    while (h1.left) zb_huf_one(h1, cells, log);
+    while (h2.left) zb_huf_one(h2, cells, log);
+    while (h3.left) zb_huf_one(h3, cells, log);
+    return h0.b.left() == 0 && h1.b.left() == 0 && h2.b.left() == 0 && h3.b.left() == 0;
 }
 
 // Resolve one sequence-table descriptor for this block.  For ZB_SRC_NCOUNT the normalized counts
@@ -178,12 +210,15 @@ __device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 m
     return used;
 }
 
+__device__ unsigned long long g_zb_ent_phase[8];      // summed cycles per phase (lane 0 of every warp), for tuning
+#define ZB_EMARK(k) do { if (lane == 0) { long long const t_ = clock64(); atomicAdd(&g_zb_ent_phase[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
+
 __global__ void __launch_bounds__(ZB_ENT_WARPS * 32)
 zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
                   const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
                   ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
                   u32* __restrict__ work_counter, ZbDictDev dict, u32* status, u64* __restrict__ out_sizes,
-                  u32* __restrict__ ck_expect)
+                  u32* __restrict__ ck_expect, u32 take)
 {
     extern __shared__ __align__(16) u8 zb_smem[];
     u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,11 +233,14 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
 
     for (;;) {
         u32 base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        // `take` frames per warp and grab: 32 for small frames; fewer when frames (hence their tables) are large,
+        // so that a warp holds only as many frames as its table pool serves in one pass and the batch spreads over
+        // more warps and SMs
+        if (lane == 0) base = atomicAdd(work_counter, take);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_frames) return;
         u32 const f = base + lane;
-        bool done = !(f < n_frames) || status[f] != ZB_OK;
+        bool done = lane >= take || !(f < n_frames) || status[f] != ZB_OK;
 
         // ---- per-frame lane state
         const u8* s = src; u64 n = 0; ZbHdr h; ZbFramePlace pl; u32 err = ZB_OK;
@@ -224,8 +262,10 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
         }
         u64 const hist_extra = dict.content_size;
 
+        long long t_ph = clock64();
         // ---- one block per lane per round
         while (__any_sync(0xFFFFFFFFu, !done)) {
+            ZB_EMARK(0);
             ZbBlock B; B.kind = 0; B.regen = 0; B.n_seq = 0; B.n_lit = 0; B.lit_kind = 0; B.lit_byte = 0; B.src_pos = 0; B.seq_pos = seq_i; B.out_pos = out_pos;
             bool comp = false, last = false;
             u32 bsize = 0; const u8* bs = nullptr; const u8* bend = nullptr; const u8* ip = nullptr;
@@ -258,6 +298,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                 } while (0);
                 if (err) { done = true; comp = false; }
             }
+            ZB_EMARK(1);
             // -- B: literals
             bool wantH = false; u32 hlog = 0, hns = 0; u32 rank[13]; const u8* hp = nullptr; u32 hleft = 0;
             if (comp) {
@@ -289,6 +330,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
             if (comp && B.lit_kind == ZB_LIT_SCRATCH && dHuf.kind == ZB_SRC_DICT) {
                 if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, dict.huf, dict.huf_log)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
             }
+            ZB_EMARK(2);
             {   // claim pool space for the Huffman cells, decode; lanes that do not fit wait for the next pass
                 bool pending = wantH;
                 while (__any_sync(0xFFFFFFFFu, pending)) {
@@ -303,6 +345,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                     __syncwarp();
                 }
             }
+            ZB_EMARK(3);
             if (comp && B.lit_kind == ZB_LIT_SCRATCH) lit_i += (L.regen + 15) & ~15u;
             // -- C: sequences section header
             u32 nseq = 0, logLL = 0, logOF = 0, logML = 0, msLL = 0, msOF = 0, msML = 0, needS = 0;
@@ -331,6 +374,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                 } while (0);
                 if (err) { done = true; comp = false; nseq = 0; }
             }
+            ZB_EMARK(4);
             // -- D: build the three tables in the pool and run the sequence stream
             u32 lit_used = 0, produced = 0;
             {
@@ -409,6 +453,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                     __syncwarp();
                 }
             }
+            ZB_EMARK(5);
             // -- E: close the block
             if (!done) {
                 if (comp) {
@@ -434,8 +479,8 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                 if (err) done = true;
             }
         }
-        if (f < n_frames && status[f] == ZB_OK) {
+        if (lane < take && f < n_frames && status[f] == ZB_OK) {
             if (err) { status[f] = err; out_sizes[f] = 0; } else out_sizes[f] = out_pos;
-        } else if (f < n_frames) out_sizes[f] = 0;
+        } else if (lane < take && f < n_frames) out_sizes[f] = 0;
     }
 }
