@@ -371,7 +371,9 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         u32* const counter = n_chunks > 1 ? d_counter + 8 + k : d_counter;
         // frames per warp: large frames carry large decode tables (a 128 KiB block: ~4 KB Huffman + ~5 KB FSE cells per lane)
         u64 const avg_out = (cpl.size() > 1 && n_chunks > 1 ? (cpl[k + 1].dst_off - cpl[k].dst_off) : totals[0]) / (f1 - f0 ? f1 - f0 : 1);
-        u32 const take = avg_out <= (8u << 10) ? 32u : (avg_out <= (16u << 10) ? 16u : (avg_out <= (32u << 10) ? 8u : (avg_out <= (64u << 10) ? 4u : 3u)));
+        u32 take = avg_out <= (8u << 10) ? 32u : (avg_out <= (16u << 10) ? 16u : (avg_out <= (32u << 10) ? 8u : (avg_out <= (64u << 10) ? 4u : 3u)));
+        // small batches: spread the frames over all resident warps rather than filling few warps' lanes
+        { u32 const spread = (f1 - f0 + ctas * 8 - 1) / (ctas * 8); if (take > spread) take = spread ? spread : 1; }
         u32 cc = ctas; { u32 const need = (f1 - f0 + 8 * take - 1) / (8 * take); if (cc > need) cc = need; if (cc == 0) cc = 1; }
         { KSpan s(ctx, ZB200_K_ENTROPY);
           zb_launch_entropy(d_src, d_segs, f1, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
