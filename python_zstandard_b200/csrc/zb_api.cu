@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -157,6 +159,9 @@ bool is_pinned_pool(zb200_ctx* c, const void* p)
     for (auto& b : c->pinned) if ((const char*)p >= (const char*)b.p && (const char*)p < (const char*)b.p + b.cap) return true;
     return false;
 }
+
+bool zb_trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("ZB200_TRACE"); v = (e && *e && *e != '0') ? 1 : 0; } return v == 1; }
+double zb_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 ZbDictDev no_dict() { ZbDictDev d; memset(&d, 0, sizeof d); return d; }
 
@@ -488,6 +493,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     *out = nullptr;
     if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_compress_batch: bad arguments", cudaSuccess);
     cudaSetDevice(ctx->device);
+    double const tr0 = zb_trace_on() ? zb_now_ms() : 0; double tr1 = 0, tr2 = 0;
     zb200_cparams P; if (params) P = *params; else { P.level = 3; P.write_checksum = 0; P.write_content_size = 1; P.dict_id = 0; }
     std::vector<zb200_segment> hsegs;
     const u8* d_src; const ZbSegment* d_segs;
@@ -512,6 +518,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
         }
         d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
     }
+    if (zb_trace_on()) tr1 = zb_now_ms();
     // block jobs: every <=128 KiB slice of every segment (ZSTD_compress_frameChunk's block loop, zstd/zstd.c:27545)
     std::vector<HostJob> jobs; std::vector<HostSegInfo> sinfo(n);
     jobs.reserve(n);
@@ -554,6 +561,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     u64 total = 0;
     CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (zb_trace_on()) tr2 = zb_now_ms();
     CK(ctx->dst.ensure(total + 64));
     { KSpan s(ctx, ZB200_K_FRAMES);
       zb_launch_write_frames(d_src, d_segs, ctx->seginfo.p, ctx->bouts.p, ctx->slots.as<u8>(), slot_bytes, (u32)n, P.write_checksum ? 1 : 0,
@@ -569,6 +577,9 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->prof) fold_spans(ctx);
     ctx->last_scratch = (u64)ctas * zb_encode_scratch_bytes() + nj * slot_bytes;
+    if (zb_trace_on()) { double const tr3 = zb_now_ms();
+        fprintf(stderr, "[zb200] compress ctx %p n=%zu blocks=%zu: start %.3f upload %.2f kernels %.2f frames+download %.2f ms\n",
+                (void*)ctx, n, nj, tr0, tr1 - tr0, tr2 - tr1, tr3 - tr2); }
     *out = res;
     return 0;
 }

@@ -430,20 +430,27 @@ __device__ static u32 ze_huf_write_table(u8* out, const ZeHuf& H, ZeCTable& ct, 
 __device__ unsigned long long g_ze_phase[16];     // summed clock cycles per phase (thread 0 of every CTA), for tuning
 #define ZE_MARK(k) do { if (tid == 0) { long long const t_ = clock64(); atomicAdd(&g_ze_phase[k], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
 struct ZeShared {
-    u16 head[1 << ZE_HLOG];           // A: hash heads.  E: reused as u32 staging by the packers
+    // The hash heads live only in phase A; the entropy-stage tables and staging are first touched in phase D/E, so
+    // the two share storage (36 KB per CTA instead of 51 KB: 6 CTAs per SM instead of 4 -- the kernel is bound by
+    // dependent-instruction latency, so resident warps are throughput).
+    union {
+        u16 head[1 << ZE_HLOG];       // A: hash heads
+        struct {
+            ZeCTable ct[4];           // LL, OF, ML, Huffman-weight table
+            ZeHuf huf;
+            u32 wk[1600];
+            u8 tmp_sym[3][512];
+            u8 lit_hdr_buf[8]; u8 seq_hdr_buf[256];
+            u8 huf_tbl[160];
+        };
+    };
     u32 hist[256];
     u32 hLL[36], hOF[32], hML[56];
-    ZeCTable ct[4];                   // LL, OF, ML, Huffman-weight table
-    ZeHuf huf;
-    u32 wk[1600];
-    u8 tmp_sym[3][512];
     u32 s_warp[8];
     __align__(16) u32 ring[256];      // A: 2 x 512 B input ring
     u16 ucnt[128]; u16 utail[128];
     u32 uoff[128]; u32 ucarry[128];
     u32 nseq, nlit, tail_lit, all_same, lit_mode, lit_hdr, lit_bytes, seq_bytes, stream_bits[4], huf_tbl_bytes, seq_hdr_bytes, use_raw, body;
-    u8 lit_hdr_buf[8]; u8 seq_hdr_buf[256];
-    u8 huf_tbl[160];
 };
 
 __device__ __forceinline__ u32 ze_off_code(u32 off, u32 ll, u32& r0, u32& r1, u32& r2)
@@ -534,6 +541,45 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             ring[lane] = chunk_ld(0);
             uint4 pend = chunk_ld(1);
             u32 const nchunks = (span + 511) / 512;
+            if (!exact) {
+                // Big blocks: a branch-free step (no votes, no same-step resolution: the 32 positions of a step do not
+                // see each other, +0.8 % size in the CPU model tools/enc_model2.c), four steps in flight so that the
+                // shared-memory round trips of one step hide behind the arithmetic of its neighbours.  dist[] is only
+                // a hint (the parse verifies every candidate against the input), so table races cost ratio, not correctness.
+                for (u32 c = 0; c < nchunks; c++) {
+                    ring[((c + 1) & 1) * 32 + lane] = pend;              // chunk c+1 (requested a chunk ago)
+                    pend = chunk_ld(c + 2);
+                    __syncwarp();
+                    #pragma unroll 1
+                    for (u32 k4 = 0; k4 < 16; k4 += 4) {
+                        u32 hh[4], pvv[4]; bool va[4], in_[4];
+                        #pragma unroll
+                        for (u32 u = 0; u < 4; u++) {
+                            u32 const q = c * 512 + (k4 + u) * 32 + lane;
+                            int const pp = (int)q - (int)skew;
+                            u32 const bo = q & 1023;
+                            u32 const w0 = S.ring[bo >> 2], w1 = S.ring[((bo >> 2) + 1) & 255];
+                            u32 const vcur = __funnelshift_r(w0, w1, (bo & 3) * 8);
+                            va[u] = pp >= 0 && (u32)pp + 4 <= n;
+                            pvv[u] = (u32)pp + D;
+                            in_[u] = va[u] && (pvv[u] & 0xFFFFu) != 0xFFFFu && !(skip0 && pp == 0);
+                            hh[u] = va[u] ? ze_hash4(vcur) : 0;
+                        }
+                        u32 oldv[4];
+                        #pragma unroll
+                        for (u32 u = 0; u < 4; u++) {
+                            oldv[u] = va[u] ? vhead[hh[u]] : 0xFFFFu;
+                            if (in_[u]) vhead[hh[u]] = (u16)pvv[u];
+                        }
+                        #pragma unroll
+                        for (u32 u = 0; u < 4; u++) {
+                            int const pp = (int)(c * 512 + (k4 + u) * 32 + lane) - (int)skew;
+                            u32 const d = oldv[u] != 0xFFFFu ? ((pvv[u] - oldv[u]) & 0xFFFFu) : 0u;      // nearest earlier slot owner, mod 2^16
+                            if (pp >= 0 && (u32)pp < n) G.dist[pp] = (u16)d;
+                        }
+                    }
+                }
+            } else
             for (u32 c = 0; c < nchunks; c++) {
                 ring[((c + 1) & 1) * 32 + lane] = pend;                  // chunk c+1 (requested a chunk ago)
                 pend = chunk_ld(c + 2);

@@ -6,6 +6,7 @@ The work itself runs as CUDA kernels through libzb200 (include/zb200.h); there i
 Streaming objects (stream_reader, copy_stream, ...) are out of scope for this tier.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -215,54 +216,53 @@ class ZstdDecompressor:
 
     # sub-batches in flight per device: while one copies its output to the host, the next runs its kernels
     # and a third uploads its input (PCIe is full duplex; the copies dominate the end-to-end time)
-    PIPELINE_DEPTH = 3
-    SUB_BATCH_INPUT_BYTES = 24 << 20
+    PIPELINE_DEPTH = int(os.environ.get("ZB200_PIPELINE_DEPTH", "4"))
+    SUB_BATCH_INPUT_BYTES = int(os.environ.get("ZB200_SUB_BATCH_MB", "24")) << 20
 
     def _run_contiguous(self, b, n, sizes_bytes, first_index, threads):
         if n == 0:
             return []
         L = _native.lib()
         segs = np.frombuffer(b._segments, dtype=np.uint64).reshape(-1, 2)
+        lens = np.ascontiguousarray(segs[:, 1])
         data = np.frombuffer(b._data, dtype=np.uint8) if b.size else np.zeros(1, dtype=np.uint8)
         sizes_arr = np.frombuffer(sizes_bytes, dtype=np.uint64) if sizes_bytes is not None else None
         devs = _devices(threads)
-        parts = self._split(None, segs[:, 1], len(devs))
+        parts = self._split(None, lens, len(devs))
+        depth = self.PIPELINE_DEPTH
         jobs = []           # (device, slot, lo, hi) in output order
         for di, (lo, hi) in enumerate(parts):
             dev = devs[di]
-            nbytes = int(segs[lo:hi, 1].sum())
+            nbytes = int(lens[lo:hi].sum())
             k = max(1, min((hi - lo) // 256 or 1, nbytes // self.SUB_BATCH_INPUT_BYTES))
             if k < 2:
                 jobs.append((dev, 0, lo, hi))
                 continue
-            for i, (a, c) in enumerate(self._split(None, segs[lo:hi, 1], k)):
-                jobs.append((dev, i % self.PIPELINE_DEPTH, lo + a, lo + c))
+            for i, (a, c) in enumerate(self._split(None, lens[lo:hi], k)):
+                jobs.append((dev, i % depth, lo + a, lo + c))
 
         def run(job):
+            # everything per sub-batch happens on the worker (launch, error lookup, wrapping the result) so that
+            # it overlaps the other sub-batches' device work; errors are returned, the lowest item wins below
             dev, slot, lo, hi = job
             ctx = _native.Context.get(dev, slot)
             sub = np.ascontiguousarray(segs[lo:hi])
             ssz = np.ascontiguousarray(sizes_arr[lo:hi]) if sizes_arr is not None else None
-            return ctx, lo, self._launch(ctx, data.ctypes.data, sub, hi - lo, ssz)
+            res = self._launch(ctx, data.ctypes.data, sub, hi - lo, ssz)
+            try:
+                self._raise_item_error(L, res, first_index + lo)
+                return BufferWithSegments._from_result(ctx, res)
+            except Exception as e:
+                return e
 
         if len(jobs) == 1:
             handles = [run(jobs[0])]
         else:
-            handles = list(_executor(self.PIPELINE_DEPTH * len(parts)).map(run, jobs))
-        out = []
-        err = None
-        for ctx, lo, res in handles:
-            if err is None:
-                try:
-                    self._raise_item_error(L, res, first_index + lo)
-                    out.append(BufferWithSegments._from_result(ctx, res))
-                except Exception as e:      # lowest failing item wins; free the rest
-                    err = e
-            else:
-                L.zb200_result_free(res)
-        if err is not None:
-            raise err
-        return out
+            handles = list(_executor(depth * len(parts)).map(run, jobs))
+        for h in handles:
+            if isinstance(h, Exception):
+                raise h
+        return handles
 
     def _run_list(self, views, sizes, threads):
         L = _native.lib()

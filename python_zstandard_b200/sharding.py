@@ -14,11 +14,15 @@ def split_ranges(lengths, parts):
     if parts <= 1 or n < 2:
         return [(0, n)]
     parts = min(parts, n)
-    cum = np.cumsum(lengths)
+    cum = np.cumsum(lengths, dtype=np.uint64)
     total = int(cum[-1])
+    # one vectorised search for all targets (same dtype as `cum`: a Python int would make numpy convert the
+    # whole array on every call)
+    targets = np.array([total * p // parts for p in range(1, parts)], dtype=np.uint64)
+    found = np.searchsorted(cum, targets, side="left")
     cuts = [0]
     for p in range(1, parts):
-        k = int(np.searchsorted(cum, total * p // parts, side="left")) + 1
+        k = int(found[p - 1]) + 1
         k = min(max(k, cuts[-1] + 1), n - (parts - p))
         cuts.append(k)
     cuts.append(n)
