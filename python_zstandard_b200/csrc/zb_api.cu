@@ -33,7 +33,8 @@ void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
 size_t zb_encode_scratch_bytes();
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, cudaStream_t st);
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table,
+                               const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st);
 void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st);
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
                             u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
@@ -68,6 +69,7 @@ struct zb200_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // device->host copies of finished chunks, overlapping later chunks' kernels
     cudaEvent_t chunk_ev[64] = {nullptr};
+    unsigned long long* h_progress = nullptr;    // pinned: the byte counts the chunked upload publishes to the compress kernel
     std::string last_error;
     int sm_count = 148;
     // device arenas (grow-only)
@@ -188,6 +190,7 @@ int zb200_ctx_create(int device, zb200_ctx** out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaHostAlloc((void**)&ctx->h_progress, 64 * sizeof(unsigned long long), cudaHostAllocPortable);
     zb_launch_default_tables(ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -1; }
     *out = ctx;
@@ -207,6 +210,7 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->h_progress) cudaFreeHost(ctx->h_progress);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -497,6 +501,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     zb200_cparams P; if (params) P = *params; else { P.level = 3; P.write_checksum = 0; P.write_content_size = 1; P.dict_id = 0; }
     std::vector<zb200_segment> hsegs;
     const u8* d_src; const ZbSegment* d_segs;
+    const u8* up_src = nullptr; u64 up_bytes = 0;          // host input to upload while the kernel runs
     if (flags & ZB200_SRC_DEVICE) {
         hsegs.resize(n);
         CK(cudaMemcpyAsync(hsegs.data(), segs, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
@@ -508,14 +513,12 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
         for (size_t i = 0; i < n; i++) { if (segs[i].offset < lo) lo = segs[i].offset; if (segs[i].offset + segs[i].length > hi) hi = segs[i].offset + segs[i].length; }
         if (hi < lo) { lo = hi = 0; }
         for (auto& s : hsegs) s.offset -= lo;
-        CK(ctx->src.ensure(hi - lo + 64));
+        CK(ctx->src.ensure(hi - lo + 512));
         CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
-        {
-            std::lock_guard<std::mutex> up(g_upload_mu[ctx->device & 15]);     // stagger sub-batches of different contexts
-            CK(cudaMemcpyAsync(ctx->src.p, (const u8*)src_base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->segs.p, hsegs.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-        }
+        CK(cudaMemcpyAsync(ctx->segs.p, hsegs.data(), n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        // the input itself is uploaded in chunks on the copy stream AFTER the block kernel has been launched: the kernel
+        // waits per block for the bytes it needs (ZeUpload), so the upload hides behind the compression of earlier blocks
+        up_src = (const u8*)src_base + lo; up_bytes = hi - lo;
         d_src = ctx->src.as<u8>(); d_segs = ctx->segs.as<ZbSegment>();
     }
     if (zb_trace_on()) tr1 = zb_now_ms();
@@ -548,19 +551,40 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     CK(ctx->small.ensure(256));
     u64* d_total = ctx->small.as<u64>();
     u32* d_counter = (u32*)(d_total + 8);
-    u32 zero = 0;
     if (nj) CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(HostJob), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->seginfo.p, sinfo.data(), n * sizeof(HostSegInfo), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_counter, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_counter, 0, 64, ctx->stream));                       // work counter, upload status, upload progress
+    u32* const d_upstatus = d_counter + 1;
+    unsigned long long* const d_progress = (unsigned long long*)(d_counter + 4);
+    bool const overlap_upload = up_bytes != 0 && nj != 0 && ctx->h_progress != nullptr;
+    if (up_bytes && !overlap_upload) CK(cudaMemcpyAsync(ctx->src.p, up_src, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (overlap_upload) { CK(cudaEventRecord(ctx->chunk_ev[0], ctx->stream)); CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0)); }
     if (nj) { KSpan s(ctx, ZB200_K_COMPRESS);
       zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
-                                dict ? dict->c_tail : nullptr, dict ? dict->c_D : 0, dict ? dict->d_ctable : nullptr, ctx->stream); }
+                                dict ? dict->c_tail : nullptr, dict ? dict->c_D : 0, dict ? dict->d_ctable : nullptr,
+                                overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, ctx->stream); }
+    if (overlap_upload) {
+        // <= 48 chunks of >= 4 MiB; after each chunk the copy engine also writes the new byte count next to the work counter
+        u64 chunk = (up_bytes + 47) / 48; if (chunk < ((u64)4 << 20)) chunk = (u64)4 << 20; chunk = (chunk + 255) & ~(u64)255;
+        u32 k = 0;
+        for (u64 pos = 0; pos < up_bytes; pos += chunk, k++) {
+            u64 const len = up_bytes - pos < chunk ? up_bytes - pos : chunk;
+            CK(cudaMemcpyAsync((u8*)ctx->src.p + pos, up_src + pos, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ctx->h_progress[k] = pos + len;
+            CK(cudaMemcpyAsync(d_progress, &ctx->h_progress[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        // the layout kernels read the input again (raw blocks): they wait for the whole upload, whatever order the segments came in
+        CK(cudaEventRecord(ctx->chunk_ev[1], ctx->copy_stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[1], 0));
+    }
     { KSpan s(ctx, ZB200_K_LAYOUT);
       zb_launch_frame_layout(d_segs, ctx->seginfo.p, ctx->bouts.p, (u32)n, P.write_checksum ? 1 : 0, P.write_content_size ? 1 : 0, P.dict_id,
                              ctx->fsizes.as<u64>(), ctx->out_segs.as<ZbSegment>(), d_total, ctx->stream); }
-    u64 total = 0;
+    u64 total = 0; u32 upstatus = 0;
     CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&upstatus, d_upstatus, sizeof upstatus, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (overlap_upload) CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (upstatus) return fail(ctx, "zb200_compress_batch: the input upload did not complete", cudaErrorUnknown);
     if (zb_trace_on()) tr2 = zb_now_ms();
     CK(ctx->dst.ensure(total + 64));
     { KSpan s(ctx, ZB200_K_FRAMES);
