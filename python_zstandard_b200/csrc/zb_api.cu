@@ -23,7 +23,7 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
                      u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, cudaStream_t st);
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, u32 warps, cudaStream_t st);
 void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_sizes, const ZbFrameInfo* info, const u32* ck_expect,
                       u32 first, u32 end, u32* status, cudaStream_t st);
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
@@ -380,14 +380,15 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         u32* const counter = n_chunks > 1 ? d_counter + 8 + k : d_counter;
         // frames per warp: large frames carry large decode tables (a 128 KiB block: ~4 KB Huffman + ~5 KB FSE cells per lane)
         u64 const avg_out = (cpl.size() > 1 && n_chunks > 1 ? (cpl[k + 1].dst_off - cpl[k].dst_off) : totals[0]) / (f1 - f0 ? f1 - f0 : 1);
+        u32 const EW = avg_out <= (8u << 10) ? 8u : 7u;          // warps per CTA: see zb_entropy.cuh
         u32 take = avg_out <= (8u << 10) ? 32u : (avg_out <= (16u << 10) ? 16u : (avg_out <= (32u << 10) ? 8u : (avg_out <= (64u << 10) ? 4u : 3u)));
         // small batches: spread the frames over all resident warps rather than filling few warps' lanes
-        { u32 const spread = (f1 - f0 + ctas * 8 - 1) / (ctas * 8); if (take > spread) take = spread ? spread : 1; }
-        u32 cc = ctas; { u32 const need = (f1 - f0 + 8 * take - 1) / (8 * take); if (cc > need) cc = need; if (cc == 0) cc = 1; }
+        { u32 const spread = (f1 - f0 + ctas * EW - 1) / (ctas * EW); if (take > spread) take = spread ? spread : 1; }
+        u32 cc = ctas; { u32 const need = (f1 - f0 + EW * take - 1) / (EW * take); if (cc > need) cc = need; if (cc == 0) cc = 1; }
         { KSpan s(ctx, ZB200_K_ENTROPY);
           zb_launch_entropy(d_src, d_segs, f1, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
-                            ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, ctx->stream); }
+                            ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, EW, ctx->stream); }
         { KSpan s(ctx, ZB200_K_EXECUTE);
           zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), f0, f1, dd, ctx->stream); }

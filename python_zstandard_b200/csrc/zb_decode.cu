@@ -704,7 +704,7 @@ __global__ void zb_digest_dict(const u8* __restrict__ dict, u32 n, ZbDictDigest*
         __align__(16) u8 ws[256]; u32 rank[13], log, nsym;
         u32 const used = zb_huf_weights(ws, p, (u32)(end - p), log, nsym, rank);
         if (!used) { out->status = ZB_E_DICT_CORRUPTED; return; }
-        zb_huf_fill(out->huf, ws, log, nsym, rank);
+        zb_huf_fill(out->huf, ws, log, nsym, rank, 0, 0);          // the digest keeps the full table (read in place from global memory)
         out->huf_log = log; p += used;
     }
     short norm[64]; u32 mx, log, used;
@@ -750,12 +750,18 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
 
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
-                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, cudaStream_t st)
+                       ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, u32 warps, cudaStream_t st)
 {
-    // persistent grid: one CTA of ZB_ENT_WARPS warps per SM, each warp with its own shared-memory table pool
-    cudaFuncSetAttribute(zb_entropy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM);      // per device: cheap, so set on every launch
-    zb_entropy_decode<<<n_ctas, ZB_ENT_WARPS * 32, ZB_ENT_SMEM, st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
-                                                                     work_counter, dict, status, out_sizes, ck_expect, take);
+    // persistent grid: one CTA of `warps` (7 or 8) warps per SM, each warp with its own shared-memory table pool
+    if (warps == 8) {
+        cudaFuncSetAttribute(zb_entropy_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM(8));      // per device: cheap, so set on every launch
+        zb_entropy_decode<8><<<n_ctas, 8 * 32, ZB_ENT_SMEM(8), st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
+                                                                    work_counter, dict, status, out_sizes, ck_expect, take);
+    } else {
+        cudaFuncSetAttribute(zb_entropy_decode<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM(7));
+        zb_entropy_decode<7><<<n_ctas, 7 * 32, ZB_ENT_SMEM(7), st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
+                                                                    work_counter, dict, status, out_sizes, ck_expect, take);
+    }
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,

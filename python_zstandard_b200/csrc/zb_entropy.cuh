@@ -16,11 +16,15 @@
 // ZSTD_decodeSeqHeaders (:46328), ZSTD_buildFSETable_body (:46118), ZSTD_decodeSequence (:46862).
 #pragma once
 
-#define ZB_ENT_WARPS      8                       // warps per CTA (one CTA per SM)
+// Warps per CTA (one CTA per SM) is a template parameter: each warp owns a shared-memory pool of
+// (227 KB - LUT) / warps.  Level-3 frames of a few KiB carry three 64-cell FSE tables (768 B per lane) and a ~600 B
+// Huffman table: 8 warps (28.9 KB pools) serve them best; frames of 16 KiB and more have larger tables and run faster
+// with 7 warps and 33 KB pools (measured 7.2 vs 8.8 ms on 65536 x 16 KiB), since a lane whose tables do not fit waits
+// for a second pass.
 #define ZB_ENT_WS_BYTES   256                     // per-lane workspace (weights / normalized counts)
-#define ZB_ENT_POOL_BYTES (27 * 1024 + 512)       // per-warp pool, workspace included (4 / 6 warps with bigger pools measured slower: 7.1 / 6.3 vs 5.7 ms)
+#define ZB_ENT_POOL_BYTES(W) ((((227 * 1024 - 512) / (W))) & ~15)
 #define ZB_ENT_LUT_BYTES  512                     // CTA-wide baseline tables (LL_base, ML_base)
-#define ZB_ENT_SMEM       (ZB_ENT_WARPS * ZB_ENT_POOL_BYTES + ZB_ENT_LUT_BYTES)
+#define ZB_ENT_SMEM(W)    ((W) * ZB_ENT_POOL_BYTES(W) + ZB_ENT_LUT_BYTES)
 
 // where a table comes from; enough to rebuild it for a later block
 enum : u32 { ZB_SRC_NONE = 0, ZB_SRC_PREDEF = 1, ZB_SRC_RLE = 2, ZB_SRC_NCOUNT = 3, ZB_SRC_DICT = 4 };
@@ -111,13 +115,33 @@ __device__ static u32 zb_huf_weights(u8* ws, const u8* s, u32 n, u32& out_log, u
     return hdr + 1;
 }
 
-// fill the decode cells (u16: symbol | nbBits << 8) from the nibble weights (HUF_readDTableX1_wksp layout)
-__device__ static void zb_huf_fill(u16* cells, const u8* ws, u32 log, u32 nsym, const u32* rank)
+// Split Huffman decode table.  The reference's table (HUF_readDTableX1_wksp, zstd/zstd.c:39651) has 2^log cells; at one
+// frame per lane that is the shared-memory hog (2 KB at log 10: 13 of 32 lanes fit a warp's pool).  Cells are laid out by
+// ascending weight, i.e. longest codes first, and every weight's range starts at a multiple of its cell run (Kraft
+// equality), so above the codes longer than ZB_HUF_COARSE bits a cell depends only on the top ZB_HUF_COARSE bits of
+// the index.  Only the first T cells (codes longer than 8 bits: the rare symbols) are kept at full resolution; the
+// rest is one cell per 2^shift indices:   cell(v) = v < T ? fine[v] : coarse[v >> shift].
+// A 4 KiB text frame needs ~600 bytes instead of 2 KB, so all 32 lanes of a warp decode in one pass.
+#define ZB_HUF_COARSE 8u
+struct ZbHufTab { const u16* cells; u32 log, shift, T, base; };       // base = index of coarse[0] in cells
+__device__ __forceinline__ void zb_huf_shape(u32 log, const u32* rank, u32& shift, u32& T, u32& base, u32& bytes)
+{
+    shift = log > ZB_HUF_COARSE ? log - ZB_HUF_COARSE : 0u;
+    T = 0; for (u32 wt = 1; wt <= shift; wt++) T += rank[wt] << (wt - 1);
+    base = (T + 3u) & ~3u;
+    bytes = 2u * (base + (1u << (log - shift)));
+}
+__device__ __forceinline__ ZbHufTab zb_huf_full(const u16* cells, u32 log) { ZbHufTab t; t.cells = cells; t.log = log; t.shift = 0; t.T = 0; t.base = 0; return t; }
+#define ZB_HCELL(t, v) ((t).cells[(v) < (t).T ? (v) : (t).base + ((v) >> (t).shift)])
+
+// fill the decode cells (u16: symbol | nbBits << 8) from the nibble weights
+__device__ static void zb_huf_fill(u16* cells, const u8* ws, u32 log, u32 nsym, const u32* rank, u32 shift, u32 base)
 {
     u32 start[13]; { u32 p = 0; for (u32 wt = 1; wt <= 12; wt++) { start[wt] = p; p += wt <= log ? (rank[wt] << (wt - 1)) : 0; } }
     for (u32 i = 0; i < nsym; i++) {
         u32 const wt = (ws[i >> 1] >> ((i & 1) * 4)) & 15; if (!wt) continue;
-        u32 const len = 1u << (wt - 1), p = start[wt]; start[wt] = p + len;
+        u32 len = 1u << (wt - 1), p = start[wt]; start[wt] = p + len;
+        if (wt > shift) { len >>= shift; p = base + (p >> shift); }       // coarse part: one cell per 2^shift indices
         u32 const cell = i | ((log + 1 - wt) << 8);
         if (len >= 4) { u64 const v = cell * 0x0001000100010001ull; u64* q = (u64*)(cells + p); for (u32 k = 0; k < len / 4; k++) q[k] = v; }
         else if (len == 2) *(u32*)(cells + p) = cell * 0x00010001u;
@@ -126,20 +150,21 @@ __device__ static void zb_huf_fill(u16* cells, const u8* ws, u32 log, u32 nsym, 
 }
 
 // one Huffman stream -> n_out bytes at out (global scratch), 4 symbols per 32-bit store where aligned
-__device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, const u16* cells, u32 log)
+__device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, ZbHufTab const t)
 {
     ZbBitR b;
     if (!b.init(s, n)) return false;
+    u32 const log = t.log;
     u32 i = 0;
-    while (i < n_out && ((uintptr_t)(out + i) & 3)) { u32 c = cells[b.peek(log)]; out[i++] = (u8)c; b.skip(c >> 8); b.refill(); }
+    while (i < n_out && ((uintptr_t)(out + i) & 3)) { u32 v = b.peek(log); u32 c = ZB_HCELL(t, v); out[i++] = (u8)c; b.skip(c >> 8); b.refill(); }
     for (; i + 4 <= n_out; i += 4) {
-        u32 c0 = cells[b.peek(log)]; b.skip(c0 >> 8);
-        u32 c1 = cells[b.peek(log)]; b.skip(c1 >> 8); b.refill();
-        u32 c2 = cells[b.peek(log)]; b.skip(c2 >> 8);
-        u32 c3 = cells[b.peek(log)]; b.skip(c3 >> 8); b.refill();
+        u32 v0 = b.peek(log); u32 c0 = ZB_HCELL(t, v0); b.skip(c0 >> 8);
+        u32 v1 = b.peek(log); u32 c1 = ZB_HCELL(t, v1); b.skip(c1 >> 8); b.refill();
+        u32 v2 = b.peek(log); u32 c2 = ZB_HCELL(t, v2); b.skip(c2 >> 8);
+        u32 v3 = b.peek(log); u32 c3 = ZB_HCELL(t, v3); b.skip(c3 >> 8); b.refill();
         *(u32*)(out + i) = (c0 & 255) | ((c1 & 255) << 8) | ((c2 & 255) << 16) | (c3 << 24);
     }
-    for (; i < n_out; i++) { u32 c = cells[b.peek(log)]; out[i] = (u8)c; b.skip(c >> 8); b.refill(); }
+    for (; i < n_out; i++) { u32 v = b.peek(log); u32 c = ZB_HCELL(t, v); out[i] = (u8)c; b.skip(c >> 8); b.refill(); }
     return b.left() == 0;
 }
 
@@ -148,21 +173,21 @@ __device__ static bool zb_huf_stream2(u8* out, u32 n_out, const u8* s, u32 n, co
 // other three (what HUF_decompress4X1_usingDTable_internal_body does with its four BIT_DStream_t, zstd/zstd.c:39868-39964).
 struct ZbHufLane { ZbBitR b; u8* out; u32 left; };
 
-__device__ __forceinline__ void zb_huf_one(ZbHufLane& h, const u16* cells, u32 log)
+__device__ __forceinline__ void zb_huf_one(ZbHufLane& h, ZbHufTab const& t)
 {
-    u32 const c = cells[h.b.peek(log)]; *h.out++ = (u8)c; h.b.skip(c >> 8); h.b.refill(); h.left--;
+    u32 const v = h.b.peek(t.log); u32 const c = ZB_HCELL(t, v); *h.out++ = (u8)c; h.b.skip(c >> 8); h.b.refill(); h.left--;
 }
 // four symbols of one stream -> one aligned 32-bit store
 #define ZB_HUF4(h) do { \
-        u32 const c0_ = cells[h.b.peek(log)]; h.b.skip(c0_ >> 8); \
-        u32 const c1_ = cells[h.b.peek(log)]; h.b.skip(c1_ >> 8); h.b.refill(); \
-        u32 const c2_ = cells[h.b.peek(log)]; h.b.skip(c2_ >> 8); \
-        u32 const c3_ = cells[h.b.peek(log)]; h.b.skip(c3_ >> 8); h.b.refill(); \
+        u32 const v0_ = h.b.peek(t.log); u32 const c0_ = ZB_HCELL(t, v0_); h.b.skip(c0_ >> 8); \
+        u32 const v1_ = h.b.peek(t.log); u32 const c1_ = ZB_HCELL(t, v1_); h.b.skip(c1_ >> 8); h.b.refill(); \
+        u32 const v2_ = h.b.peek(t.log); u32 const c2_ = ZB_HCELL(t, v2_); h.b.skip(c2_ >> 8); \
+        u32 const v3_ = h.b.peek(t.log); u32 const c3_ = ZB_HCELL(t, v3_); h.b.skip(c3_ >> 8); h.b.refill(); \
         *(u32*)h.out = (c0_ & 255) | ((c1_ & 255) << 8) | ((c2_ & 255) << 16) | (c3_ << 24); h.out += 4; h.left -= 4; } while (0)
 
-__device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, bool single, const u16* cells, u32 log)
+__device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, bool single, ZbHufTab const t)
 {
-    if (single) return zb_huf_stream2(dstl, regen, p, left, cells, log);
+    if (single) return zb_huf_stream2(dstl, regen, p, left, t);
     if (left < 10) return false;
     u32 const l1 = zb_rd16(p), l2 = zb_rd16(p + 2), l3 = zb_rd16(p + 4), seg = (regen + 3) / 4;
     if (6 + l1 + l2 + l3 > left || seg * 3 > regen) return false;
@@ -172,20 +197,20 @@ __device__ static bool zb_huf_block(u8* dstl, u32 regen, const u8* p, u32 left, 
     h0.out = dstl; h1.out = dstl + seg; h2.out = dstl + 2 * seg; h3.out = dstl + 3 * seg;
     h0.left = h1.left = h2.left = seg; h3.left = regen - 3 * seg;
     // bring every stream's output pointer to a 4-byte boundary
-    while (h0.left && ((uintptr_t)h0.out & 3)) zb_huf_one(h0, cells, log);
-    while (h1.left && ((uintptr_t)h1.out & 3)) zb_huf_one(h1, cells, log);
-    while (h2.left && ((uintptr_t)h2.out & 3)) zb_huf_one(h2, cells, log);
-    while (h3.left && ((uintptr_t)h3.out & 3)) zb_huf_one(h3, cells, log);
+    while (h0.left && ((uintptr_t)h0.out & 3)) zb_huf_one(h0, t);
+    while (h1.left && ((uintptr_t)h1.out & 3)) zb_huf_one(h1, t);
+    while (h2.left && ((uintptr_t)h2.out & 3)) zb_huf_one(h2, t);
+    while (h3.left && ((uintptr_t)h3.out & 3)) zb_huf_one(h3, t);
     // main loop: 4 symbols of each of the 4 streams per iteration
     while (h0.left >= 4 && h1.left >= 4 && h2.left >= 4 && h3.left >= 4) { ZB_HUF4(h0); ZB_HUF4(h1); ZB_HUF4(h2); ZB_HUF4(h3); }
     while (h0.left >= 4) ZB_HUF4(h0);
     while (h1.left >= 4) ZB_HUF4(h1);
     while (h2.left >= 4) ZB_HUF4(h2);
     while (h3.left >= 4) ZB_HUF4(h3);
-    while (h0.left) zb_huf_one(h0, cells, log);
-    while (h1.left) zb_huf_one(h1, cells, log);
-    while (h2.left) zb_huf_one(h2, cells, log);
-    while (h3.left) zb_huf_one(h3, cells, log);
+    while (h0.left) zb_huf_one(h0, t);
+    while (h1.left) zb_huf_one(h1, t);
+    while (h2.left) zb_huf_one(h2, t);
+    while (h3.left) zb_huf_one(h3, t);
     return h0.b.left() == 0 && h1.b.left() == 0 && h2.b.left() == 0 && h3.b.left() == 0;
 }
 
@@ -213,6 +238,7 @@ __device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 m
 __device__ unsigned long long g_zb_ent_phase[8];      // summed cycles per phase (lane 0 of every warp), for tuning
 #define ZB_EMARK(k) do { if (lane == 0) { long long const t_ = clock64(); atomicAdd(&g_zb_ent_phase[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
 
+template <int ZB_ENT_WARPS>
 __global__ void __launch_bounds__(ZB_ENT_WARPS * 32)
 zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
                   const ZbFramePlace* __restrict__ place, const u64* __restrict__ dst_sizes,
@@ -226,10 +252,10 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
     if (threadIdx.x < 36) lutLL[threadIdx.x] = c_LL_base[threadIdx.x];
     if (threadIdx.x < 53) lutML[threadIdx.x] = c_ML_base[threadIdx.x];
     __syncthreads();
-    u8* const pool = zb_smem + ZB_ENT_LUT_BYTES + warp * ZB_ENT_POOL_BYTES;
+    u8* const pool = zb_smem + ZB_ENT_LUT_BYTES + warp * ZB_ENT_POOL_BYTES(ZB_ENT_WARPS);
     u8* const ws = pool + lane * ZB_ENT_WS_BYTES;                       // lane workspace
     u8* const tabs = pool + 32 * ZB_ENT_WS_BYTES;                       // claimable table space
-    u32 const TAB_BYTES = ZB_ENT_POOL_BYTES - 32 * ZB_ENT_WS_BYTES;
+    u32 const TAB_BYTES = ZB_ENT_POOL_BYTES(ZB_ENT_WARPS) - 32 * ZB_ENT_WS_BYTES;
 
     for (;;) {
         u32 base = 0;
@@ -328,18 +354,21 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
             }
             // dictionary Huffman table: read in place from the digest (shared by every lane, cache resident)
             if (comp && B.lit_kind == ZB_LIT_SCRATCH && dHuf.kind == ZB_SRC_DICT) {
-                if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, dict.huf, dict.huf_log)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+                if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, zb_huf_full(dict.huf, dict.huf_log))) { err = ZB_E_CORRUPTION; done = true; comp = false; }
             }
             ZB_EMARK(2);
             {   // claim pool space for the Huffman cells, decode; lanes that do not fit wait for the next pass
                 bool pending = wantH;
+                u32 hshift = 0, hT = 0, hbase = 0, hbytes = 0;
+                if (wantH) zb_huf_shape(hlog, rank, hshift, hT, hbase, hbytes);
                 while (__any_sync(0xFFFFFFFFu, pending)) {
-                    u32 const need = pending ? (2u << hlog) : 0;
+                    u32 const need = pending ? hbytes : 0;
                     u32 const incl = zb_warp_incl_scan((need + 15) & ~15u, lane);
                     if (pending && incl <= TAB_BYTES) {
                         u16* cells = (u16*)(tabs + incl - ((need + 15) & ~15u));
-                        zb_huf_fill(cells, ws, hlog, hns, rank);
-                        if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, cells, hlog)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+                        zb_huf_fill(cells, ws, hlog, hns, rank, hshift, hbase);
+                        ZbHufTab t; t.cells = cells; t.log = hlog; t.shift = hshift; t.T = hT; t.base = hbase;
+                        if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, t)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
                         pending = false;
                     }
                     __syncwarp();
@@ -408,6 +437,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                                 u32 const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
                                 u32 const ofc = ZB_CELL_SYM(co), llc = ZB_CELL_SYM(cl);
                                 u32 ll = lutLL[llc], ml = lutML[ZB_CELL_SYM(cm)], off;      // baselines: off the state chain
+                                // (a branch-free select chain over {rep0, rep1, rep2, rep0 - 1, new} was measured 3-5 % slower than this branch)
                                 if (ofc > 1) {
                                     off = (1u << ofc) - 3 + b.read(ofc);
                                     rep2 = rep1; rep1 = rep0; rep0 = off;

@@ -27,3 +27,10 @@ for _ in range(5): L.zb200_result_free(step())
 p = ctx.profile_read()
 tot = sum(v[0] / v[1] for v in p.values())
 print({k: round(v[0] / v[1], 3) for k, v in p.items()}, "total ms %.3f -> %.1f GB/s" % (tot, len(blob) / tot / 1e6))
+if os.environ.get("PHASES"):
+    L.zb_entropy_phase_read.argtypes = [C.c_void_p, C.c_int]
+    buf = (C.c_uint64 * 8)(); L.zb_entropy_phase_read(buf, 1)
+    L.zb200_result_free(step()); L.zb_entropy_phase_read(buf, 1)
+    names = ['other/loop', 'A block header', 'B literals hdr+weights', 'huffman table+streams', 'C seq header+ncount', 'D tables+sequences']
+    tot = float(sum(buf[i] for i in range(6))) or 1.0
+    print('entropy phases (share of summed warp cycles):', {nm: "%.1f%%" % (100.0 * buf[i] / tot) for i, nm in enumerate(names)}, "sum Mcycles %.0f" % (tot / 1e6))
