@@ -238,7 +238,7 @@ def main():
     assert last == blob[-FRAME:].tobytes()
 
     # ---------------- secondary arm: multi_compress_to_buffer on 128 KiB Silesia-mix segments (configs[2], scaled)
-    cn = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "2048"))      # set to a small number for quick kernel experiments
+    cn = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "8192"))      # set to a small number for quick kernel experiments
     cblob_in, coff_in, cln_in = corpus.silesia_mix(cn, 131072)
     csegs = np.stack([coff_in, cln_in], axis=1).astype(np.uint64)
     d_cin = torch.empty(len(cblob_in) + 256, dtype=torch.uint8, device="cuda")

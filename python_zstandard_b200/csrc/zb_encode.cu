@@ -693,34 +693,45 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     u32 const back_room = pbi >= 0 ? (u32)pbi : D - (u32)(-pbi);          // bytes available before the candidate
                     u32 const em = (searching && d0) ? min(4u, min(ip - anchor, back_room)) : 0u;   // bytes that may extend the match backwards
                     has_bk = em != 0; bk_max = em;
-                    int const pki = has_bk ? (int)ip - (int)em : (int)pa;
-                    int const pli = has_bk ? pbi - (int)em : (int)pa;
                     bool const act = searching || extending;
                     #define ZE_P(x) ((x) >= 0 ? in + (x) : dict_end + (x))
                     const u8* const qa = in + (act ? pa : 0); const u8* const qb = act ? ZE_P(pbi) : in; const u8* const qc = act ? ZE_P(pci) : in;
                     const u8* const qp = act ? ZE_P(ppi) : in; const u8* const qq = act ? ZE_P(pqi) : in;
-                    const u8* const qk = act ? ZE_P(pki) : in; const u8* const ql = act ? ZE_P(pli) : in;
                     #define ZE_W(q) ((const u32*)((uintptr_t)(q) & ~(uintptr_t)3))
                     #define ZE_S(q) ((u32)((uintptr_t)(q) & 3) * 8)
-                    const u32* const wa = ZE_W(qa); const u32* const wb = ZE_W(qb); const u32* const wc = ZE_W(qc);
-                    const u32* const wpp = ZE_W(qp); const u32* const wq = ZE_W(qq); const u32* const wk = ZE_W(qk); const u32* const wl = ZE_W(ql);
                     // predicated (not branched) loads: a lane only spends load bandwidth on what it will look at.
                     // A candidate that coincides with the main candidate (same distance) reuses its bytes.
+                    // Every lane works in its own unit, so each load instruction costs 32 cache-sector lookups whatever its
+                    // width, and this phase is bound by exactly those lookups: an 8-byte window is fetched as the two
+                    // aligned 8-byte words that contain it (2 loads instead of 3) and the four bytes in front of a window
+                    // come from the one word before it.
                     bool const ldb = extending || (searching && d0 != 0);
                     bool const c_same = has_c1 && d0 != 0 && d1 == d0, p_same = has_rp && d0 != 0 && r0 == d0;
                     bool const ldc = has_c1 && !c_same, ldp = has_rp && !p_same;
-                    u32 const a0 = act ? wa[0] : 0, a1 = act ? wa[1] : 0, a2 = act ? wa[2] : 0;
-                    u32 const b0 = ldb ? wb[0] : 0, b1 = ldb ? wb[1] : 0, b2 = ldb ? wb[2] : 0;
-                    u32 const c0 = ldc ? wc[0] : 0, c1 = ldc ? wc[1] : 0, c2 = ldc ? wc[2] : 0;
-                    u32 const p0 = ldp ? wpp[0] : 0, p1 = ldp ? wpp[1] : 0, p2 = ldp ? wpp[2] : 0;
-                    u32 const q0 = has_rq ? wq[0] : 0, q1 = has_rq ? wq[1] : 0, q2 = has_rq ? wq[2] : 0;
-                    u32 const k0 = has_bk ? wk[0] : 0, k1 = has_bk ? wk[1] : 0, l0 = has_bk ? wl[0] : 0, l1 = has_bk ? wl[1] : 0;
+                    uintptr_t const in_lo = (uintptr_t)in & ~(uintptr_t)7, in_hi = (uintptr_t)(in + n);    // block bytes: [in, in + n)
+                    // x0..x2 = the three aligned 32-bit words that hold the 8 bytes at q (dictionary pointers have 16 bytes of slack)
+                    #define ZE_LD3(q, on, blockptr, x0, x1, x2) \
+                        u32 x0, x1, x2; { \
+                            const uint2* const w_ = (const uint2*)((uintptr_t)(q) & ~(uintptr_t)7); \
+                            bool const on1_ = (on) && (!(blockptr) || (uintptr_t)(w_ + 1) < in_hi); \
+                            uint2 const lo_ = (on) ? w_[0] : make_uint2(0u, 0u), hi_ = on1_ ? w_[1] : make_uint2(0u, 0u); \
+                            bool const up_ = ((uintptr_t)(q) & 4) != 0; \
+                            x0 = up_ ? lo_.y : lo_.x; x1 = up_ ? hi_.x : lo_.y; x2 = up_ ? hi_.y : hi_.x; }
+                    ZE_LD3(qa, act, true, a0, a1, a2)
+                    ZE_LD3(qb, ldb, pbi >= 0, b0, b1, b2)
+                    ZE_LD3(qc, ldc, pci >= 0, c0, c1, c2)
+                    ZE_LD3(qp, ldp, ppi >= 0, p0, p1, p2)
+                    ZE_LD3(qq, has_rq, pqi >= 0, q0, q1, q2)
+                    // the word in front of the A and B windows (backward extension); never below the block's first word
+                    const u32* const wka = ZE_W(qa) - 1; const u32* const wkb = ZE_W(qb) - 1;
+                    u32 const ka = (has_bk && (uintptr_t)wka >= in_lo) ? *wka : 0u;
+                    u32 const kb = (has_bk && (pbi < 0 || (uintptr_t)wkb >= in_lo)) ? *wkb : 0u;
                     u32 const dn = (searching && ip + 2 < n) ? G.dist[ip + 2] : 0;
                     #define ZE_J(x0, x1, x2, q) ((u64)__funnelshift_r(x0, x1, ZE_S(q)) | ((u64)__funnelshift_r(x1, x2, ZE_S(q)) << 32))
                     A = ZE_J(a0, a1, a2, qa); B = ZE_J(b0, b1, b2, qb); C1 = ZE_J(c0, c1, c2, qc); RP = ZE_J(p0, p1, p2, qp); RQ = ZE_J(q0, q1, q2, qq);
                     if (c_same) { C1 = B >> 8; capC = capB > 0 ? capB - 1 : 0; }
                     if (p_same) { RP = B >> 8; capP = capB > 0 ? capB - 1 : 0; }
-                    bka = __funnelshift_r(k0, k1, ZE_S(qk)) << ((4 - em) * 8 & 31); bkb = __funnelshift_r(l0, l1, ZE_S(ql)) << ((4 - em) * 8 & 31);
+                    bka = __funnelshift_r(ka, a0, ZE_S(qa)); bkb = __funnelshift_r(kb, b0, ZE_S(qb));      // the 4 bytes before ip / before the candidate, nearest on top
                     d2 = dn;
                     if (searching && !d0) B = ~A;
                 }
