@@ -334,7 +334,7 @@ def main():
     one_core = sub * FRAME / (time.perf_counter() - t0) / 1e9
 
     tcb = 1e9
-    for _ in range(2):
+    for _ in range(3):
         t0 = time.perf_counter()
         refc_total = ref.batch(True, cblob_in, coff_in, cln_in, level=3, threads=cores, gather=False)
         tcb = min(tcb, time.perf_counter() - t0)
