@@ -107,6 +107,9 @@ struct ZbDictDev {
 struct ZbDictDigest {
     u16 huf[4096]; ZbFseCell ll[512]; ZbFseCell ml[512]; ZbFseCell of[256];
     u32 huf_log, ll_log, of_log, ml_log; u32 rep[3]; u32 dict_id; u32 content_off; u32 status; u32 has_entropy; u32 pad;
+    // encoder view of the same entropy tables (ZSTD_loadCEntropy, zstd/zstd.c:28015): normalized counts and code lengths
+    short c_norm_ll[36], c_norm_of[32], c_norm_ml[54]; u32 c_max_ll, c_max_of, c_max_ml;
+    u8 c_huf_nb[256]; u32 c_huf_max;
 };
 
 __device__ __forceinline__ u32 zb_rd16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }

@@ -706,16 +706,25 @@ __global__ void zb_digest_dict(const u8* __restrict__ dict, u32 n, ZbDictDigest*
         if (!used) { out->status = ZB_E_DICT_CORRUPTED; return; }
         zb_huf_fill(out->huf, ws, log, nsym, rank, 0, 0);          // the digest keeps the full table (read in place from global memory)
         out->huf_log = log; p += used;
+        u32 mxs = 0;
+        for (u32 i = 0; i < 256; i++) {
+            u32 const wt = i < nsym ? (ws[i >> 1] >> ((i & 1) * 4)) & 15 : 0;
+            out->c_huf_nb[i] = wt ? (u8)(log + 1 - wt) : 0; if (wt) mxs = i;
+        }
+        out->c_huf_max = mxs;
     }
     short norm[64]; u32 mx, log, used;
     mx = 31; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 8) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    for (u32 i = 0; i < 32; i++) out->c_norm_of[i] = i <= mx ? norm[i] : 0; out->c_max_of = mx;      // before zb_build_fse: it consumes norm
     zb_build_fse(out->of, norm, mx, log, K_OF); out->of_log = log; p += used;
     mx = 52; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    for (u32 i = 0; i < 54; i++) out->c_norm_ml[i] = i <= mx ? norm[i] : 0; out->c_max_ml = mx;      // before zb_build_fse: it consumes norm
     zb_build_fse(out->ml, norm, mx, log, K_ML); out->ml_log = log; p += used;
     mx = 35; used = zb_read_ncount(norm, mx, log, p, (u32)(end - p));
     if (!used || log > 9) { out->status = ZB_E_DICT_CORRUPTED; return; }
+    for (u32 i = 0; i < 36; i++) out->c_norm_ll[i] = i <= mx ? norm[i] : 0; out->c_max_ll = mx;      // before zb_build_fse: it consumes norm
     zb_build_fse(out->ll, norm, mx, log, K_LL); out->ll_log = log; p += used;
     if (p + 12 > end) { out->status = ZB_E_DICT_CORRUPTED; return; }
     u32 const content = (u32)(end - (p + 12));

@@ -58,7 +58,7 @@ struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };
 
 // dictionary as the block compressor sees it: the last <= 32 KiB of the dictionary content act as history
 // right before the first block of every frame (restates the "attach dictionary" mode, zstd/zstd.c:25263-25277)
-struct ZeDict { const u8* tail; u32 D; u32 pad; const u16* table; };
+struct ZeDict { const u8* tail; u32 D; u32 pad; const u16* table; const ZbDictDigest* ent; };   // ent: the dictionary's entropy tables (nullptr: none)
 struct ZeUpload { const unsigned long long* progress; unsigned long long total; u32* status; };   // progress == nullptr: input already resident
 
 // per-CTA scratch in global memory (L2 resident: reused for every block the CTA processes)
@@ -275,7 +275,8 @@ __device__ static u32 ze_cost(const u32* count, const short* norm, u32 max_sym, 
 
 // choose mode + build everything for one symbol stream (LL, OF or ML).  One thread.
 __device__ static void ze_make_table(ZeCTable& ct, const u32* count, u32 max_sym_kind, u32 nseq, u32 max_log, u32 def_log,
-                                     const short* defnorm, u32 def_max, u8* tmp_sym)
+                                     const short* defnorm, u32 def_max, u8* tmp_sym,
+                                     const short* dictnorm = nullptr, u32 dict_max = 0, u32 dict_log = 0)
 {
     u32 max_sym = 0, present = 0, most = 0;
     for (u32 s = 0; s <= max_sym_kind; s++) if (count[s]) { max_sym = s; present++; if (count[s] > most) most = count[s]; }
@@ -305,6 +306,18 @@ __device__ static void ze_make_table(ZeCTable& ct, const u32* count, u32 max_sym
     u32 cost_cmp = 0xFFFFFFFFu; u32 nc_bytes = 0;
     bool ok = nseq >= 32 && (1u << log) >= present && ze_normalize(norm, count, max_sym, nseq, log);
     if (ok) { nc_bytes = ze_write_ncount(ct.hdr, norm, max_sym, log); cost_cmp = ze_cost(count, norm, max_sym, log) + nc_bytes * 8; }
+    // the dictionary's table ("repeat" mode in the first block of a frame, ZSTD_selectEncodingType's set_repeat, zstd/zstd.c:21283):
+    // no header at all, so it wins on the short records dictionaries are made for
+    if (dictnorm && max_sym <= dict_max) {
+        short dn[56]; for (u32 s = 0; s < 56; s++) dn[s] = s <= dict_max ? dictnorm[s] : 0;
+        u32 const cost_rep = ze_cost(count, dn, max_sym, dict_log);
+        u32 sum = 0; for (u32 s = 0; s <= dict_max; s++) sum += dn[s] == -1 ? 1u : (dn[s] > 0 ? (u32)dn[s] : 0u);
+        if (sum == (1u << dict_log) && dict_log <= max_log && cost_rep != 0xFFFFFFFFu && cost_rep <= cost_def && cost_rep <= (ok ? cost_cmp : 0xFFFFFFFFu)) {
+            ct.mode = 3; ct.hdr_bytes = 0; ze_build_ctable(ct, dn, dict_max, dict_log, tmp_sym);
+            for (u32 s = dict_max + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+            return;
+        }
+    }
     if (ok && cost_cmp < cost_def) {
         ct.mode = 2; ct.hdr_bytes = nc_bytes; ze_build_ctable(ct, norm, max_sym, log, tmp_sym);
         for (u32 s = max_sym + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
@@ -329,6 +342,16 @@ __device__ static void ze_make_table(ZeCTable& ct, const u32* count, u32 max_sym
 // back with the shallowest" repair), assign canonical codes (HUF_buildCTableFromTree :17487).
 // ---------------------------------------------------------------------------
 struct ZeHuf { u16 code[256]; u8 nb[256]; u32 max_sym; u32 log; };
+
+// canonical values from the code lengths in H.nb: longest codes get the smallest values, symbols ascending within a length
+__device__ static void ze_huf_assign(ZeHuf& H, u32 max_sym, u32 maxnb)
+{
+    u32 per[13]; for (u32 b = 0; b <= 12; b++) per[b] = 0;
+    for (u32 s = 0; s <= max_sym; s++) per[H.nb[s]]++;
+    u32 val[13]; { u32 mn = 0; for (u32 b = maxnb; b >= 1; b--) { val[b] = mn; mn += per[b]; mn >>= 1; } }
+    for (u32 s = 0; s <= max_sym; s++) { H.code[s] = 0; if (H.nb[s]) H.code[s] = (u16)val[H.nb[s]]++; }
+    H.max_sym = max_sym; H.log = maxnb;
+}
 
 __device__ static bool ze_huf_build(ZeHuf& H, const u32* count, u32* wk /* >= 1600 u32 */)
 {
@@ -374,12 +397,7 @@ __device__ static bool ze_huf_build(ZeHuf& H, const u32* count, u32* wk /* >= 16
     u32 maxnb = 0; for (u32 i = 0; i < n; i++) if (depth[i] > maxnb) maxnb = depth[i];
     for (u32 s = 0; s < 256; s++) { H.nb[s] = 0; H.code[s] = 0; }
     for (u32 i = 0; i < n; i++) H.nb[sym[i]] = depth[i];
-    // canonical values: longest codes get the smallest values, symbols ascending within a length
-    u32 per[13]; for (u32 b = 0; b <= 12; b++) per[b] = 0;
-    for (u32 s = 0; s <= max_sym; s++) per[H.nb[s]]++;
-    u32 val[13]; { u32 mn = 0; for (u32 b = maxnb; b >= 1; b--) { val[b] = mn; mn += per[b]; mn >>= 1; } }
-    for (u32 s = 0; s <= max_sym; s++) if (H.nb[s]) H.code[s] = (u16)val[H.nb[s]]++;
-    H.max_sym = max_sym; H.log = maxnb;
+    ze_huf_assign(H, max_sym, maxnb);
     return true;
 }
 
@@ -451,6 +469,7 @@ struct ZeShared {
     __align__(16) u32 ring[256];      // A: 2 x 512 B input ring
     u16 ucnt[128]; u16 utail[128];
     u32 uoff[128]; u32 ucarry[128];
+    u32 lit_treeless;                 // literals coded with the dictionary's Huffman table (no table in the block)
     u32 nseq, nlit, tail_lit, all_same, lit_mode, lit_hdr, lit_bytes, seq_bytes, stream_bits[4], huf_tbl_bytes, seq_hdr_bytes, use_raw, body;
 };
 
@@ -652,6 +671,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             u32 const ilimit = n >= 8 ? n - 8 : 0;
             u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
             if (alive && ip == 0 && skip0) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
+            if (tid == 0 && D && dict.ent) { r0 = dict.ent->rep[0]; r1 = dict.ent->rep[1]; r2 = dict.ent->rep[2]; }   // a frame with a dictionary starts from its repcodes (ZSTD_loadCEntropy)
             uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
             u32 mode = 0, m_start = 0, m_off = 0, m_len = 0;
             u32 d0 = 0, d1 = 0;
@@ -840,18 +860,34 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         ZE_MARK(3);
         // ---------------- E: entropy tables.  thread 0: LL, 32: OF, 64: ML (own scratch each), 96: literals mode + Huffman code
         if (nseq) {
-            if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0]);
-            if (tid == 32) ze_make_table(S.ct[1], S.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.tmp_sym[1]);
-            if (tid == 64) ze_make_table(S.ct[2], S.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.tmp_sym[2]);
+            const ZbDictDigest* const de = (D && dict.ent) ? dict.ent : nullptr;      // first block of a frame that has a full dictionary
+            if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0], de ? de->c_norm_ll : nullptr, de ? de->c_max_ll : 0, de ? de->ll_log : 0);
+            if (tid == 32) ze_make_table(S.ct[1], S.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.tmp_sym[1], de ? de->c_norm_of : nullptr, de ? de->c_max_of : 0, de ? de->of_log : 0);
+            if (tid == 64) ze_make_table(S.ct[2], S.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.tmp_sym[2], de ? de->c_norm_ml : nullptr, de ? de->c_max_ml : 0, de ? de->ml_log : 0);
         }
         if (tid == 96) {
-            S.lit_mode = 0; S.huf_tbl_bytes = 0;
+            S.lit_mode = 0; S.huf_tbl_bytes = 0; S.lit_treeless = 0;
             u32 most = 0; for (u32 s = 0; s < 256; s++) if (S.hist[s] > most) most = S.hist[s];
+            const ZbDictDigest* const de = (D && dict.ent) ? dict.ent : nullptr;
             if (nlit >= 8 && most == nlit) S.lit_mode = 1;                // RLE literals
-            else if (nlit >= 64) {                                       // ZSTD_minLiteralsToCompress (dfast: 64), zstd/zstd.c:20918
-                if (ze_huf_build(S.huf, S.hist, S.wk)) {
-                    u32 const tb = ze_huf_write_table(S.huf_tbl, S.huf, S.ct[3], (u8*)(S.wk + 1200));
-                    if (tb) { S.huf_tbl_bytes = tb; S.lit_mode = 2; }
+            else {
+                u32 cost_new = 0xFFFFFFFFu;                              // bytes with a table of this block's own
+                if (nlit >= 64) {                                        // ZSTD_minLiteralsToCompress (dfast: 64), zstd/zstd.c:20918
+                    if (ze_huf_build(S.huf, S.hist, S.wk)) {
+                        u32 const tb = ze_huf_write_table(S.huf_tbl, S.huf, S.ct[3], (u8*)(S.wk + 1200));
+                        if (tb) { S.huf_tbl_bytes = tb; S.lit_mode = 2; u32 bits = 0; for (u32 s = 0; s < 256; s++) bits += S.hist[s] * S.huf.nb[s]; cost_new = (bits + 7) / 8 + tb; }
+                    }
+                }
+                // the dictionary's Huffman table ("treeless" literals; with a valid previous table the reference compresses
+                // from 7 literals on, ZSTD_minLiteralsToCompress zstd/zstd.c:20918-20930)
+                if (de && nlit > 6) {
+                    bool ok = true; u32 bits = 0;
+                    for (u32 s = 0; s < 256; s++) if (S.hist[s]) { u32 const nb = de->c_huf_nb[s]; if (!nb) ok = false; bits += S.hist[s] * nb; }
+                    if (ok && (bits + 7) / 8 <= cost_new) {
+                        for (u32 s = 0; s < 256; s++) S.huf.nb[s] = de->c_huf_nb[s];
+                        ze_huf_assign(S.huf, de->c_huf_max, de->huf_log);
+                        S.huf_tbl_bytes = 0; S.lit_mode = 2; S.lit_treeless = 1;
+                    }
                 }
             }
         }
@@ -1001,9 +1037,10 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             // literals section header (ZSTD_compressLiterals / ZSTD_noCompressLiterals, zstd/zstd.c:20851-21038)
             if (S.lit_mode == 2) {
                 u32 const lh = 3 + (nlit >= 1024) + (nlit >= 16384);
-                if (lh == 3) { u32 const v = 2 | ((four ? 1u : 0u) << 2) | (nlit << 4) | (lit_payload << 14); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); }
-                else if (lh == 4) { u32 const v = 2 | (2u << 2) | (nlit << 4) | (lit_payload << 18); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); o[3] = (u8)(v >> 24); }
-                else { u32 const v = 2 | (3u << 2) | (nlit << 4) | (lit_payload << 22); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); o[3] = (u8)(v >> 24); o[4] = (u8)(lit_payload >> 10); }
+                u32 const ty = S.lit_treeless ? 3u : 2u;       // compressed / treeless (the dictionary's table)
+                if (lh == 3) { u32 const v = ty | ((four ? 1u : 0u) << 2) | (nlit << 4) | (lit_payload << 14); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); }
+                else if (lh == 4) { u32 const v = ty | (2u << 2) | (nlit << 4) | (lit_payload << 18); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); o[3] = (u8)(v >> 24); }
+                else { u32 const v = ty | (3u << 2) | (nlit << 4) | (lit_payload << 22); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); o[3] = (u8)(v >> 24); o[4] = (u8)(lit_payload >> 10); }
                 p = lh;
             } else {
                 u32 const t = S.lit_mode;      // 0 raw, 1 RLE
@@ -1203,10 +1240,10 @@ size_t zb_encode_scratch_bytes() { return sizeof(ZeScratch); }
 void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st) { zb_dict_table<<<1, 32, 0, st>>>(tail, D, table); }
 
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table,
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest,
                                const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st)
 {
-    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table;
+    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table; dict.ent = (const ZbDictDigest*)dict_digest;
     ZeUpload up; up.progress = upload_progress; up.total = upload_total; up.status = upload_status;
     cudaFuncSetAttribute(zb_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));      // per device: cheap, so set on every launch
     zb_compress_blocks<<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
