@@ -33,9 +33,11 @@ void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st);
 size_t zb_encode_scratch_bytes();
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest,
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
                                const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st);
 void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st);
+u32 zb_encode_ctable_bytes();
+void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st);
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
                             u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
 void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
@@ -91,7 +93,7 @@ struct zb200_ctx {
 
 struct zb200_ddict {
     zb200_ctx* ctx; void* d_raw = nullptr; ZbDictDigest* d_digest = nullptr; ZbDictDev dev; size_t size = 0;
-    u16* d_ctable = nullptr; const u8* c_tail = nullptr; u32 c_D = 0;      // compression view: last <= 32 KiB of the content + its hash table
+    u16* d_ctable = nullptr; const u8* c_tail = nullptr; u32 c_D = 0; void* d_cct = nullptr;      // compression view: last <= 32 KiB of the content + its hash table
 };
 
 struct zb200_result {
@@ -301,6 +303,8 @@ int zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddic
     d->c_tail = v.content + (v.content_size - d->c_D);
     if (d->c_D >= 8 && cudaMalloc((void**)&d->d_ctable, 16384 * sizeof(u16)) == cudaSuccess) {
         zb_launch_dict_table(d->c_tail, d->c_D, d->d_ctable, ctx->stream);
+        if (v.has_entropy && cudaMalloc(&d->d_cct, 3 * (size_t)zb_encode_ctable_bytes()) == cudaSuccess)
+            zb_launch_dict_ctables(d->d_digest, d->d_cct, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     } else d->c_D = 0;
     *out = d;
@@ -313,6 +317,7 @@ void zb200_ddict_free(zb200_ddict* d)
     if (d->d_raw) cudaFree(d->d_raw);
     if (d->d_digest) cudaFree(d->d_digest);
     if (d->d_ctable) cudaFree(d->d_ctable);
+    if (d->d_cct) cudaFree(d->d_cct);
     delete d;
 }
 uint32_t zb200_ddict_id(const zb200_ddict* d) { return d ? d->dev.dict_id : 0; }
@@ -563,7 +568,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     if (nj) { KSpan s(ctx, ZB200_K_COMPRESS);
       zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
                                 dict ? dict->c_tail : nullptr, dict ? dict->c_D : 0, dict ? dict->d_ctable : nullptr,
-                                (dict && dict->c_D && dict->dev.has_entropy) ? (const void*)dict->d_digest : nullptr,
+                                (dict && dict->c_D && dict->dev.has_entropy) ? (const void*)dict->d_digest : nullptr, dict ? dict->d_cct : nullptr,
                                 overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, ctx->stream); }
     if (overlap_upload) {
         // <= 48 chunks of >= 4 MiB; after each chunk the copy engine also writes the new byte count next to the work counter

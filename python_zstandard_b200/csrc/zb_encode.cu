@@ -58,7 +58,7 @@ struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };
 
 // dictionary as the block compressor sees it: the last <= 32 KiB of the dictionary content act as history
 // right before the first block of every frame (restates the "attach dictionary" mode, zstd/zstd.c:25263-25277)
-struct ZeDict { const u8* tail; u32 D; u32 pad; const u16* table; const ZbDictDigest* ent; };   // ent: the dictionary's entropy tables (nullptr: none)
+struct ZeDict { const u8* tail; u32 D; u32 pad; const u16* table; const ZbDictDigest* ent; const void* cct; };   // ent: the dictionary's entropy tables (nullptr: none)
 struct ZeUpload { const unsigned long long* progress; unsigned long long total; u32* status; };   // progress == nullptr: input already resident
 
 // per-CTA scratch in global memory (L2 resident: reused for every block the CTA processes)
@@ -276,7 +276,7 @@ __device__ static u32 ze_cost(const u32* count, const short* norm, u32 max_sym, 
 // choose mode + build everything for one symbol stream (LL, OF or ML).  One thread.
 __device__ static void ze_make_table(ZeCTable& ct, const u32* count, u32 max_sym_kind, u32 nseq, u32 max_log, u32 def_log,
                                      const short* defnorm, u32 def_max, u8* tmp_sym,
-                                     const short* dictnorm = nullptr, u32 dict_max = 0, u32 dict_log = 0)
+                                     const short* dictnorm = nullptr, u32 dict_max = 0, u32 dict_log = 0, const ZeCTable* prebuilt = nullptr)
 {
     u32 max_sym = 0, present = 0, most = 0;
     for (u32 s = 0; s <= max_sym_kind; s++) if (count[s]) { max_sym = s; present++; if (count[s] > most) most = count[s]; }
@@ -313,8 +313,14 @@ __device__ static void ze_make_table(ZeCTable& ct, const u32* count, u32 max_sym
         u32 const cost_rep = ze_cost(count, dn, max_sym, dict_log);
         u32 sum = 0; for (u32 s = 0; s <= dict_max; s++) sum += dn[s] == -1 ? 1u : (dn[s] > 0 ? (u32)dn[s] : 0u);
         if (sum == (1u << dict_log) && dict_log <= max_log && cost_rep != 0xFFFFFFFFu && cost_rep <= cost_def && cost_rep <= (ok ? cost_cmp : 0xFFFFFFFFu)) {
-            ct.mode = 3; ct.hdr_bytes = 0; ze_build_ctable(ct, dn, dict_max, dict_log, tmp_sym);
-            for (u32 s = dict_max + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+            if (prebuilt && prebuilt->mode == 3) {              // built once per dictionary (zb_dict_ctables): a copy instead of a 512-cell spread per record
+                const uint4* const src4 = (const uint4*)prebuilt; uint4* const dst4 = (uint4*)&ct;
+                for (u32 i = 0; i < sizeof(ZeCTable) / 16; i++) dst4[i] = src4[i];
+            } else {
+                ze_build_ctable(ct, dn, dict_max, dict_log, tmp_sym);
+                for (u32 s = dict_max + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+            }
+            ct.mode = 3; ct.hdr_bytes = 0;
             return;
         }
     }
@@ -697,7 +703,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 // back to back as raw aligned words; the funnel shifts that consume them come afterwards
                 u64 A = 0, B = 0, C1 = 0, RP = 0, RQ = 0; u32 bka = 0, bkb = 1, d2 = 0, bk_max = 0;
                 u32 capB = 64, capC = 64, capP = 64, capQ = 64;
-                bool has_c1 = false, has_rp = false, has_rq = false, has_bk = false;
+                bool has_c1 = false, has_rp = false, has_rq = false, has_bk = false, ext1 = false, ext2 = false; u64 X2 = 0;
                 {
                     u32 const pa = extending ? m_start + m_len : ip;
                     // candidate positions are block-relative and may be negative: -k means k bytes before the
@@ -706,9 +712,14 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     has_c1 = searching && d1 != 0 && ip + 5 <= end;
                     has_rp = searching && r0 != 0 && (int)ip + 1 - (int)r0 >= -(int)D && ip + 5 <= end;
                     has_rq = searching && anchor == ip && r1 != 0 && (int)ip - (int)r1 >= -(int)D;
-                    int const pci = has_c1 ? (int)ip + 1 - (int)d1 : (int)pa;
-                    int const ppi = has_rp ? (int)ip + 1 - (int)r0 : (int)pa;
-                    int const pqi = has_rq ? (int)ip - (int)r1 : (int)pa;
+                    // EXTEND has no use for the candidate slots, so they fetch the next 16 bytes of both sides (24 bytes per step).
+                    // A further window counts only if it lies wholly inside the block and wholly on one side of the dictionary end.
+                    ext1 = extending && pa + 16 <= n && (pbi >= 0 || pbi + 16 <= 0);
+                    ext2 = ext1 && pa + 24 <= n && (pbi >= 0 || pbi + 24 <= 0);
+                    int const pci = has_c1 ? (int)ip + 1 - (int)d1 : (ext1 ? (int)pa + 8 : (int)pa);
+                    int const ppi = has_rp ? (int)ip + 1 - (int)r0 : (ext1 ? pbi + 8 : (int)pa);
+                    int const pqi = has_rq ? (int)ip - (int)r1 : (ext2 ? (int)pa + 16 : (int)pa);
+                    int const pxi = ext2 ? pbi + 16 : (int)pa;
                     capB = pbi < 0 ? (u32)(-pbi) : 64u; capC = pci < 0 ? (u32)(-pci) : 64u; capP = ppi < 0 ? (u32)(-ppi) : 64u; capQ = pqi < 0 ? (u32)(-pqi) : 64u;
                     u32 const back_room = pbi >= 0 ? (u32)pbi : D - (u32)(-pbi);          // bytes available before the candidate
                     u32 const em = (searching && d0) ? min(4u, min(ip - anchor, back_room)) : 0u;   // bytes that may extend the match backwards
@@ -716,7 +727,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     bool const act = searching || extending;
                     #define ZE_P(x) ((x) >= 0 ? in + (x) : dict_end + (x))
                     const u8* const qa = in + (act ? pa : 0); const u8* const qb = act ? ZE_P(pbi) : in; const u8* const qc = act ? ZE_P(pci) : in;
-                    const u8* const qp = act ? ZE_P(ppi) : in; const u8* const qq = act ? ZE_P(pqi) : in;
+                    const u8* const qp = act ? ZE_P(ppi) : in; const u8* const qq = act ? ZE_P(pqi) : in; const u8* const qx = act ? ZE_P(pxi) : in;
                     #define ZE_W(q) ((const u32*)((uintptr_t)(q) & ~(uintptr_t)3))
                     #define ZE_S(q) ((u32)((uintptr_t)(q) & 3) * 8)
                     // predicated (not branched) loads: a lane only spends load bandwidth on what it will look at.
@@ -727,7 +738,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     // come from the one word before it.
                     bool const ldb = extending || (searching && d0 != 0);
                     bool const c_same = has_c1 && d0 != 0 && d1 == d0, p_same = has_rp && d0 != 0 && r0 == d0;
-                    bool const ldc = has_c1 && !c_same, ldp = has_rp && !p_same;
+                    bool const ldc = (has_c1 && !c_same) || ext1, ldp = (has_rp && !p_same) || ext1, ldq = has_rq || ext2;
                     uintptr_t const in_lo = (uintptr_t)in & ~(uintptr_t)7, in_hi = (uintptr_t)(in + n);    // block bytes: [in, in + n)
                     // x0..x2 = the three aligned 32-bit words that hold the 8 bytes at q (dictionary pointers have 16 bytes of slack)
                     #define ZE_LD3(q, on, blockptr, x0, x1, x2) \
@@ -741,7 +752,8 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     ZE_LD3(qb, ldb, pbi >= 0, b0, b1, b2)
                     ZE_LD3(qc, ldc, pci >= 0, c0, c1, c2)
                     ZE_LD3(qp, ldp, ppi >= 0, p0, p1, p2)
-                    ZE_LD3(qq, has_rq, pqi >= 0, q0, q1, q2)
+                    ZE_LD3(qq, ldq, pqi >= 0, q0, q1, q2)
+                    ZE_LD3(qx, ext2, pxi >= 0, x0, x1, x2)
                     // the word in front of the A and B windows (backward extension); never below the block's first word
                     const u32* const wka = ZE_W(qa) - 1; const u32* const wkb = ZE_W(qb) - 1;
                     u32 const ka = (has_bk && (uintptr_t)wka >= in_lo) ? *wka : 0u;
@@ -749,6 +761,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     u32 const dn = (searching && ip + 2 < n) ? G.dist[ip + 2] : 0;
                     #define ZE_J(x0, x1, x2, q) ((u64)__funnelshift_r(x0, x1, ZE_S(q)) | ((u64)__funnelshift_r(x1, x2, ZE_S(q)) << 32))
                     A = ZE_J(a0, a1, a2, qa); B = ZE_J(b0, b1, b2, qb); C1 = ZE_J(c0, c1, c2, qc); RP = ZE_J(p0, p1, p2, qp); RQ = ZE_J(q0, q1, q2, qq);
+                    X2 = ZE_J(x0, x1, x2, qx);
                     if (c_same) { C1 = B >> 8; capC = capB > 0 ? capB - 1 : 0; }
                     if (p_same) { RP = B >> 8; capP = capB > 0 ? capB - 1 : 0; }
                     bka = __funnelshift_r(ka, a0, ZE_S(qa)); bkb = __funnelshift_r(kb, b0, ZE_S(qb));      // the 4 bytes before ip / before the candidate, nearest on top
@@ -791,9 +804,11 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     }
                 } else if (extending) {
                     u32 const room = end - (m_start + m_len);
-                    u32 const c = min(ze_common8(A, B), capB); u32 const k = min(c, room);
+                    u32 total = ze_common8(A, B), compared = 8;                      // in EXTEND: C1/RP = bytes 8..15, RQ/X2 = bytes 16..23 of the two sides
+                    if (total == 8 && ext1) { total += ze_common8(C1, RP); compared = 16; if (total == 16 && ext2) { total += ze_common8(RQ, X2); compared = 24; } }
+                    u32 const c = min(total, capB); u32 const k = min(c, room);
                     m_len += k;
-                    if (!(c == 8 && capB > 8 && m_start + m_len < end)) { fin = true; f_start = m_start; f_off = m_off; f_len = m_len; }
+                    if (!(total == compared && capB > total && m_start + m_len < end)) { fin = true; f_start = m_start; f_off = m_off; f_len = m_len; }
                 }
                 if (fin) {
                     u32 const ll = f_start - anchor;
@@ -861,9 +876,9 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         // ---------------- E: entropy tables.  thread 0: LL, 32: OF, 64: ML (own scratch each), 96: literals mode + Huffman code
         if (nseq) {
             const ZbDictDigest* const de = (D && dict.ent) ? dict.ent : nullptr;      // first block of a frame that has a full dictionary
-            if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0], de ? de->c_norm_ll : nullptr, de ? de->c_max_ll : 0, de ? de->ll_log : 0);
-            if (tid == 32) ze_make_table(S.ct[1], S.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.tmp_sym[1], de ? de->c_norm_of : nullptr, de ? de->c_max_of : 0, de ? de->of_log : 0);
-            if (tid == 64) ze_make_table(S.ct[2], S.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.tmp_sym[2], de ? de->c_norm_ml : nullptr, de ? de->c_max_ml : 0, de ? de->ml_log : 0);
+            if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0], de ? de->c_norm_ll : nullptr, de ? de->c_max_ll : 0, de ? de->ll_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 0 : nullptr);
+            if (tid == 32) ze_make_table(S.ct[1], S.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.tmp_sym[1], de ? de->c_norm_of : nullptr, de ? de->c_max_of : 0, de ? de->of_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 1 : nullptr);
+            if (tid == 64) ze_make_table(S.ct[2], S.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.tmp_sym[2], de ? de->c_norm_ml : nullptr, de ? de->c_max_ml : 0, de ? de->ml_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 2 : nullptr);
         }
         if (tid == 96) {
             S.lit_mode = 0; S.huf_tbl_bytes = 0; S.lit_treeless = 0;
@@ -1094,6 +1109,26 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
 // dictionary hash table: the block compressor's table state after "having seen" the dictionary tail
 // (restates what ZSTD_loadDictionaryContent leaves in the match-state tables, zstd/zstd.c:27900-27990)
 // ===========================================================================
+// the dictionary's three sequence CTables, built once (ZSTD_loadCEntropy builds the same at dictionary load, zstd/zstd.c:28015)
+__global__ void zb_dict_ctables(const ZbDictDigest* __restrict__ ent, ZeCTable* __restrict__ out3)
+{
+    u32 const k = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) || k > 2) return;
+    const short* const src = k == 0 ? ent->c_norm_ll : (k == 1 ? ent->c_norm_of : ent->c_norm_ml);
+    u32 const mx = k == 0 ? ent->c_max_ll : (k == 1 ? ent->c_max_of : ent->c_max_ml), lg = k == 0 ? ent->ll_log : (k == 1 ? ent->of_log : ent->ml_log);
+    u32 const cap = k == 0 ? 35u : (k == 1 ? 31u : 52u), maxlog = k == 1 ? 8u : 9u;
+    ZeCTable& ct = out3[k];
+    ct.mode = 0xFF; ct.hdr_bytes = 0; ct.rle_sym = 0; ct.log = 0;
+    if (!ent->has_entropy || mx > cap || lg > maxlog || lg < 5) return;
+    short dn[56]; u32 sum = 0;
+    for (u32 s = 0; s < 56; s++) { dn[s] = s <= mx ? src[s] : 0; sum += dn[s] == -1 ? 1u : (dn[s] > 0 ? (u32)dn[s] : 0u); }
+    if (sum != (1u << lg)) return;
+    u8 tmp[512];
+    ze_build_ctable(ct, dn, mx, lg, tmp);
+    for (u32 s = mx + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+    ct.mode = 3;
+}
+
 __global__ void zb_dict_table(const u8* __restrict__ tail, u32 D, u16* __restrict__ table)
 {
     u32 const lane = threadIdx.x;
@@ -1240,10 +1275,10 @@ size_t zb_encode_scratch_bytes() { return sizeof(ZeScratch); }
 void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st) { zb_dict_table<<<1, 32, 0, st>>>(tail, D, table); }
 
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
-                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest,
+                               void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
                                const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st)
 {
-    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table; dict.ent = (const ZbDictDigest*)dict_digest;
+    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table; dict.ent = (const ZbDictDigest*)dict_digest; dict.cct = dict_digest ? dict_cct : nullptr;
     ZeUpload up; up.progress = upload_progress; up.total = upload_total; up.status = upload_status;
     cudaFuncSetAttribute(zb_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));      // per device: cheap, so set on every launch
     zb_compress_blocks<<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
@@ -1267,6 +1302,8 @@ void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* se
 }
 
 u32 zb_encode_smem_bytes() { return (u32)sizeof(ZeShared); }
+u32 zb_encode_ctable_bytes() { return (u32)sizeof(ZeCTable); }
+void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st) { zb_dict_ctables<<<1, 96, 0, st>>>((const ZbDictDigest*)digest, (ZeCTable*)out3); }
 
 void zb_encode_phase_read(unsigned long long* out16, int reset)
 {

@@ -44,6 +44,14 @@ ctx.profile(True); r2 = cctx.multi_compress_to_buffer(bws); pk = ctx.profile_rea
 print("GPU compress e2e %.2f GB/s (ratio %.2f, %+.1f%% vs reference), kernels %s" % (
     U / tg / 1e9, U / csz, 100.0 * (csz / float(rl.sum()) - 1), {k: round(v[0], 3) for k, v in pk.items()}), flush=True)
 
+import ctypes as C
+L = _native.lib(); L.zb_encode_phase_read.argtypes = [C.c_void_p, C.c_int]
+buf = (C.c_uint64 * 16)(); L.zb_encode_phase_read(buf, 1)
+r2 = cctx.multi_compress_to_buffer(bws); del r2
+L.zb_encode_phase_read(buf, 1)
+names = ["setup/rle", "A hash links", "C parse", "D compaction+gather", "E tables", "E literals", "E chains", "E seq pack", "F assemble"]
+print("compress phases, cycles per record:", {nm: int(buf[i] / n) for i, nm in enumerate(names)}, flush=True)
+
 # decode: the reference's frames (host pinned) through the public API
 pin2 = zstd.PinnedBuffer(len(rc)); np.frombuffer(pin2, dtype=np.uint8)[:] = rc
 fbws = zstd.BufferWithSegments(pin2, np.stack([ro, rl.astype(np.uint64)], axis=1).astype(np.uint64).tobytes())
