@@ -161,8 +161,8 @@ def test_ragged_sizes(ref, oracle):
 def test_dictionary_compression(ref, oracle):
     """Config 4: records compressed against a trained dictionary.  The frames carry the dictionary id,
     decode bit-exact through the reference decoder (with the dictionary) and are far smaller than without
-    it; the size margin against the reference's dictionary compression is stated (we use the dictionary as
-    match history only, not its entropy tables)."""
+    it; the size margin against the reference's dictionary compression is stated (the dictionary serves as match
+    history, start repcodes and entropy tables; measured +0.3 % on the config-4 workload, asserted <= 1.35x)."""
     import os
     from tests import helpers
     dct = open(os.path.join(helpers.GOLDEN, "dict.bin"), "rb").read()
