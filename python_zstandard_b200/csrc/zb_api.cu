@@ -157,13 +157,6 @@ void pinned_put(zb200_ctx* c, void* p)
     std::lock_guard<std::mutex> g(c->mu);
     for (auto& b : c->pinned) if (b.p == p) { b.busy = false; return; }
 }
-bool is_pinned_pool(zb200_ctx* c, const void* p)
-{
-    std::lock_guard<std::mutex> g(c->mu);
-    for (auto& b : c->pinned) if ((const char*)p >= (const char*)b.p && (const char*)p < (const char*)b.p + b.cap) return true;
-    return false;
-}
-
 bool zb_trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("ZB200_TRACE"); v = (e && *e && *e != '0') ? 1 : 0; } return v == 1; }
 double zb_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
