@@ -1,0 +1,85 @@
+"""Host build of the encoder's serial entropy-table helpers, for CPU known-answer tests.
+
+The helpers (FSE normalisation, NCount writer, CTable builder, table choice, Huffman code construction and its
+weight header) are plain single-thread code inside python_zstandard_b200/csrc/zb_encode.cu.  This module cuts that
+very text out of the .cu file, swaps the CUDA qualifiers for host ones and compiles it with g++ into
+tests/_build/libze_host.so, so the CPU suite checks the same source lines the kernel runs -- against the
+reference's own FSE_* / HUF_* functions in oracle/_ref (tests/test_encoder_tables.py).  Test infrastructure only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(ROOT, "python_zstandard_b200", "csrc", "zb_encode.cu")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD, "libze_host.so")
+
+PRELUDE = r"""
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
+struct uint4 { u32 x, y, z, w; };
+static inline u32 ze_hibit(u32 v) { return 31u - (u32)__builtin_clz(v); }
+#define __log2f log2f
+"""
+
+WRAPPERS = r"""
+extern "C" {
+int t_normalize(short* norm, const u32* count, u32 max_sym, u32 total, u32 log) { return ze_normalize(norm, count, max_sym, total, log) ? 1 : 0; }
+u32 t_write_ncount(u8* out, const short* norm, u32 max_sym, u32 log) { return ze_write_ncount(out, norm, max_sym, log); }
+u32 t_cost(const u32* count, const short* norm, u32 max_sym, u32 log) { return ze_cost(count, norm, max_sym, log); }
+void t_build_ctable(const short* norm, u32 max_sym, u32 log, u16* state, int* dnb, int* dfs)
+{
+    static ZeCTable ct; static u8 tmp[512];
+    ze_build_ctable(ct, norm, max_sym, log, tmp);
+    memcpy(state, ct.state, sizeof(u16) << log); memcpy(dnb, ct.dnb, sizeof(int) * (max_sym + 1)); memcpy(dfs, ct.dfs, sizeof(int) * (max_sym + 1));
+}
+// mode, log, header bytes of the table the encoder would pick for this histogram (no dictionary)
+void t_make_table(const u32* count, u32 max_sym_kind, u32 nseq, u32 max_log, u32 def_log, const short* defnorm, u32 def_max,
+                  u32* mode, u32* log, u32* hdr_bytes, u8* hdr)
+{
+    static ZeCTable ct; static u8 tmp[512];
+    ze_make_table(ct, count, max_sym_kind, nseq, max_log, def_log, defnorm, def_max, tmp);
+    *mode = ct.mode; *log = ct.log; *hdr_bytes = ct.hdr_bytes; memcpy(hdr, ct.hdr, 64);
+}
+int t_huf_build(const u32* count, u8* nb, u16* code, u32* max_sym, u32* log)
+{
+    static ZeHuf H; static u32 wk[1600];
+    if (!ze_huf_build(H, count, wk)) return 0;
+    memcpy(nb, H.nb, 256); memcpy(code, H.code, 512); *max_sym = H.max_sym; *log = H.log;
+    return 1;
+}
+u32 t_huf_write_table(const u32* count, u8* out)
+{
+    static ZeHuf H; static u32 wk[1600]; static ZeCTable ct; static u8 tmp[512];
+    if (!ze_huf_build(H, count, wk)) return 0;
+    return ze_huf_write_table(out, H, ct, tmp);
+}
+}
+"""
+
+
+def _extract():
+    src = open(SRC).read()
+    a = src.index("struct ZeCTable {")
+    b = src.index("// the block kernel")
+    b = src.rindex("// ----", 0, b)
+    chunk = src[a:b]
+    return chunk.replace("__device__ static", "static").replace("__device__ __forceinline__", "static inline")
+
+
+def build():
+    os.makedirs(BUILD, exist_ok=True)
+    cpp = os.path.join(BUILD, "ze_host.cpp")
+    text = PRELUDE + _extract() + WRAPPERS
+    if not (os.path.exists(LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", LIB, cpp, "-lm"])
+    L = C.CDLL(LIB)
+    L.t_write_ncount.restype = C.c_uint32
+    L.t_cost.restype = C.c_uint32
+    L.t_huf_write_table.restype = C.c_uint32
+    return L
