@@ -71,6 +71,43 @@ def _extract():
     return chunk.replace("__device__ static", "static").replace("__device__ __forceinline__", "static inline")
 
 
+DEC_SRC = os.path.join(ROOT, "python_zstandard_b200", "csrc", "zb_entropy.cuh")
+DEC_LIB = os.path.join(BUILD, "libzd_host.so")
+DEC_WRAPPERS = r"""
+extern "C" {
+// builds the split table for the given nibble weights and returns its shape; cells must hold 4096 entries
+void t_huf_split(const u8* ws, u32 log, u32 nsym, const u32* rank, u16* cells, u32* shift, u32* T, u32* base, u32* bytes)
+{
+    zb_huf_shape(log, rank, *shift, *T, *base, *bytes);
+    zb_huf_fill(cells, ws, log, nsym, rank, *shift, *base);
+}
+void t_huf_full(const u8* ws, u32 log, u32 nsym, const u32* rank, u16* cells) { zb_huf_fill(cells, ws, log, nsym, rank, 0, 0); }
+u32 t_huf_cell(const u16* cells, u32 log, u32 shift, u32 T, u32 base, u32 v)
+{
+    ZbHufTab t; t.cells = cells; t.log = log; t.shift = shift; t.T = T; t.base = base;
+    return ZB_HCELL(t, v);
+}
+}
+"""
+
+
+def build_decoder_helpers():
+    """Host build of the split Huffman decode table code of zb_entropy.cuh (shape, fill, lookup)."""
+    os.makedirs(BUILD, exist_ok=True)
+    src = open(DEC_SRC).read()
+    a = src.index("#define ZB_HUF_COARSE")
+    b = src.index("// one Huffman stream")
+    chunk = src[a:b].replace("__device__ static", "static").replace("__device__ __forceinline__", "static inline")
+    text = PRELUDE + chunk + DEC_WRAPPERS
+    cpp = os.path.join(BUILD, "zd_host.cpp")
+    if not (os.path.exists(DEC_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", DEC_LIB, cpp])
+    L = C.CDLL(DEC_LIB)
+    L.t_huf_cell.restype = C.c_uint32
+    return L
+
+
 def build():
     os.makedirs(BUILD, exist_ok=True)
     cpp = os.path.join(BUILD, "ze_host.cpp")

@@ -224,3 +224,41 @@ def test_huffman_code_and_weight_header(libs):
             got = [tlog.value + 1 - w[s] if w[s] else 0 for s in range(nsym.value)]
             assert got == lens[:nsym.value].tolist()
     assert worst <= 0.01, worst
+
+
+def test_split_huffman_decode_table_equals_the_full_table(libs):
+    """The decoder keeps full-resolution cells only for codes longer than 8 bits (zb_entropy.cuh).  For every code our
+    encoder can emit, every index of the reference-shaped full table must read the same cell through the split table."""
+    ours, ref = libs
+    dec = host_encoder.build_decoder_helpers()
+    rng = np.random.default_rng(10)
+    text = open(__file__, "rb").read()
+    samples = [np.frombuffer(text, dtype=np.uint8), np.frombuffer(text[:900], dtype=np.uint8),
+               np.clip(rng.geometric(0.05, 50000), 0, 255).astype(np.uint8), rng.integers(0, 256, 70000).astype(np.uint8),
+               np.concatenate([np.full(60000, 65, np.uint8), np.arange(256, dtype=np.uint8)]),
+               np.concatenate([np.full(3000, 7, np.uint8), np.full(40, 9, np.uint8), np.arange(20, dtype=np.uint8)])]
+    saw_split = False
+    for data in samples:
+        count = np.bincount(data, minlength=256).astype(np.uint32)
+        nb = (C.c_ubyte * 256)(); code = (C.c_uint16 * 256)(); ms = C.c_uint32(); lg = C.c_uint32()
+        assert ours.t_huf_build((C.c_uint * 256)(*count.tolist()), nb, code, C.byref(ms), C.byref(lg))
+        log, nsym = lg.value, ms.value + 1
+        ws = (C.c_ubyte * 128)(); rank = (C.c_uint32 * 13)()
+        for s in range(nsym):
+            w = log + 1 - nb[s] if nb[s] else 0
+            ws[s >> 1] |= w << ((s & 1) * 4)
+            rank[w] += 1 if w else 0
+        full = (C.c_uint16 * 4096)(); split = (C.c_uint16 * 4096)()
+        dec.t_huf_full(ws, log, nsym, rank, full)
+        shift, T, base, nbytes = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        dec.t_huf_split(ws, log, nsym, rank, split, C.byref(shift), C.byref(T), C.byref(base), C.byref(nbytes))
+        assert nbytes.value <= 2 << log and (shift.value == 0) == (log <= 8)
+        saw_split |= shift.value > 0 and nbytes.value < (2 << log)
+        for v in range(1 << log):
+            assert dec.t_huf_cell(split, log, shift.value, T.value, base.value, v) == full[v], (log, v)
+        # and the full table is the canonical one: index -> (symbol, length) of the code that prefixes it
+        for s in range(nsym):
+            if nb[s]:
+                lo = code[s] << (log - nb[s])
+                assert full[lo] == (s | (nb[s] << 8)) and full[lo + (1 << (log - nb[s])) - 1] == (s | (nb[s] << 8))
+    assert saw_split
