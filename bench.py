@@ -317,7 +317,10 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    launches = sum(v["launches"] for v in kernels.values())
+    # the library times spans, some of which hold two kernels: placement = zb_place_reduce + zb_place_scan, execute =
+    # zb_execute_tile + zb_execute (frames above the 4 KiB tile; exits at once when there are none)
+    per_span = {"zb_place_frames": 2, "zb_execute": 2}
+    launches = sum(v["launches"] * per_span.get(k, 1) for k, v in kernels.items())
 
     # ---------------- CPU baseline: the unmodified reference on this box's cores, same batch
     cores = os.cpu_count() or 1
