@@ -108,6 +108,58 @@ def build_decoder_helpers():
     return L
 
 
+LIT_LIB = os.path.join(BUILD, "libzl_host.so")
+LIT_PRELUDE = r"""
+#include <cstdint>
+#include <cstring>
+// host stand-ins for the few device intrinsics the bit reader uses (PTX shf.{l,r}.{wrap,clamp})
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)(v >> (s & 31)); }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; s = s > 32 ? 32 : s; return (unsigned)(s == 32 ? v >> 32 : v >> s); }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; s = s > 32 ? 32 : s; return (unsigned)((s == 32 ? (v << 31) << 1 : v << s) >> 32); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+"""
+LIT_WRAPPERS = r"""
+extern "C" {
+// a Huffman-coded literals payload (weights header + 1 or 4 streams, as HUF_compress{1,4}X writes it) -> regen bytes.
+// returns 1 on success, 0 on a rejected payload; *hdr_used = bytes of the weights header
+int t_literals_decode(u8* dst, u32 regen, const u8* payload, u32 n, int single, u32* hdr_used, u32* table_bytes)
+{
+    static u8 ws[256]; static u16 cells[4096 + 8]; u32 rank[13], log = 0, nsym = 0;
+    u32 const used = zb_huf_weights(ws, payload, n, log, nsym, rank);
+    *hdr_used = used;
+    if (used == 0 || used >= n) return 0;
+    u32 shift, T, base, bytes;
+    zb_huf_shape(log, rank, shift, T, base, bytes);
+    *table_bytes = bytes;
+    zb_huf_fill(cells, ws, log, nsym, rank, shift, base);
+    ZbHufTab t; t.cells = cells; t.log = log; t.shift = shift; t.T = T; t.base = base;
+    return zb_huf_block(dst, regen, payload + used, n - used, single != 0, t) ? 1 : 0;
+}
+u32 t_read_ncount(short* norm, u32* max_sym, u32* log, const u8* s, u32 n) { u32 ms = *max_sym, lg = 0; u32 r = zb_read_ncount(norm, ms, lg, s, n); *max_sym = ms; *log = lg; return r; }
+}
+"""
+
+
+def build_literals_decoder():
+    """Host build of the decoder's literal path: zb_common.cuh (bit reader) + the NCount reader of zb_decode.cu + the
+    Huffman weights / split table / 1- and 4-stream decode of zb_entropy.cuh."""
+    os.makedirs(BUILD, exist_ok=True)
+    csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
+    dec = open(os.path.join(csrc, "zb_decode.cu")).read()
+    a = dec.index("struct ZbFwdR {"); b = dec.index("// additional-bit count of a symbol code")
+    ent = open(DEC_SRC).read()
+    c = ent.index("// --- Huffman weights (HUF_readStats_body)"); d = ent.index("// Resolve one sequence-table descriptor")
+    text = (LIT_PRELUDE + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh") + dec[a:b] + ent[c:d] + LIT_WRAPPERS)
+    cpp = os.path.join(BUILD, "zl_host.cpp")
+    if not (os.path.exists(LIT_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", LIT_LIB, cpp])
+    L = C.CDLL(LIT_LIB)
+    L.t_read_ncount.restype = C.c_uint32
+    return L
+
+
 def build():
     os.makedirs(BUILD, exist_ok=True)
     cpp = os.path.join(BUILD, "ze_host.cpp")
