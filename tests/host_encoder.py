@@ -136,6 +136,8 @@ int t_literals_decode(u8* dst, u32 regen, const u8* payload, u32 n, int single, 
     ZbHufTab t; t.cells = cells; t.log = log; t.shift = shift; t.T = T; t.base = base;
     return zb_huf_block(dst, regen, payload + used, n - used, single != 0, t) ? 1 : 0;
 }
+// the tANS decode table of one sequence stream (kind 0 LL, 1 OF, 2 ML): cells[1 << log], norm is consumed
+void t_build_fse(u32* cells, short* norm, u32 max_sym, u32 log, int kind) { zb_build_fse((ZbFseCell*)cells, norm, max_sym, log, kind); }
 u32 t_read_ncount(short* norm, u32* max_sym, u32* log, const u8* s, u32 n) { u32 ms = *max_sym, lg = 0; u32 r = zb_read_ncount(norm, ms, lg, s, n); *max_sym = ms; *log = lg; return r; }
 }
 """
@@ -147,10 +149,12 @@ def build_literals_decoder():
     os.makedirs(BUILD, exist_ok=True)
     csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
     dec = open(os.path.join(csrc, "zb_decode.cu")).read()
-    a = dec.index("struct ZbFwdR {"); b = dec.index("// additional-bit count of a symbol code")
+    a = dec.index("struct ZbFwdR {"); b = dec.index("__global__ void zb_build_default_tables()")
+    k0 = dec.index("__constant__ u8 c_LL_bits[36]"); k1 = dec.index("enum { K_LL = 0")
+    k1 = dec.index("\n", k1) + 1
     ent = open(DEC_SRC).read()
     c = ent.index("// --- Huffman weights (HUF_readStats_body)"); d = ent.index("// Resolve one sequence-table descriptor")
-    text = (LIT_PRELUDE + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh") + dec[a:b] + ent[c:d] + LIT_WRAPPERS)
+    text = (LIT_PRELUDE + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh") + dec[k0:k1] + dec[a:b] + ent[c:d] + LIT_WRAPPERS)
     cpp = os.path.join(BUILD, "zl_host.cpp")
     if not (os.path.exists(LIT_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
         open(cpp, "w").write(text)

@@ -152,3 +152,51 @@ def test_ncount_reader_equals_the_reference(libs):
                         assert list(mine[:ms.value + 1]) == list(theirs[:rms.value + 1])
                         agree += 1
     assert valid > 200 and agree > valid
+
+
+LL_BITS = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+ML_BITS = [0] * 32 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+LL_DEF = [4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1]
+OF_DEF = [1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1]
+ML_DEF = [1, 4, 3, 2, 2, 2, 2, 2, 2] + [1] * 37 + [-1] * 7
+
+
+def test_sequence_decode_tables_equal_the_reference(libs):
+    """zb_build_fse (our 4-byte cells: next state | bits | extra bits | symbol) holds the same state machine as the
+    reference's ZSTD_buildFSETable (zstd/zstd.c:46118) for the predefined distributions and for random ones."""
+    ours, ref = libs
+    rng = np.random.default_rng(24)
+    cases = [(0, LL_DEF, 6), (1, OF_DEF, 5), (2, ML_DEF, 6)]
+    for kind, n_sym, maxlog in ((0, 36, 9), (1, 32, 8), (2, 53, 9)):
+        for k in range(25):
+            total = int(rng.integers(40, 20000))
+            p = rng.geometric(0.2, total) - 1 if k % 2 else rng.integers(0, n_sym, total)
+            count = np.bincount(np.clip(p, 0, n_sym - 1), minlength=n_sym).astype(np.uint32)
+            max_sym = int(np.nonzero(count)[0].max())
+            if np.count_nonzero(count) < 2:
+                continue
+            log = int(rng.integers(5, maxlog + 1))
+            if (1 << log) < np.count_nonzero(count):
+                continue
+            norm = (C.c_short * 64)()
+            r = ref.FSE_normalizeCount(norm, log, (C.c_uint * 64)(*count.tolist()), total, max_sym, 1)
+            if not ref.FSE_isError(C.c_size_t(r)):
+                cases.append((kind, list(norm[:max_sym + 1]), log))
+    assert len(cases) > 40
+    ident = (C.c_uint32 * 64)(*range(64))                      # baseValue := the symbol itself, so the reference cell names its symbol
+    for kind, norm_l, log in cases:
+        bits_l = LL_BITS if kind == 0 else (list(range(32)) if kind == 1 else ML_BITS)
+        bits = (C.c_ubyte * 64)(*bits_l)
+        size = 1 << log
+        dt = (C.c_uint64 * (size + 1))()                       # ZSTD_seqSymbol is 8 bytes; dt[0] is the header
+        wk = (C.c_uint32 * 512)()
+        ref.ZSTD_buildFSETable(dt, (C.c_short * 64)(*norm_l), len(norm_l) - 1, ident, bits, log, wk, 2048, 0)
+        raw = np.frombuffer(dt, dtype=np.uint8)[8:].reshape(size, 8)
+        next_state = raw[:, 0:2].copy().view(np.uint16)[:, 0]
+        add_bits, nb_bits = raw[:, 2], raw[:, 3]
+        sym = raw[:, 4:8].copy().view(np.uint32)[:, 0]
+        cells = (C.c_uint32 * size)()
+        ours.t_build_fse(cells, (C.c_short * 64)(*norm_l), len(norm_l) - 1, log, kind)
+        c = np.frombuffer(cells, dtype=np.uint32)
+        assert ((c & 1023) == next_state).all() and (((c >> 10) & 15) == nb_bits).all()
+        assert (((c >> 14) & 31) == add_bits).all() and ((c >> 19) == sym).all(), (kind, log)
