@@ -108,6 +108,29 @@ def build_decoder_helpers():
     return L
 
 
+HDR_LIB = os.path.join(BUILD, "libzh_host.so")
+
+
+def build_frame_header():
+    """Host build of ze_frame_header (zb_encode.cu): u32 t_frame_header(u8* out, u64 size, checksum, content_size, dict_id)."""
+    os.makedirs(BUILD, exist_ok=True)
+    src = open(SRC).read()
+    a = src.index("__device__ __forceinline__ u32 ze_frame_header")
+    b = src.index("\n}\n", a) + 3
+    text = (PRELUDE + "struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };\n"
+            + src[a:b].replace("__device__ __forceinline__", "static inline")
+            + 'extern "C" u32 t_frame_header(u8* o, u64 size, u32 checksum, u32 content_size, u32 dict_id)\n'
+              "{ ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3; return ze_frame_header(o, size, P); }\n")
+    cpp = os.path.join(BUILD, "zh_host.cpp")
+    if not (os.path.exists(HDR_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", HDR_LIB, cpp])
+    L = C.CDLL(HDR_LIB)
+    L.t_frame_header.restype = C.c_uint32
+    L.t_frame_header.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    return L
+
+
 LIT_LIB = os.path.join(BUILD, "libzl_host.so")
 LIT_PRELUDE = r"""
 #include <cstdint>

@@ -262,3 +262,35 @@ def test_split_huffman_decode_table_equals_the_full_table(libs):
                 lo = code[s] << (log - nb[s])
                 assert full[lo] == (s | (nb[s] << 8)) and full[lo + (1 << (log - nb[s])) - 1] == (s | (nb[s] << 8))
     assert saw_split
+
+
+def test_frame_header_bytes_equal_the_reference():
+    """ze_frame_header writes the header the reference writes (ZSTD_writeFrameHeader, zstd/zstd.c:27649) for every size
+    class of the content-size field, with and without checksum, and for 1-, 2- and 4-byte dictionary ids; and a header the
+    reference parses back when the content size is left out."""
+    from oracle import RefZstd
+    ref = RefZstd()
+    H = host_encoder.build_frame_header()
+    rng = np.random.default_rng(11)
+    for size in (0, 1, 255, 256, 257, 4096, 65791, 65792, 131072, 300000, 1 << 20):
+        data = rng.integers(0, 256, size).astype(np.uint8).tobytes()
+        for checksum in (0, 1):
+            frame = ref.compress(data, level=3, checksum=bool(checksum))
+            out = (C.c_ubyte * 32)()
+            n = H.t_frame_header(out, size, checksum, 1, 0)
+            assert bytes(out[:n]) == frame[:n], (size, checksum)
+    # dictionary ids: the header field the reference's parser reads back
+    for did in (7, 300, 70000, 1123828263):
+        for cs in (0, 1):
+            out = (C.c_ubyte * 32)()
+            n = H.t_frame_header(out, 5000, 1, cs, did)
+            hdr = bytes(out[:n])
+            fhd = hdr[4]
+            assert fhd & 3 == (1 if did < 256 else 2 if did < 65536 else 3) and (fhd >> 2) & 1 == 1
+            pos = 5 + (0 if cs else 1)
+            k = [0, 1, 2, 4][fhd & 3]
+            assert int.from_bytes(hdr[pos:pos + k], "little") == did
+            if cs:
+                assert (fhd >> 5) & 1 == 1 and int.from_bytes(hdr[pos + k:n], "little") + 256 == 5000
+            else:
+                assert (fhd >> 5) & 1 == 0 and (1 << (10 + (hdr[5] >> 3))) >= 5000
