@@ -131,6 +131,29 @@ def build_frame_header():
     return L
 
 
+PARSE_LIB = os.path.join(BUILD, "libzp_host.so")
+
+
+def build_header_parser():
+    """Host build of the device frame-header parser (zb_parse_header, zb_decode.cu):
+    t_parse_header(src, n, out[6] = {content_size, window, dict_id, hdr_size, checksum, status})."""
+    os.makedirs(BUILD, exist_ok=True)
+    csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
+    dec = open(os.path.join(csrc, "zb_decode.cu")).read()
+    a = dec.index("struct ZbHdr {")
+    b = dec.index("// skip leading skippable frames")
+    text = (LIT_PRELUDE + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh") + dec[a:b]
+            + 'extern "C" void t_parse_header(const u8* s, u64 n, u64* out)\n'
+              "{ ZbHdr h; zb_parse_header(s, n, h); out[0] = h.content_size; out[1] = h.window; out[2] = h.dict_id; out[3] = h.hdr_size; out[4] = h.checksum; out[5] = h.status; }\n")
+    cpp = os.path.join(BUILD, "zp_host.cpp")
+    if not (os.path.exists(PARSE_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", PARSE_LIB, cpp])
+    L = C.CDLL(PARSE_LIB)
+    L.t_parse_header.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    return L
+
+
 LIT_LIB = os.path.join(BUILD, "libzl_host.so")
 LIT_PRELUDE = r"""
 #include <cstdint>
