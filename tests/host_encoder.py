@@ -154,6 +154,117 @@ def build_header_parser():
     return L
 
 
+KERNEL_LIB = os.path.join(BUILD, "libzk_host.so")
+KERNEL_SHIMS = r"""
+// one emulated thread (lane 0 of warp 0 of CTA 0): warp votes and shuffles see only that lane
+struct ZbDim3 { unsigned x, y, z; };
+static ZbDim3 zb_tid = {0, 0, 0}, zb_bid = {0, 0, 0}, zb_bdim = {256, 1, 1};
+#define threadIdx zb_tid
+#define blockIdx zb_bid
+#define blockDim zb_bdim
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return T(0); }     // partner lanes contribute nothing
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) {}
+static inline void __syncthreads() {}
+static inline long long clock64() { return 0; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+alignas(16) unsigned char zb_smem[232448 + 64];
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+"""
+KERNEL_WRAPPERS = r"""
+// Decode ONE frame with the entropy kernel's own code (one lane), then regenerate the bytes from its block / sequence /
+// literal records exactly as the execute kernels read them.  returns the status code; *out_n = bytes produced.
+extern "C" int t_decode_frame(const u8* src, u64 n, const u8* dict_raw, u32 dict_n, u8* out, u64 cap, u64* out_n, u32* n_blocks, u32* n_seq)
+{
+    static bool tables = false;
+    if (!tables) { zb_build_default_tables(); tables = true; }
+    // the CTA-wide baseline LUT is filled by threads 0..52; only thread 0 exists here
+    { u32* const lutLL = (u32*)zb_smem; u32* const lutML = lutLL + 36; for (u32 i = 0; i < 36; i++) lutLL[i] = c_LL_base[i]; for (u32 i = 0; i < 53; i++) lutML[i] = c_ML_base[i]; }
+    static ZbDictDigest dg; ZbDictDev dict; memset(&dict, 0, sizeof dict);
+    if (dict_raw && dict_n) {
+        zb_digest_dict(dict_raw, dict_n, &dg);
+        if (dg.status != ZB_OK) return (int)dg.status;
+        if (dg.has_entropy) {
+            dict.content = dict_raw + dg.content_off; dict.content_size = dict_n - dg.content_off; dict.dict_id = dg.dict_id; dict.has_entropy = 1;
+            dict.huf = dg.huf; dict.huf_log = dg.huf_log; dict.ll = dg.ll; dict.of = dg.of; dict.ml = dg.ml;
+            dict.ll_log = dg.ll_log; dict.of_log = dg.of_log; dict.ml_log = dg.ml_log;
+            dict.rep[0] = dg.rep[0]; dict.rep[1] = dg.rep[1]; dict.rep[2] = dg.rep[2];
+        } else { dict.content = dict_raw; dict.content_size = dict_n; }
+    }
+    ZbSegment seg; seg.offset = 0; seg.length = n;
+    ZbFrameInfo fi; zb_scan_frames(src, &seg, 1, &fi);
+    if (fi.status != ZB_OK) return (int)fi.status;
+    u64 const want = fi.content_size != ZB_CONTENT_UNKNOWN ? fi.content_size : cap;
+    if (want > cap) return (int)ZB_E_DSTSIZE_TOO_SMALL;
+    ZbFramePlace place[2]; memset(place, 0, sizeof place);
+    place[0].dst_cap = want; place[1].dst_off = want; place[1].blk_off = fi.n_blocks; place[1].seq_off = fi.n_seq_rec; place[1].lit_off = fi.n_lit;
+    ZbBlock* blocks = new ZbBlock[fi.n_blocks + 1]; ZbSeq* seqs = new ZbSeq[fi.n_seq_rec + 2]; u8* lits = new u8[fi.n_lit + 64];
+    u32 counter = 0, status = ZB_OK, ck = 0; u64 out_size = 0;
+    u64 sizes = want;
+    zb_entropy_decode<8>(src, &seg, 1, place, fi.content_size != ZB_CONTENT_UNKNOWN ? &sizes : nullptr, blocks, seqs, lits, &counter, dict, &status, &out_size, &ck, 1);
+    *n_blocks = fi.n_blocks; *n_seq = 0;
+    // zb_finish's job for one frame; the kernel records errors in status[]
+    int rc = (int)status;
+    if (rc == ZB_OK) {
+        const u8* const dict_end = dict.content + dict.content_size;
+        u64 total = 0;
+        for (u32 bi = 0; bi < fi.n_blocks; bi++) {
+            ZbBlock const& B = blocks[bi];
+            u8* const bout = out + B.out_pos;
+            if (B.out_pos + B.regen > cap) { rc = (int)ZB_E_DSTSIZE_TOO_SMALL; break; }
+            if (B.kind == ZB_BLK_RAW) memcpy(bout, src + B.src_pos, B.regen);
+            else if (B.kind == ZB_BLK_RLE) memset(bout, (int)B.lit_byte, B.regen);
+            else {
+                const u8* const lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
+                const ZbSeq* const sq = seqs + B.seq_pos;
+                *n_seq += B.n_seq;
+                for (u32 i = 0; i <= B.n_seq; i++) {
+                    u32 const ll = i < B.n_seq ? sq[i + 1].x - sq[i].x : B.n_lit - sq[i].x;
+                    for (u32 k = 0; k < ll; k++) bout[sq[i].y + k] = B.lit_kind == ZB_LIT_RLE ? (u8)B.lit_byte : lit[sq[i].x + k];
+                    if (i == B.n_seq) break;
+                    long long const m0 = (long long)B.out_pos + sq[i].y + ll;
+                    for (u32 k = 0; k < sq[i].z; k++) { long long const sp = m0 + k - (long long)sq[i].w; out[m0 + k] = sp < 0 ? dict_end[sp] : out[sp]; }
+                }
+            }
+            total = B.out_pos + B.regen;
+        }
+        *out_n = total;
+    }
+    delete[] blocks; delete[] seqs; delete[] lits;
+    return rc;
+}
+"""
+
+
+def build_entropy_kernel():
+    """Host build of the decode kernels' own source (header scan, dictionary digest, the whole lane-per-frame entropy
+    kernel) with a single emulated lane, plus a serial execute over the records the kernel writes."""
+    os.makedirs(BUILD, exist_ok=True)
+    csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
+    dec = open(os.path.join(csrc, "zb_decode.cu")).read()
+    a = dec.index('#include "zb_common.cuh"')
+    a = dec.index("\n", a) + 1
+    b = dec.index("// K4: LZ copy-execute")
+    b = dec.rindex("// ====", 0, b)
+    body = dec[a:b].replace('#include "zb_entropy.cuh"', open(DEC_SRC).read().replace("#pragma once", ""))
+    d0 = dec.index("__global__ void zb_digest_dict(")
+    d1 = dec.index("// ====", d0)
+    text = (LIT_PRELUDE + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh") + KERNEL_SHIMS + body + dec[d0:d1] + KERNEL_WRAPPERS)
+    cpp = os.path.join(BUILD, "zk_host.cpp")
+    if not (os.path.exists(KERNEL_LIB) and os.path.exists(cpp) and open(cpp).read() == text):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", KERNEL_LIB, cpp])
+    L = C.CDLL(KERNEL_LIB)
+    L.t_decode_frame.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    return L
+
+
 LIT_LIB = os.path.join(BUILD, "libzl_host.so")
 LIT_PRELUDE = r"""
 #include <cstdint>
