@@ -1156,10 +1156,15 @@ __device__ __forceinline__ u32 ze_frame_header(u8* o, u64 size, ZeParams P)
     u32 const did = P.dict_id ? (P.dict_id < 256 ? 1 : (P.dict_id < 65536 ? 2 : 3)) : 0;
     if (P.content_size) {
         u32 const fcs = (size >= 256) + (size >= 65536 + 256) + (size >= 0xFFFFFFFFull);
-        o[p++] = (u8)((fcs << 6) | (1u << 5) | (P.checksum << 2) | did);          // single segment: no window byte
+        // like the reference at level 3 (window log 21): a frame is "single segment" (window = content) only up to 2 MiB;
+        // bigger frames declare a 2 MiB window, so that streaming decoders with a window limit still take them
+        // (our matches never reach further back than 64 KiB + the dictionary tail)
+        bool const single = size <= (1ull << 21);
+        o[p++] = (u8)((fcs << 6) | ((single ? 1u : 0u) << 5) | (P.checksum << 2) | did);
+        if (!single) o[p++] = (u8)((21 - 10) << 3);
         if (did == 1) o[p++] = (u8)P.dict_id; else if (did == 2) { o[p++] = (u8)P.dict_id; o[p++] = (u8)(P.dict_id >> 8); }
         else if (did == 3) for (int k = 0; k < 4; k++) o[p++] = (u8)(P.dict_id >> (8 * k));
-        if (fcs == 0) o[p++] = (u8)size;
+        if (fcs == 0) { if (single) o[p++] = (u8)size; }
         else if (fcs == 1) { u32 const v = (u32)size - 256; o[p++] = (u8)v; o[p++] = (u8)(v >> 8); }
         else if (fcs == 2) for (int k = 0; k < 4; k++) o[p++] = (u8)(size >> (8 * k));
         else for (int k = 0; k < 8; k++) o[p++] = (u8)(size >> (8 * k));

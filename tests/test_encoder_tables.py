@@ -272,8 +272,8 @@ def test_frame_header_bytes_equal_the_reference():
     ref = RefZstd()
     H = host_encoder.build_frame_header()
     rng = np.random.default_rng(11)
-    for size in (0, 1, 255, 256, 257, 4096, 65791, 65792, 131072, 300000, 1 << 20):
-        data = rng.integers(0, 256, size).astype(np.uint8).tobytes()
+    for size in (0, 1, 255, 256, 257, 4096, 65791, 65792, 131072, 300000, 1 << 20, 2 << 20, (2 << 20) + 1, 3 << 20, 9 << 20):
+        data = rng.integers(0, 256, size).astype(np.uint8).tobytes() if size <= (1 << 20) else bytes(size)
         for checksum in (0, 1):
             frame = ref.compress(data, level=3, checksum=bool(checksum))
             out = (C.c_ubyte * 32)()
