@@ -23,6 +23,12 @@
 // A second kernel lays the frames out tightly (frame header ZSTD_writeFrameHeader :27649).
 #include "zb_common.cuh"
 
+// Lock-step marker for the CPU emulation of tests/simt.h (fibers run ahead between warp collectives; the hardware does not).
+// Expands to nothing in the device build.
+#ifndef ZB_SIMT_STEP
+#define ZB_SIMT_STEP()
+#endif
+
 #define ZE_THREADS   128
 #define ZE_HLOG      14
 #define ZE_UNIT      1024
@@ -612,7 +618,9 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                         #pragma unroll
                         for (u32 u = 0; u < 4; u++) {
                             oldv[u] = va[u] ? vhead[hh[u]] : 0xFFFFu;
+                            ZB_SIMT_STEP();                              // (CPU emulation only: all lanes load before any lane stores, as the hardware does)
                             if (in_[u]) vhead[hh[u]] = (u16)pvv[u];
+                            ZB_SIMT_STEP();
                         }
                         #pragma unroll
                         for (u32 u = 0; u < 4; u++) {
@@ -699,6 +707,9 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                 bool const extending = alive && mode == 1;
                 if (!__any_sync(0xFFFFFFFFu, searching || extending)) break;
                 if (alive && !searching && !extending) alive = false;
+                // dist[] is a hint: a distance that would reach in front of the history (only a corrupted table could hold one)
+                // is dropped here, so that the parse never forms an address outside the block and the dictionary tail
+                if (searching) { if (d0 > ip + D) d0 = 0; if (d1 > ip + 1 + D) d1 = 0; }
                 // all loads of the step, unconditional (invalid ones alias the current position) and issued
                 // back to back as raw aligned words; the funnel shifts that consume them come afterwards
                 u64 A = 0, B = 0, C1 = 0, RP = 0, RQ = 0; u32 bka = 0, bkb = 1, d2 = 0, bk_max = 0;

@@ -154,6 +154,73 @@ def build_header_parser():
     return L
 
 
+SIM_LIB = os.path.join(BUILD, "libzs_host.so")
+SIM_WRAPPERS = r"""
+// The whole compression path of the library on the CPU: block jobs as zb_api.cu makes them, zb_compress_blocks on
+// `n_ctas` CTAs of 128 threads, then the frame layout kernels.  No dictionary, input resident.  Returns total bytes.
+extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u64* seg_len, u32 n_segs, u32 checksum, u32 content_size,
+                                      u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len)
+{
+    std::vector<ZbSegment> segs(n_segs); std::vector<ZeBlockJob> jobs; std::vector<ZeSegInfo> info(n_segs);
+    u32 max_block = 0;
+    for (u32 i = 0; i < n_segs; i++) {
+        segs[i].offset = seg_off[i]; segs[i].length = seg_len[i];
+        info[i].first_job = jobs.size(); info[i].n_jobs = 0; info[i].pad = 0;
+        for (u64 pos = 0; pos < seg_len[i];) {
+            u32 const sz = (u32)(seg_len[i] - pos < ZE_BLOCK ? seg_len[i] - pos : ZE_BLOCK);
+            ZeBlockJob j; j.src_pos = seg_off[i] + pos; j.size = sz; j.seg = i; j.first = pos == 0; j.last = pos + sz == seg_len[i];
+            jobs.push_back(j); info[i].n_jobs++; pos += sz; if (sz > max_block) max_block = sz;
+        }
+    }
+    u32 const nj = (u32)jobs.size();
+    u64 const slot_bytes = ((u64)max_block + (max_block >> 7) + 64 + 15) & ~15ull;
+    std::vector<u8> slots((size_t)(nj + 1) * slot_bytes); std::vector<ZeBlockOut> outs(nj + 1);
+    if (n_ctas > nj) n_ctas = nj ? nj : 1;
+    ZeScratch* scratch = (ZeScratch*)aligned_alloc(64, ((sizeof(ZeScratch) + 63) & ~(size_t)63) * n_ctas);
+    u32 counter = 0;
+    ZeDict dict; memset(&dict, 0, sizeof dict);
+    ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
+    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = 0; P.level = 3;
+    if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    std::vector<u64> sizes(n_segs); std::vector<ZbSegment> out_segs(n_segs); u64 total = 0;
+    simt::launch((n_segs + 255) / 256, 256, [&] { zb_frame_sizes(segs.data(), info.data(), outs.data(), n_segs, P, sizes.data()); });
+    simt::launch(1, 1024, [&] { zb_scan_sizes(sizes.data(), n_segs, out_segs.data(), &total); });
+    free(scratch);
+    if (total > out_cap) return -1;
+    simt::launch((n_segs + 7) / 8, 256, [&] { zb_write_frames(src, segs.data(), info.data(), outs.data(), slots.data(), slot_bytes, n_segs, P, out_segs.data(), out); });
+    for (u32 i = 0; i < n_segs; i++) { out_off[i] = out_segs[i].offset; out_len[i] = out_segs[i].length; }
+    return (long long)total;
+}
+"""
+
+
+def build_compress_sim():
+    """Host build of the whole compression kernel source (zb_encode.cu up to its launchers) on the mini SIMT runtime of
+    tests/simt.h: 128 fibers per CTA, warp collectives and barriers as rendezvous."""
+    os.makedirs(BUILD, exist_ok=True)
+    import re
+    csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
+    enc = open(SRC).read()
+    a = enc.index('#include "zb_common.cuh"')
+    a = enc.index("\n", a) + 1
+    b = enc.index('extern "C" {')
+    b = enc.rindex("// ====", 0, enc.rindex("// ====", 0, b))
+    body = enc[a:b]
+    body = re.sub(r"extern __shared__ __align__\(16\) u8 (\w+)\[\];", r"u8* const \1 = simt_dyn_smem;", body)
+    text = (LIT_PRELUDE + "#include <cmath>\n#include <vector>\n" + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh")
+            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n#define ZB_SIMT_STEP() __syncwarp()\n" + body + SIM_WRAPPERS)
+    cpp = os.path.join(BUILD, "zs_host.cpp")
+    if not (os.path.exists(SIM_LIB) and os.path.exists(cpp) and open(cpp).read() == text
+            and os.path.getmtime(SIM_LIB) >= os.path.getmtime(os.path.join(HERE, "simt.h"))):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", SIM_LIB, cpp])
+    L = C.CDLL(SIM_LIB)
+    L.t_compress_batch.restype = C.c_longlong
+    L.t_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    return L
+
+
 KERNEL_LIB = os.path.join(BUILD, "libzk_host.so")
 KERNEL_SHIMS = r"""
 // one emulated thread (lane 0 of warp 0 of CTA 0): warp votes and shuffles see only that lane

@@ -1,0 +1,114 @@
+"""The compression kernels' own source, run on the CPU.
+
+tests/host_encoder.build_compress_sim() compiles python_zstandard_b200/csrc/zb_encode.cu (everything above its
+launchers: the block kernel with all its phases, the frame layout kernels, XXH64) with g++ on the mini SIMT runtime of
+tests/simt.h -- every thread of a CTA is a fiber, __syncthreads and the warp collectives are rendezvous points -- and
+drives it the way zb_api.cu does (block jobs, persistent CTAs, slots, frame sizes, scan, frame writer).  The frames go
+through the unmodified reference decoder and the oracle.  The device build differs only in timing, so the compressed
+bytes are the same except where the link phase lets lanes of one step race for a hash slot (the hardware picks a winner
+we cannot predict); sizes are asserted against the reference with the margins the GPU suite uses."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import corpus
+from tests import host_encoder
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libzstd_ref.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref is built from /root/reference (see oracle/Makefile)")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return host_encoder.build_compress_sim()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import RefZstd
+    return RefZstd()
+
+
+def compress(sim, segs, checksum=False, content_size=True, n_ctas=2):
+    """[frame bytes] for a batch of byte strings through the kernel source."""
+    blob = b"".join(segs) + bytes(64)
+    off = np.cumsum([0] + [len(s) for s in segs[:-1]]).astype(np.uint64)
+    ln = np.array([len(s) for s in segs], dtype=np.uint64)
+    src = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    cap = sum(len(s) + len(s) // 128 + 64 for s in segs) + 64
+    out = (C.c_ubyte * cap)()
+    oo = (C.c_uint64 * len(segs))(); ol = (C.c_uint64 * len(segs))()
+    tot = sim.t_compress_batch(C.addressof(src), off.ctypes.data, ln.ctypes.data, len(segs), int(checksum), int(content_size), n_ctas,
+                               C.addressof(out), cap, C.addressof(oo), C.addressof(ol))
+    assert tot >= 0 and tot == sum(ol)
+    assert all(oo[i] == sum(ol[:i]) for i in range(len(segs)))          # frames are packed tightly, in order
+    return [bytes(out[oo[i]:oo[i] + ol[i]]) for i in range(len(segs))]
+
+
+def test_reference_known_answers(sim, ref):
+    """Byte-exact frames where the reference's tests pin them (tests/test_compressor_compress.py:19,28,34;
+    tests/test_compressor_multi_compress_to_buffer.py:45,64 and the frames SURVEY.md probed)."""
+    f = compress(sim, [b"foo" * 12, b"bar" * 6], checksum=True)
+    assert f[0] == bytes.fromhex("28b52ffd24244d000018666f6f01008e6e08a788b46f")
+    assert len(f[0]) + len(f[1]) == 44 and f[1] == ref.compress(b"bar" * 6, level=3, checksum=True)
+    f = compress(sim, [b"foo" * 4, b"bar" * 6], checksum=True)
+    assert len(f[0]) + len(f[1]) == 47 and f[0] == ref.compress(b"foo" * 4, level=3, checksum=True)
+    assert compress(sim, [b"", b"foo"]) == [bytes.fromhex("28b52ffd2000010000"), bytes.fromhex("28b52ffd2003190000666f6f")]
+    assert compress(sim, [b"", b"x"], content_size=False)[0] == bytes.fromhex("28b52ffd0000010000")
+    assert len(compress(sim, [b"x" * 64], checksum=True)[0]) <= 21
+
+
+def test_round_trips_through_the_reference_and_the_oracle(sim, ref):
+    from oracle import Oracle
+    orc = Oracle()
+    rng = np.random.default_rng(41)
+    text = corpus.text_corpus(1 << 20)
+    segs = [b"a", b"ab" * 5, bytes(9), bytes(text[:300]), bytes(text[1000:1000 + 2047]), bytes(text[5000:5000 + 2048]),
+            bytes(text[9000:9000 + 4096]), bytes(40000), rng.integers(0, 256, 20000).astype(np.uint8).tobytes(),
+            corpus.binary_blob(30000).tobytes(), bytes(text[20000:20000 + 70000]),
+            (b"0123456789abcdef" * 3000) + bytes(text[:777]) + b"0123456789abcdef" * 500]
+    for checksum in (False, True):
+        frames = compress(sim, segs, checksum=checksum, n_ctas=3)
+        for s, f in zip(segs, frames):
+            assert ref.decompress(f, len(s)) == s
+            assert orc.decompress(f, len(s)) == s
+            assert len(f) <= len(s) + len(s) // 128 + 24                 # never much larger than the input
+    frames = compress(sim, segs[:6], content_size=False)
+    for s, f in zip(segs[:6], frames):
+        assert ref.decompress(f, len(s)) == s
+
+
+def test_multi_block_segments(sim, ref):
+    """Segments above 128 KiB are cut into blocks that different CTAs may take; frame headers follow the size class."""
+    text = corpus.text_corpus(1 << 20)
+    segs = [bytes(text[100000:100000 + 300000]), bytes(text[:131072]), bytes(text[7:7 + 131073])]
+    frames = compress(sim, segs, checksum=True, n_ctas=4)
+    for s, f in zip(segs, frames):
+        assert ref.decompress(f, len(s)) == s
+    assert len(frames[1]) <= len(ref.compress(segs[1], level=3, checksum=True)) * 1.06      # single block, GPU-suite margin
+
+
+def test_sizes_against_the_reference(sim, ref):
+    """The size margins of tests/test_gpu_compress.py, on the CPU: 4 KiB text within 2 %, mixed content within 3 %."""
+    blob, off, ln = corpus.text_segments(40, 4096)
+    segs = [bytes(blob[int(o):int(o) + int(l)]) for o, l in zip(off, ln)]
+    ours = sum(len(f) for f in compress(sim, segs, n_ctas=4))
+    theirs = sum(len(ref.compress(s, level=3)) for s in segs)
+    assert ours <= theirs * 1.02, (ours, theirs)
+    mix, off, ln = corpus.silesia_mix(6, 32768)
+    segs = [bytes(mix[int(o):int(o) + int(l)]) for o, l in zip(off, ln)]
+    frames = compress(sim, segs, n_ctas=3)
+    assert all(ref.decompress(f, len(s)) == s for s, f in zip(segs, frames))
+    assert sum(map(len, frames)) <= sum(len(ref.compress(s, level=3)) for s in segs) * 1.03
+
+
+def test_frames_above_two_mebibytes_declare_a_window(sim, ref):
+    """Above 2 MiB the header carries a window descriptor (2 MiB, the reference's level-3 window) instead of the
+    single-segment flag; the frame still regenerates the input through the reference decoder."""
+    data = bytes(3 << 20)
+    f = compress(sim, [data], checksum=True, n_ctas=4)[0]
+    theirs = ref.compress(data, level=3, checksum=True)
+    assert f[:10] == theirs[:10] and (f[4] >> 5) & 1 == 0 and f[5] == (21 - 10) << 3
+    assert ref.decompress(f, len(data)) == data
