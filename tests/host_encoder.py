@@ -221,6 +221,75 @@ def build_compress_sim():
     return L
 
 
+DSIM_LIB = os.path.join(BUILD, "libzd_sim.so")
+DSIM_WRAPPERS = r"""
+// The whole decompression path on the CPU, kernel by kernel as zb_api.cu launches them: scan, placement (reduce + scan),
+// the lane-per-frame entropy kernel on `n_ctas` CTAs of `warps` warps with `take` frames per warp, both execute kernels,
+// checksum verification, finish.  Output: tightly packed bytes + per-frame {offset, length}, status[] per frame.
+extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const u64* seg_len, u32 n, const u8* dict_raw, u32 dict_n,
+                                        u32 n_ctas, u32 warps, u32 take, u8* out, u64 out_cap, u64* out_off, u64* out_len, u32* status_out)
+{
+    static bool tables = false;
+    if (!tables) { simt::launch(1, 32, [] { zb_build_default_tables(); }); tables = true; }
+    static ZbDictDigest dg; ZbDictDev dict; memset(&dict, 0, sizeof dict);
+    if (dict_raw && dict_n) {
+        simt::launch(1, 32, [&] { zb_digest_dict(dict_raw, dict_n, &dg); });
+        if (dg.status != ZB_OK) return -(long long)dg.status;
+        if (dg.has_entropy) {
+            dict.content = dict_raw + dg.content_off; dict.content_size = dict_n - dg.content_off; dict.dict_id = dg.dict_id; dict.has_entropy = 1;
+            dict.huf = dg.huf; dict.huf_log = dg.huf_log; dict.ll = dg.ll; dict.of = dg.of; dict.ml = dg.ml;
+            dict.ll_log = dg.ll_log; dict.of_log = dg.of_log; dict.ml_log = dg.ml_log;
+            dict.rep[0] = dg.rep[0]; dict.rep[1] = dg.rep[1]; dict.rep[2] = dg.rep[2];
+        } else { dict.content = dict_raw; dict.content_size = dict_n; }
+    }
+    std::vector<ZbSegment> segs(n); for (u32 i = 0; i < n; i++) { segs[i].offset = seg_off[i]; segs[i].length = seg_len[i]; }
+    std::vector<ZbFrameInfo> info(n); std::vector<ZbFramePlace> place(n + 1); std::vector<u32> status(n, 0);
+    u64 totals[8] = {0}; u32 const pctas = (n + ZB_PLACE_CTA - 1) / ZB_PLACE_CTA; std::vector<u64> partial(pctas * 4 + 4);
+    simt::launch((n + 127) / 128, 128, [&] { zb_scan_frames(src, segs.data(), n, info.data()); });
+    simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_reduce(info.data(), nullptr, n, partial.data()); });
+    simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_scan(info.data(), nullptr, n, partial.data(), place.data(), totals, status.data()); });
+    if (totals[0] > out_cap) return -1000;
+    std::vector<ZbBlock> blocks(totals[1] + 1); std::vector<ZbSeq> seqs(totals[2] + 2); std::vector<u8> lits(totals[3] + 64);
+    std::vector<u64> out_sizes(n, 0); std::vector<u32> ck(n, 0); u32 counter = 0;
+    if (warps == 8) simt::launch(n_ctas, 8 * 32, [&] { zb_entropy_decode<8>(src, segs.data(), n, place.data(), nullptr, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
+    else simt::launch(n_ctas, 7 * 32, [&] { zb_entropy_decode<7>(src, segs.data(), n, place.data(), nullptr, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
+    simt::launch((n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, [&] { zb_execute_tile(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict); });
+    simt::launch((n + 7) / 8, 256, [&] { zb_execute(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict, (u64)ZB_TILE_CAP + 1); });
+    if (totals[4]) simt::launch((n + 127) / 128, 128, [&] { zb_verify_checksums(out, place.data(), out_sizes.data(), info.data(), ck.data(), 0, n, status.data()); });
+    std::vector<ZbSegment> out_segs(n); u32 first_error = 0xFFFFFFFFu;
+    simt::launch((n + 255) / 256, 256, [&] { zb_finish(place.data(), out_sizes.data(), status.data(), n, out_segs.data(), &first_error); });
+    for (u32 i = 0; i < n; i++) { out_off[i] = out_segs[i].offset; out_len[i] = out_segs[i].length; status_out[i] = status[i]; }
+    return (long long)totals[0];
+}
+"""
+
+
+def build_decode_sim():
+    """Host build of ALL decompression kernels (zb_decode.cu + zb_entropy.cuh up to the launchers) on tests/simt.h."""
+    import re
+    os.makedirs(BUILD, exist_ok=True)
+    csrc = os.path.join(ROOT, "python_zstandard_b200", "csrc")
+    dec = open(os.path.join(csrc, "zb_decode.cu")).read()
+    a = dec.index('#include "zb_common.cuh"')
+    a = dec.index("\n", a) + 1
+    b = dec.index('extern "C" {')
+    b = dec.rindex("// ====", 0, dec.rindex("// ====", 0, b))
+    body = dec[a:b].replace('#include "zb_entropy.cuh"', open(DEC_SRC).read().replace("#pragma once", ""))
+    body = re.sub(r"extern __shared__ __align__\(16\) u8 (\w+)\[\];", r"u8* const \1 = simt_dyn_smem;", body)
+    text = (LIT_PRELUDE + "#include <cmath>\n#include <vector>\n" + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh")
+            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n" + body + DSIM_WRAPPERS)
+    cpp = os.path.join(BUILD, "zd_sim.cpp")
+    if not (os.path.exists(DSIM_LIB) and os.path.exists(cpp) and open(cpp).read() == text
+            and os.path.getmtime(DSIM_LIB) >= os.path.getmtime(os.path.join(HERE, "simt.h"))):
+        open(cpp, "w").write(text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", DSIM_LIB, cpp])
+    L = C.CDLL(DSIM_LIB)
+    L.t_decompress_batch.restype = C.c_longlong
+    L.t_decompress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
 KERNEL_LIB = os.path.join(BUILD, "libzk_host.so")
 KERNEL_SHIMS = r"""
 // one emulated thread (lane 0 of warp 0 of CTA 0): warp votes and shuffles see only that lane

@@ -1,0 +1,112 @@
+"""All decompression kernels, run on the CPU kernel by kernel the way zb_api.cu launches them.
+
+tests/host_encoder.build_decode_sim() compiles zb_decode.cu + zb_entropy.cuh (frame scan, placement scans, the
+lane-per-frame entropy kernel with its shared-memory pool claims, both execute kernels with their dependency frontier,
+checksum verification, finish) on the mini SIMT runtime of tests/simt.h: 32 lanes per warp in lock step at every
+collective, 7 or 8 warps per CTA, persistent CTAs pulling frames from the work counter.  Output must equal the
+reference's, per-frame status codes must match what the GPU suite expects."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import corpus
+from tests import helpers, host_encoder
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libzstd_ref.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref is built from /root/reference (see oracle/Makefile)")
+PAD = 64
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return host_encoder.build_decode_sim()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import RefZstd
+    return RefZstd()
+
+
+def decompress(sim, frames, sizes, dct=b"", n_ctas=1, warps=8, take=32):
+    """(outputs, statuses) of a batch of frames through the kernels."""
+    blob = bytes(PAD) + b"".join(frames) + bytes(PAD)
+    off = (np.cumsum([0] + [len(f) for f in frames[:-1]]) + PAD).astype(np.uint64)
+    ln = np.array([len(f) for f in frames], dtype=np.uint64)
+    src = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    dbuf = (C.c_ubyte * (len(dct) + 2 * PAD)).from_buffer_copy(bytes(PAD) + dct + bytes(PAD))
+    cap = sum(sizes) + 64
+    out = (C.c_ubyte * cap)()
+    n = len(frames)
+    oo = (C.c_uint64 * n)(); ol = (C.c_uint64 * n)(); st = (C.c_uint32 * n)()
+    tot = sim.t_decompress_batch(C.addressof(src), off.ctypes.data, ln.ctypes.data, n, (C.addressof(dbuf) + PAD) if dct else None, len(dct),
+                                 n_ctas, warps, take, C.addressof(out), cap, C.addressof(oo), C.addressof(ol), C.addressof(st))
+    assert tot >= 0
+    return [bytes(out[oo[i]:oo[i] + ol[i]]) for i in range(n)], list(st)
+
+
+def test_golden_vectors_in_one_batch(sim):
+    vecs = helpers.golden_vectors()
+    plain = [v for v in vecs if not v[3]]
+    outs, st = decompress(sim, [v[1] for v in plain], [len(v[2]) for v in plain])
+    for (name, frame, raw, _), got, s in zip(plain, outs, st):
+        if frame[4] >> 6 == 0 and not (frame[4] >> 5) & 1:        # no content size in the header: the batch call needs sizes
+            assert s == 200, name
+        else:
+            assert s == 0 and got == raw, name
+    withd = [v for v in vecs if v[3]]
+    outs, st = decompress(sim, [v[1] for v in withd], [len(v[2]) for v in withd], withd[0][3])
+    assert st == [0] * len(withd) and outs == [v[2] for v in withd]
+
+
+@pytest.mark.parametrize("warps,take,n_ctas", [(8, 32, 1), (8, 32, 2), (7, 16, 1), (8, 3, 2)])
+def test_batch_of_small_frames_with_bad_ones(sim, ref, warps, take, n_ctas):
+    """70 x 4 KiB level-3 frames (half with checksums) share warps; a corrupted frame, a truncated one and one with a wrong
+    checksum get their own status and do not disturb their neighbours."""
+    blob, off, ln = corpus.text_segments(70, 4096)
+    segs = [bytes(blob[int(o):int(o) + int(l)]) for o, l in zip(off, ln)]
+    frames = [ref.compress(s, level=3, checksum=(i % 2 == 0)) for i, s in enumerate(segs)]
+    bad = bytearray(frames[10]); bad[len(bad) // 2] ^= 0x10; frames[10] = bytes(bad)       # checksummed: any damage is caught
+    frames[21] = frames[21][:-5]
+    wrong = bytearray(frames[34]); wrong[-1] ^= 1; frames[34] = bytes(wrong)
+    outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=n_ctas, warps=warps, take=take)
+    for i, s in enumerate(segs):
+        if i in (10, 21, 34):
+            assert st[i] != 0, i
+        else:
+            assert st[i] == 0 and outs[i] == s, i
+    assert st[34] == 22                                          # checksum_wrong, from zb_verify_checksums
+
+
+def test_large_and_multi_block_frames(sim, ref):
+    """Frames above the 4 KiB tile take the generic execute kernel; 128 KiB blocks, several blocks per frame, long matches,
+    RLE and raw blocks, levels 1..19."""
+    text = corpus.text_corpus(1 << 20)
+    rng = np.random.default_rng(51)
+    segs = [bytes(text[:131072]), bytes(text[50000:50000 + 300000]), bytes(60000), rng.integers(0, 256, 40000).astype(np.uint8).tobytes(),
+            (b"abcdefgh" * 9000) + bytes(text[:100]), corpus.binary_blob(70000).tobytes(), bytes(text[3:3 + 5000])]
+    frames = [ref.compress(s, level=lv, checksum=True) for s, lv in zip(segs, (3, 3, 1, 3, 19, 7, 3))]
+    outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=2, warps=7, take=3)
+    assert st == [0] * len(segs) and outs == segs
+
+
+def test_dictionary_records(sim, ref):
+    recs = corpus.json_records(460)
+    dct = ref.train_dictionary(16384, recs[:400])
+    frames = [ref.compress(r, level=3, dict_data=dct) for r in recs[400:]]
+    outs, st = decompress(sim, frames, [len(r) for r in recs[400:]], dct)
+    assert st == [0] * 60 and outs == recs[400:]
+
+
+def test_kernel_to_kernel_round_trip():
+    """Frames written by the compression kernels (CPU build) regenerate through the decompression kernels (CPU build)."""
+    from tests.test_compress_kernel_host import compress
+    csim = host_encoder.build_compress_sim()
+    dsim = host_encoder.build_decode_sim()
+    text = corpus.text_corpus(1 << 20)
+    segs = [bytes(text[i * 5000:i * 5000 + 3000 + 97 * i]) for i in range(20)] + [bytes(text[200000:200000 + 140000]), bytes(5000), b"q"]
+    frames = compress(csim, segs, checksum=True, n_ctas=3)
+    outs, st = decompress(dsim, frames, [len(s) for s in segs], n_ctas=2)
+    assert st == [0] * len(segs) and outs == segs
