@@ -159,7 +159,7 @@ SIM_WRAPPERS = r"""
 // The whole compression path of the library on the CPU: block jobs as zb_api.cu makes them, zb_compress_blocks on
 // `n_ctas` CTAs of 128 threads, then the frame layout kernels.  No dictionary, input resident.  Returns total bytes.
 extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u64* seg_len, u32 n_segs, u32 checksum, u32 content_size,
-                                      u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len)
+                                      u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len, u32 dual)
 {
     std::vector<ZbSegment> segs(n_segs); std::vector<ZeBlockJob> jobs; std::vector<ZeSegInfo> info(n_segs);
     u32 max_block = 0;
@@ -181,7 +181,8 @@ extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u
     ZeDict dict; memset(&dict, 0, sizeof dict);
     ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
     ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = 0; P.level = 3;
-    if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    if (nj && dual) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    else if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     std::vector<u64> sizes(n_segs); std::vector<ZbSegment> out_segs(n_segs); u64 total = 0;
     simt::launch((n_segs + 255) / 256, 256, [&] { zb_frame_sizes(segs.data(), info.data(), outs.data(), n_segs, P, sizes.data()); });
     simt::launch(1, 1024, [&] { zb_scan_sizes(sizes.data(), n_segs, out_segs.data(), &total); });
@@ -217,7 +218,7 @@ def build_compress_sim():
     L = C.CDLL(SIM_LIB)
     L.t_compress_batch.restype = C.c_longlong
     L.t_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
     return L
 
 

@@ -31,7 +31,7 @@ def ref():
     return RefZstd()
 
 
-def compress(sim, segs, checksum=False, content_size=True, n_ctas=2):
+def compress(sim, segs, checksum=False, content_size=True, n_ctas=2, dual=False):
     """[frame bytes] for a batch of byte strings through the kernel source."""
     blob = b"".join(segs) + bytes(64)
     off = np.cumsum([0] + [len(s) for s in segs[:-1]]).astype(np.uint64)
@@ -41,7 +41,7 @@ def compress(sim, segs, checksum=False, content_size=True, n_ctas=2):
     out = (C.c_ubyte * cap)()
     oo = (C.c_uint64 * len(segs))(); ol = (C.c_uint64 * len(segs))()
     tot = sim.t_compress_batch(C.addressof(src), off.ctypes.data, ln.ctypes.data, len(segs), int(checksum), int(content_size), n_ctas,
-                               C.addressof(out), cap, C.addressof(oo), C.addressof(ol))
+                               C.addressof(out), cap, C.addressof(oo), C.addressof(ol), int(dual))
     assert tot >= 0 and tot == sum(ol)
     assert all(oo[i] == sum(ol[:i]) for i in range(len(segs)))          # frames are packed tightly, in order
     return [bytes(out[oo[i]:oo[i] + ol[i]]) for i in range(len(segs))]
@@ -112,3 +112,22 @@ def test_frames_above_two_mebibytes_declare_a_window(sim, ref):
     theirs = ref.compress(data, level=3, checksum=True)
     assert f[:10] == theirs[:10] and (f[4] >> 5) & 1 == 0 and f[5] == (21 - 10) << 3
     assert ref.decompress(f, len(data)) == data
+
+
+def test_dual_table_mode(sim, ref):
+    """Level >= 4 runs the two-table match finder (4-byte and 8-byte hash heads in the same shared memory): valid frames,
+    never larger than the single-table parse by more than noise, and at the reference's level-3 size or below on text
+    (CPU model tools/enc_model3.c predicted it)."""
+    text = corpus.text_corpus(1 << 20)
+    rng = np.random.default_rng(43)
+    segs = [bytes(text[:131072]), bytes(text[500000:500000 + 4096]), bytes(text[600000:600000 + 4096]), bytes(text[1234:1234 + 1500]),
+            b"foo" * 12, b"", bytes(9000), rng.integers(0, 256, 5000).astype(np.uint8).tobytes(), bytes(text[700000:700000 + 200000])]
+    one = compress(sim, segs, checksum=True, n_ctas=3, dual=False)
+    two = compress(sim, segs, checksum=True, n_ctas=3, dual=True)
+    for s, f in zip(segs, two):
+        assert ref.decompress(f, len(s)) == s if s else len(f) == 13
+    assert sum(map(len, two)) < sum(map(len, one))
+    theirs = [len(ref.compress(segs[i], level=3, checksum=True)) for i in (0, 1, 2)]
+    assert sum(len(two[i]) for i in (0, 1, 2)) <= sum(theirs) * 1.005
+    assert all(len(two[i]) <= t * 1.04 for i, t in zip((0, 1, 2), theirs))           # single 4 KiB segments scatter by a few %
+    assert len(two[0]) <= len(one[0]) * 0.98                      # 128 KiB text: at least 2 % smaller than the single table
