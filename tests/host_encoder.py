@@ -159,7 +159,7 @@ SIM_WRAPPERS = r"""
 // The whole compression path of the library on the CPU: block jobs as zb_api.cu makes them, zb_compress_blocks on
 // `n_ctas` CTAs of 128 threads, then the frame layout kernels.  No dictionary, input resident.  Returns total bytes.
 extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u64* seg_len, u32 n_segs, u32 checksum, u32 content_size,
-                                      u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len, u32 dual)
+                                      u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len, u32 dual, const u8* dict_raw, u32 dict_n)
 {
     std::vector<ZbSegment> segs(n_segs); std::vector<ZeBlockJob> jobs; std::vector<ZeSegInfo> info(n_segs);
     u32 max_block = 0;
@@ -179,8 +179,22 @@ extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u
     ZeScratch* scratch = (ZeScratch*)aligned_alloc(64, ((sizeof(ZeScratch) + 63) & ~(size_t)63) * n_ctas);
     u32 counter = 0;
     ZeDict dict; memset(&dict, 0, sizeof dict);
+    static ZbDictDigest dg; static u16 dtable[1 << ZE_HLOG]; static ZeCTable cct[3];
+    u32 dict_id = 0;
+    if (dict_raw && dict_n) {          // what zb200_ddict_create does: digest, compression view (last <= 32 KiB), hash table, CTables
+        simt::launch(1, 32, [&] { zb_digest_dict(dict_raw, dict_n, &dg); });
+        if (dg.status != ZB_OK) return -2;
+        const u8* content = dg.has_entropy ? dict_raw + dg.content_off : dict_raw;
+        u32 const csize = dg.has_entropy ? dict_n - dg.content_off : dict_n;
+        u32 const D = csize < 32768u ? csize : 32768u;
+        if (D >= 8) {
+            dict.tail = content + (csize - D); dict.D = D; dict.table = dtable; dict_id = dg.dict_id;
+            simt::launch(1, 32, [&] { zb_dict_table(dict.tail, D, dtable); });
+            if (dg.has_entropy) { dict.ent = &dg; dict.cct = cct; simt::launch(1, 96, [&] { zb_dict_ctables(&dg, cct); }); }
+        }
+    }
     ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
-    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = 0; P.level = 3;
+    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3;
     if (nj && dual) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     else if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     std::vector<u64> sizes(n_segs); std::vector<ZbSegment> out_segs(n_segs); u64 total = 0;
@@ -207,6 +221,12 @@ def build_compress_sim():
     b = enc.index('extern "C" {')
     b = enc.rindex("// ====", 0, enc.rindex("// ====", 0, b))
     body = enc[a:b]
+    dec = open(os.path.join(csrc, "zb_decode.cu")).read()
+    da = dec.index("\n", dec.index('#include "zb_common.cuh"')) + 1
+    db = dec.index('extern "C" {')
+    db = dec.rindex("// ====", 0, dec.rindex("// ====", 0, db))
+    dbody = dec[da:db].replace('#include "zb_entropy.cuh"', open(DEC_SRC).read().replace("#pragma once", ""))
+    body = dbody + body                                      # the dictionary digest lives with the decoder
     body = re.sub(r"extern __shared__ __align__\(16\) u8 (\w+)\[\];", r"u8* const \1 = simt_dyn_smem;", body)
     text = (LIT_PRELUDE + "#include <cmath>\n#include <vector>\n" + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh")
             + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n#define ZB_SIMT_STEP() __syncwarp()\n" + body + SIM_WRAPPERS)
@@ -218,7 +238,7 @@ def build_compress_sim():
     L = C.CDLL(SIM_LIB)
     L.t_compress_batch.restype = C.c_longlong
     L.t_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     return L
 
 

@@ -31,7 +31,7 @@ def ref():
     return RefZstd()
 
 
-def compress(sim, segs, checksum=False, content_size=True, n_ctas=2, dual=False):
+def compress(sim, segs, checksum=False, content_size=True, n_ctas=2, dual=False, dct=b""):
     """[frame bytes] for a batch of byte strings through the kernel source."""
     blob = b"".join(segs) + bytes(64)
     off = np.cumsum([0] + [len(s) for s in segs[:-1]]).astype(np.uint64)
@@ -40,8 +40,10 @@ def compress(sim, segs, checksum=False, content_size=True, n_ctas=2, dual=False)
     cap = sum(len(s) + len(s) // 128 + 64 for s in segs) + 64
     out = (C.c_ubyte * cap)()
     oo = (C.c_uint64 * len(segs))(); ol = (C.c_uint64 * len(segs))()
+    dbuf = (C.c_ubyte * (len(dct) + 64)).from_buffer_copy(dct + bytes(64))
     tot = sim.t_compress_batch(C.addressof(src), off.ctypes.data, ln.ctypes.data, len(segs), int(checksum), int(content_size), n_ctas,
-                               C.addressof(out), cap, C.addressof(oo), C.addressof(ol), int(dual))
+                               C.addressof(out), cap, C.addressof(oo), C.addressof(ol), int(dual),
+                               C.addressof(dbuf) if dct else None, len(dct))
     assert tot >= 0 and tot == sum(ol)
     assert all(oo[i] == sum(ol[:i]) for i in range(len(segs)))          # frames are packed tightly, in order
     return [bytes(out[oo[i]:oo[i] + ol[i]]) for i in range(len(segs))]
@@ -131,3 +133,23 @@ def test_dual_table_mode(sim, ref):
     assert sum(len(two[i]) for i in (0, 1, 2)) <= sum(theirs) * 1.005
     assert all(len(two[i]) <= t * 1.04 for i, t in zip((0, 1, 2), theirs))           # single 4 KiB segments scatter by a few %
     assert len(two[0]) <= len(one[0]) * 0.98                      # 128 KiB text: at least 2 % smaller than the single table
+
+
+def test_dictionary_compression(sim, ref):
+    """Config 4 on the CPU build: records against a trained dictionary (digest, hash table and CTables built by the
+    library's own kernels).  Frames carry the dictionary id, regenerate through the reference decoder and the oracle with
+    the dictionary, reuse its entropy tables (repeat modes / treeless literals) and land within 3 % of the reference's
+    size with the same dictionary; a long input whose first match reaches back into the dictionary works too."""
+    from oracle import Oracle
+    orc = Oracle()
+    recs = corpus.json_records(470)
+    dct = ref.train_dictionary(16384, recs[:400])
+    sample = recs[400:] + [recs[5] * 40]
+    frames = compress(sim, sample, checksum=True, n_ctas=3, dct=dct)
+    ours = theirs = plain = 0
+    for r, f in zip(sample, frames):
+        assert ref.decompress(f, len(r), dct) == r and orc.decompress(f, len(r), dct) == r
+        assert f[4] & 3 != 0                                       # dictionary id present
+        ours += len(f); theirs += len(ref.compress(r, level=3, dict_data=dct, checksum=True))
+    plain = sum(map(len, compress(sim, sample, checksum=True, n_ctas=3)))
+    assert ours < plain * 0.8 and ours <= theirs * 1.03, (ours, theirs, plain)

@@ -162,7 +162,7 @@ def test_dictionary_compression(ref, oracle):
     """Config 4: records compressed against a trained dictionary.  The frames carry the dictionary id,
     decode bit-exact through the reference decoder (with the dictionary) and are far smaller than without
     it; the size margin against the reference's dictionary compression is stated (the dictionary serves as match
-    history, start repcodes and entropy tables; measured +0.3 % on the config-4 workload, asserted <= 1.35x)."""
+    history, start repcodes and entropy tables; measured +0.3 % on the config-4 workload, asserted <= 1.10x)."""
     import os
     from tests import helpers
     dct = open(os.path.join(helpers.GOLDEN, "dict.bin"), "rb").read()
@@ -181,7 +181,7 @@ def test_dictionary_compression(ref, oracle):
         plain += len(nodict[i])
         refsz += len(ref.compress(r, level=3, dict_data=dct))
     assert ours < plain * 0.75                     # the dictionary must pay off
-    assert ours <= refsz * 1.35, (ours, refsz)     # stated margin vs the reference with the same dictionary
+    assert ours <= refsz * 1.10, (ours, refsz)     # stated margin vs the reference with the same dictionary (measured +0.3 %)
     out = zstd.ZstdDecompressor(dict_data=d).multi_decompress_to_buffer(res)
     assert [out[i].tobytes() for i in range(len(recs))] == recs
     # dict id is recorded unless disabled
