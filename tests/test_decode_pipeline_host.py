@@ -110,3 +110,14 @@ def test_kernel_to_kernel_round_trip():
     frames = compress(csim, segs, checksum=True, n_ctas=3)
     outs, st = decompress(dsim, frames, [len(s) for s in segs], n_ctas=2)
     assert st == [0] * len(segs) and outs == segs
+
+
+def test_pool_overflow_takes_several_passes(sim, ref):
+    """40 frames of 24 KB with 32 frames per warp: their Huffman and FSE tables do not fit one warp's shared-memory pool
+    together, so lanes wait for later passes -- same bytes, whatever the pass a lane ran in."""
+    text = corpus.text_corpus(1 << 20)
+    segs = [bytes(text[i * 20011:i * 20011 + 24000 + 13 * i]) for i in range(40)]
+    frames = [ref.compress(s, level=3 + (i % 3), checksum=True) for i, s in enumerate(segs)]
+    for warps in (8, 7):
+        outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=1, warps=warps, take=32)
+        assert st == [0] * len(segs) and outs == segs
