@@ -34,7 +34,8 @@ void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_
 size_t zb_encode_scratch_bytes();
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
                                void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
-                               const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, int dual, cudaStream_t st);
+                               const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, int dual, int small_blocks, cudaStream_t st);
+u32 zb_encode_small_max();
 void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st);
 u32 zb_encode_ctable_bytes();
 void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st);
@@ -562,7 +563,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
       zb_launch_compress_blocks(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
                                 dict ? dict->c_tail : nullptr, dict ? dict->c_D : 0, dict ? dict->d_ctable : nullptr,
                                 (dict && dict->c_D && dict->dev.has_entropy) ? (const void*)dict->d_digest : nullptr, dict ? dict->d_cct : nullptr,
-                                overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, P.level >= 4 ? 1 : 0, ctx->stream); }
+                                overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, P.level >= 4 ? 1 : 0, max_block <= zb_encode_small_max() ? 1 : 0, ctx->stream); }
     if (overlap_upload) {
         // <= 48 chunks of >= 4 MiB; after each chunk the copy engine also writes the new byte count next to the work counter
         u64 chunk = (up_bytes + 47) / 48; if (chunk < ((u64)4 << 20)) chunk = (u64)4 << 20; chunk = (chunk + 255) & ~(u64)255;

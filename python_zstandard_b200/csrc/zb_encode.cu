@@ -31,7 +31,13 @@
 
 #define ZE_THREADS   128
 #define ZE_HLOG      14
-#define ZE_UNIT      1024
+#define ZE_UNIT      1024                // bytes per parse lane ...
+// ... except in batches of small blocks: a 1 KiB record would be parsed by ONE lane (585 K of 745 K cycles per record on the
+// config-4 workload).  When no block of a call exceeds ZE_SMALL_MAX bytes the launcher takes the UNIT = 256 instantiation,
+// which puts four lanes on such a record; matches end at unit borders, which costs size (CPU build of the kernel, against
+// the reference: dictionary records -0.8 % -> +0.5 %, 1-2 KiB text +0.4 % -> +1.0 %; 128-byte units: +2.2 % / +1.8 %).
+#define ZE_UNIT_SMALL 256
+#define ZE_SMALL_MAX  2048
 #define ZE_UNIT_SEQ  257                 // max sequences of a unit (+1)
 #define ZE_MAXSEQ    32768
 #define ZE_BLOCK     (128u << 10)
@@ -509,7 +515,7 @@ __device__ __forceinline__ u32 ze_off_code(u32 off, u32 ll, u32& r0, u32& r1, u3
 // bytes plus 2^13 heads keyed on 8 bytes; a position takes its 8-byte candidate when that one verifies 8 bytes.  CPU
 // model tools/enc_model3.c: 128 KiB text +3.2 % -> -1.6 % against level 3.  Used for level >= 4; the default
 // instantiation compiles to the code it had before.
-template <bool DUAL>
+template <bool DUAL, u32 UNIT>
 __global__ void __launch_bounds__(ZE_THREADS)
 zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs, u32 n_jobs,
                    ZeScratch* __restrict__ scratch, u8* __restrict__ slots, u64 slot_bytes,
@@ -550,6 +556,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         const u8* const dict_end = dict.tail + dict.D;
         bool const skip0 = job.first && D == 0;                    // without a dictionary the reference never uses position 0 as a match source
         u32 const n = job.size;
+        constexpr u32 unit = UNIT;                                 // bytes each parse lane owns
         u8* const out = slots + (u64)j * slot_bytes;       // block header (3 bytes) + payload
         __syncthreads();
 
@@ -735,10 +742,10 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         // entry) and then decides, so a step costs one memory round trip for the whole warp instead of
         // one per divergent path.  Long matches continue in EXTEND iterations, 8 bytes per step.
         {
-            u32 const u0 = tid * ZE_UNIT;
+            u32 const u0 = tid * unit;
             u32 cnt = 0, tail = 0;
             bool alive = u0 < n;
-            u32 const end = alive ? min(u0 + ZE_UNIT, n) : 0;
+            u32 const end = alive ? min(u0 + unit, n) : 0;
             u32 const ilimit = n >= 8 ? n - 8 : 0;
             u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
             if (alive && ip == 0 && skip0) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
@@ -893,7 +900,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         ZE_MARK(2);
         // ---------------- D: compaction of the units' sequences + literal gather
         if (tid == 0) {
-            u32 off = 0, carry = 0; u32 const units = (n + ZE_UNIT - 1) / ZE_UNIT;
+            u32 off = 0, carry = 0; u32 const units = (n + unit - 1) / unit;
             for (u32 u = 0; u < 128; u++) {
                 S.uoff[u] = off; S.ucarry[u] = carry;
                 if (u < units) { if (S.ucnt[u]) carry = S.utail[u]; else carry += S.utail[u]; off += S.ucnt[u]; }
@@ -1349,19 +1356,17 @@ void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st) { 
 
 void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes,
                                void* outs, u32* work_counter, const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
-                               const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, int dual, cudaStream_t st)
+                               const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, int dual, int small_blocks, cudaStream_t st)
 {
     ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table; dict.ent = (const ZbDictDigest*)dict_digest; dict.cct = dict_digest ? dict_cct : nullptr;
     ZeUpload up; up.progress = upload_progress; up.total = upload_total; up.status = upload_status;
-    if (dual) {
-        cudaFuncSetAttribute(zb_compress_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));
-        zb_compress_blocks<true><<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
-                                                                               (ZeBlockOut*)outs, work_counter, dict, up);
-    } else {
-        cudaFuncSetAttribute(zb_compress_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));      // per device: cheap, so set on every launch
-        zb_compress_blocks<false><<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes,
-                                                                                (ZeBlockOut*)outs, work_counter, dict, up);
-    }
+    #define ZE_LAUNCH(D_, U_) do { \
+        cudaFuncSetAttribute(zb_compress_blocks<D_, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeShared));   /* per device: cheap, so set on every launch */ \
+        zb_compress_blocks<D_, U_><<<n_ctas, ZE_THREADS, sizeof(ZeShared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (ZeScratch*)scratch, slots, slot_bytes, \
+                                                                                 (ZeBlockOut*)outs, work_counter, dict, up); } while (0)
+    if (dual) { if (small_blocks) ZE_LAUNCH(true, ZE_UNIT_SMALL); else ZE_LAUNCH(true, ZE_UNIT); }
+    else      { if (small_blocks) ZE_LAUNCH(false, ZE_UNIT_SMALL); else ZE_LAUNCH(false, ZE_UNIT); }
+    #undef ZE_LAUNCH
 }
 
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
@@ -1381,6 +1386,7 @@ void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* se
 }
 
 u32 zb_encode_smem_bytes() { return (u32)sizeof(ZeShared); }
+u32 zb_encode_small_max() { return ZE_SMALL_MAX; }
 u32 zb_encode_ctable_bytes() { return (u32)sizeof(ZeCTable); }
 void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st) { zb_dict_ctables<<<1, 96, 0, st>>>((const ZbDictDigest*)digest, (ZeCTable*)out3); }
 

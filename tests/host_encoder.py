@@ -195,8 +195,11 @@ extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u
     }
     ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
     ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3;
-    if (nj && dual) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
-    else if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    bool const small_blocks = max_block <= ZE_SMALL_MAX;             // as zb_api.cu picks the instantiation
+    if (nj && dual && small_blocks) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true, ZE_UNIT_SMALL>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    else if (nj && small_blocks) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false, ZE_UNIT_SMALL>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    else if (nj && dual) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true, ZE_UNIT>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    else if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false, ZE_UNIT>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     std::vector<u64> sizes(n_segs); std::vector<ZbSegment> out_segs(n_segs); u64 total = 0;
     simt::launch((n_segs + 255) / 256, 256, [&] { zb_frame_sizes(segs.data(), info.data(), outs.data(), n_segs, P, sizes.data()); });
     simt::launch(1, 1024, [&] { zb_scan_sizes(sizes.data(), n_segs, out_segs.data(), &total); });
