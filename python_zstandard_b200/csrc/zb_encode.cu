@@ -37,7 +37,9 @@
 // which puts four lanes on such a record; matches end at unit borders, which costs size (CPU build of the kernel, against
 // the reference: dictionary records -0.8 % -> +0.5 %, 1-2 KiB text +0.4 % -> +1.0 %; 128-byte units: +2.2 % / +1.8 %).
 #define ZE_UNIT_SMALL 256
+#ifndef ZE_SMALL_MAX
 #define ZE_SMALL_MAX  2048
+#endif
 #define ZE_UNIT_SEQ  257                 // max sequences of a unit (+1)
 #define ZE_MAXSEQ    32768
 #define ZE_BLOCK     (128u << 10)

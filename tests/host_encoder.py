@@ -156,6 +156,7 @@ def build_header_parser():
 
 SIM_LIB = os.path.join(BUILD, "libzs_host.so")
 SIM_WRAPPERS = r"""
+extern "C" unsigned long long t_any_calls(int reset) { unsigned long long v = simt_any_calls; if (reset) simt_any_calls = 0; return v; }
 // The whole compression path of the library on the CPU: block jobs as zb_api.cu makes them, zb_compress_blocks on
 // `n_ctas` CTAs of 128 threads, then the frame layout kernels.  No dictionary, input resident.  Returns total bytes.
 extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u64* seg_len, u32 n_segs, u32 checksum, u32 content_size,

@@ -158,7 +158,8 @@ static inline unsigned __ballot_sync(unsigned mask, int p)
     return (unsigned)simt::collective(mask, p ? 1 : 0, [](const unsigned long long* a, unsigned need, unsigned) {
         unsigned r = 0; for (unsigned l = 0; l < 32; l++) if (((need >> l) & 1) && a[l]) r |= 1u << l; return (unsigned long long)r; });
 }
-static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
+static unsigned long long simt_any_calls = 0;      // __any_sync calls by thread 0: the iteration count of vote-driven loops
+static inline int __any_sync(unsigned mask, int p) { if (simt::tid() == 0) simt_any_calls++; return __ballot_sync(mask, p) != 0; }
 static inline int __all_sync(unsigned mask, int p)
 {
     return (int)simt::collective(mask, p ? 1 : 0, [](const unsigned long long* a, unsigned need, unsigned) {
