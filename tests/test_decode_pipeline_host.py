@@ -30,7 +30,7 @@ def ref():
     return RefZstd()
 
 
-def decompress(sim, frames, sizes, dct=b"", n_ctas=1, warps=8, take=32):
+def decompress(sim, frames, sizes, dct=b"", n_ctas=1, warps=8, take=32, exact_sizes=False):
     """(outputs, statuses) of a batch of frames through the kernels."""
     blob = bytes(PAD) + b"".join(frames) + bytes(PAD)
     off = (np.cumsum([0] + [len(f) for f in frames[:-1]]) + PAD).astype(np.uint64)
@@ -41,8 +41,10 @@ def decompress(sim, frames, sizes, dct=b"", n_ctas=1, warps=8, take=32):
     out = (C.c_ubyte * cap)()
     n = len(frames)
     oo = (C.c_uint64 * n)(); ol = (C.c_uint64 * n)(); st = (C.c_uint32 * n)()
+    want = (C.c_uint64 * n)(*sizes)                                # decompressed_sizes of the batch call, when given
     tot = sim.t_decompress_batch(C.addressof(src), off.ctypes.data, ln.ctypes.data, n, (C.addressof(dbuf) + PAD) if dct else None, len(dct),
-                                 n_ctas, warps, take, C.addressof(out), cap, C.addressof(oo), C.addressof(ol), C.addressof(st))
+                                 n_ctas, warps, take, C.addressof(out), cap, C.addressof(oo), C.addressof(ol), C.addressof(st),
+                                 C.addressof(want) if exact_sizes else None)
     assert tot >= 0
     return [bytes(out[oo[i]:oo[i] + ol[i]]) for i in range(n)], list(st)
 
@@ -121,3 +123,39 @@ def test_pool_overflow_takes_several_passes(sim, ref):
     for warps in (8, 7):
         outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=1, warps=warps, take=32)
         assert st == [0] * len(segs) and outs == segs
+
+
+def test_batches_with_random_damage_follow_the_reference(sim, ref):
+    """A slice of tools/batch_fuzz_decode.py: batches of 64 small frames, a random third corrupted / truncated; healthy
+    frames regenerate exactly whatever their warp neighbours do, damaged ones follow the reference."""
+    rng = np.random.default_rng(61)
+    text = corpus.text_corpus(1 << 20)
+    healthy = rejected = 0
+    for b in range(4):
+        sizes = rng.integers(200, 6000, 64)
+        segs = [bytes(text[o:o + int(s)]) for o, s in zip(rng.integers(0, len(text) - 6000, 64), sizes)]
+        frames = [ref.compress(s, level=int(rng.integers(1, 6)), checksum=bool(rng.integers(0, 2))) for s in segs]
+        bad = set(rng.choice(64, 20, replace=False).tolist())
+        for i in bad:
+            f = bytearray(frames[i])
+            if i % 2:
+                f[int(rng.integers(4, len(f)))] ^= 1 << int(rng.integers(0, 8))
+            else:
+                f = f[:int(rng.integers(5, len(f)))]
+            frames[i] = bytes(f)
+        outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=1 + b % 2, warps=8 - b % 2, take=(32, 16, 8, 32)[b], exact_sizes=True)
+        for i, s in enumerate(segs):
+            if i not in bad:
+                assert st[i] == 0 and outs[i] == s, (b, i)
+                healthy += 1
+                continue
+            try:
+                want = ref.decompress(frames[i], len(s))
+            except Exception:
+                want = None
+            if want is None:
+                assert st[i] != 0, (b, i)
+                rejected += 1
+            elif st[i] == 0:
+                assert outs[i] == want, (b, i)
+    assert healthy == 4 * 44 and rejected > 40

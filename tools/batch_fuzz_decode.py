@@ -1,0 +1,46 @@
+"""Batch fuzz of ALL decompression kernels on the CPU build (tests/simt.h): batches of 64 small frames in which a random
+third is corrupted, truncated or has a wrong checksum.  Healthy frames must regenerate exactly whatever their neighbours
+in the warp do; damaged ones must follow the reference (never accepted when it rejects; same bytes when both accept).
+   N=200 SEED=1 python tools/batch_fuzz_decode.py        (round 1: 300 batches / 19200 frames clean)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import corpus
+from oracle import RefZstd
+from tests import host_encoder
+from tests.test_decode_pipeline_host import decompress
+
+sim = host_encoder.build_decode_sim()
+ref = RefZstd()
+rng = np.random.default_rng(int(os.environ.get("SEED", "1")))
+text = corpus.text_corpus(1 << 20)
+N = int(os.environ.get("N", "100"))
+healthy = damaged_rej = damaged_same = stricter = 0
+for b in range(N):
+    sizes = rng.integers(200, 6000, 64)
+    segs = [bytes(text[o:o + int(s)]) for o, s in zip(rng.integers(0, len(text) - 6000, 64), sizes)]
+    frames = [ref.compress(s, level=int(rng.integers(1, 6)), checksum=bool(rng.integers(0, 2))) for s in segs]
+    bad = set(rng.choice(64, int(rng.integers(5, 25)), replace=False).tolist())
+    for i in bad:
+        f = bytearray(frames[i]); kind = int(rng.integers(0, 3))
+        if kind == 0: k = int(rng.integers(4, len(f))); f[k] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1: f = f[:int(rng.integers(5, len(f)))]
+        else: k = int(rng.integers(4, len(f))); f[k] = int(rng.integers(0, 256))
+        frames[i] = bytes(f)
+    warps, take = [(8, 32), (7, 16), (8, 8), (8, 32)][b % 4]
+    outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=1 + b % 2, warps=warps, take=take, exact_sizes=True)
+    for i, s in enumerate(segs):
+        if i not in bad:
+            assert st[i] == 0 and outs[i] == s, (b, i, st[i]); healthy += 1
+            continue
+        try:
+            want = ref.decompress(frames[i], len(s))
+        except RefZstd.Error:
+            want = None
+        if want is None:
+            assert st[i] != 0, (b, i, "accepted what the reference rejects"); damaged_rej += 1
+        elif st[i] == 0:
+            assert outs[i] == want, (b, i); damaged_same += 1
+        else:
+            stricter += 1
+print("batches", N, "healthy ok", healthy, "| damaged: both reject", damaged_rej, "both accept equal", damaged_same, "kernels stricter", stricter)
