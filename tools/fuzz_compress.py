@@ -1,7 +1,7 @@
 """Property fuzz of the compression kernels on the CPU build (tests/simt.h): random inputs of many shapes through the
 default, two-table and dictionary paths; every frame must regenerate its input through the unmodified reference
 decoder and must not exceed the input by more than the format's overhead.
-   N=200 SEED=1 python tools/fuzz_compress.py        (round 1: 3 x 600 inputs clean)"""
+   N=200 SEED=1 python tools/fuzz_compress.py        (round 1: 3 x 500 inputs, 14.5 MB, clean)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
