@@ -52,3 +52,22 @@ def test_no_cpu_fallback_without_device():
     from tests import helpers
     with pytest.raises(_native.NativeError, match="no CPU fallback"):
         zstd.ZstdDecompressor().decompress(helpers.KAT_FOO)
+
+
+def test_compress_bound_equals_the_reference():
+    """zb200_compress_bound == ZSTD_compressBound (zstd/zstd.c:4547) -- a host-only call of the C ABI."""
+    entry.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "python_zstandard_b200", "libzb200.so"))
+    lib.zb200_compress_bound.restype = ctypes.c_uint64
+    lib.zb200_compress_bound.argtypes = [ctypes.c_uint64]
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libzstd_ref.so")
+    expect = None
+    if os.path.exists(ref_path):
+        ref = ctypes.CDLL(ref_path)
+        ref.ZSTD_compressBound.restype = ctypes.c_size_t
+        ref.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+        expect = ref.ZSTD_compressBound
+    for n in (0, 1, 255, 1024, 4096, 131071, 131072, 131073, 1 << 20, (1 << 32) + 5):
+        want = expect(n) if expect else n + (n >> 8) + (((128 << 10) - n) >> 11 if n < (128 << 10) else 0)
+        assert lib.zb200_compress_bound(n) == want, n
+    assert lib.zb200_compress_bound(131072) == 131584 and lib.zb200_compress_bound(4096) == 4174     # SURVEY section 8 a21
