@@ -1,7 +1,7 @@
 """AddressSanitizer fuzz of the decode kernels' source on the CPU (tests/host_encoder.build_entropy_kernel, one emulated
 lane): mutated and truncated golden frames in exact-size heap blocks with PAD bytes of slack on both sides.
   ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) N=1500 SEED=7 python tools/asan_fuzz_decode.py
-Round 1: 24000 frames with PAD=4 clean; PAD=0 shows the by-design read of the aligned 32-bit word that holds a stream's
+Round 1: 24000 + 40000 frames with PAD=4 clean; PAD=0 shows the by-design read of the aligned 32-bit word that holds a stream's
 last byte (<= 3 bytes past the segment, inside its allocation granule on the device)."""
 import sys, os, ctypes as C, numpy as np, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
