@@ -554,8 +554,14 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         ZeBlockJob const job = jobs[j];
         long long t_phase = clock64();
         const u8* const in = src + job.src_pos;
-        u32 const D = job.first ? dict.D : 0;                       // dictionary bytes that precede this block as history
-        const u8* const dict_end = dict.tail + dict.D;
+        // bytes of history in front of the block: the dictionary tail for the first block of a frame; in the two-table mode the
+        // last ZE_HIST bytes of the previous block for the others (it is a full 128 KiB block of the same frame, so it sits
+        // right in front of `in`); otherwise blocks are compressed independently
+        constexpr u32 ZE_HIST = 32768;
+        bool const hist = DUAL && !job.first;
+        u32 const D = job.first ? dict.D : (hist ? ZE_HIST : 0u);
+        const u8* const dict_end = hist ? in : dict.tail + dict.D;
+        bool const dict_first = DUAL ? job.first != 0 : true;       // dictionary entropy tables / repcodes belong to first blocks only
         bool const skip0 = job.first && D == 0;                    // without a dictionary the reference never uses position 0 as a match source
         u32 const n = job.size;
         constexpr u32 unit = UNIT;                                 // bytes each parse lane owns
@@ -586,7 +592,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
 
         ZE_MARK(0);
         // ---------------- A: hash links (warp 0); the other warps clear the histograms meanwhile
-        if (D) { const u32* t32 = (const u32*)dict.table; for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = t32[i]; }
+        if (D && !hist) { const u32* t32 = (const u32*)dict.table; for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = t32[i]; }
         else for (u32 i = tid; i < (1u << ZE_HLOG) / 2; i += ZE_THREADS) ((u32*)S.head)[i] = 0xFFFFFFFFu;
         for (u32 i = tid; i < 256; i += ZE_THREADS) S.hist[i] = 0;
         if (tid < 36) S.hLL[tid] = 0; if (tid < 32) S.hOF[tid] = 0; if (tid < 56) S.hML[tid] = 0;
@@ -597,15 +603,17 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             bool const exact = n < 2048;
             // The block is streamed through a 2 x 512-byte shared-memory ring, filled with coalesced 128-bit
             // loads that are issued a whole chunk (16 steps) before their data is needed.
-            const u8* const in_al = (const u8*)((uintptr_t)in & ~(uintptr_t)15);
-            u32 const skew = (u32)(in - in_al);
-            u32 const span = skew + n;                                   // bytes of the aligned stream that belong to the block
+            u32 const Hh = hist ? ZE_HIST : 0u;                          // the link phase walks the history in front of the block too
+            const u8* const in0 = in - Hh;
+            const u8* const in_al = (const u8*)((uintptr_t)in0 & ~(uintptr_t)15);
+            u32 const skew = (u32)(in0 - in_al);
+            u32 const span = skew + Hh + n;                              // bytes of the aligned stream that belong to history + block
             auto chunk_ld = [&](u32 c) { u32 const o = c * 512 + lane * 16; return o < span ? *(const uint4*)(in_al + o) : make_uint4(0, 0, 0, 0); };   // aligned 16-byte loads never leave the allocation
             uint4* const ring = (uint4*)S.ring;
             ring[lane] = chunk_ld(0);
             uint4 pend = chunk_ld(1);
             u32 const nchunks = (span + 511) / 512;
-            bool const use_dual = DUAL && D == 0;                        // the dictionary's precomputed table is a single 2^14 table
+            bool const use_dual = DUAL && (D == 0 || hist);              // (the dictionary's precomputed table is a single 2^14 table)
             if constexpr (DUAL) { if (use_dual) {
                 // two tables of 2^13 heads: short (4-byte hash) in the lower half, long (8-byte hash) in the upper half.
                 // Same branch-free stepping as below, one step at a time.
@@ -617,12 +625,12 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
                     #pragma unroll 2
                     for (u32 k = 0; k < 16; k++) {
                         u32 const q = c * 512 + k * 32 + lane;
-                        int const pp = (int)q - (int)skew;
+                        int const pp = (int)q - (int)skew - (int)Hh;              // block-relative; negative = history
                         u32 const bo = q & 1023;
                         u32 const w0 = S.ring[bo >> 2], w1 = S.ring[((bo >> 2) + 1) & 255], w2 = S.ring[((bo >> 2) + 2) & 255];
                         u32 const v0 = __funnelshift_r(w0, w1, (bo & 3) * 8), v1 = __funnelshift_r(w1, w2, (bo & 3) * 8);
-                        bool const vaS = pp >= 0 && (u32)pp + 4 <= n, vaL = pp >= 0 && (u32)pp + 8 <= n;
-                        u32 const pv = (u32)pp;
+                        bool const vaS = pp >= -(int)Hh && pp + 4 <= (int)n, vaL = pp >= -(int)Hh && pp + 8 <= (int)n;
+                        u32 const pv = (u32)(pp + (int)Hh);                       // position in (history + block) space
                         bool const ins = (pv & 0xFFFFu) != 0xFFFFu && !(skip0 && pp == 0);
                         u32 const hS = vaS ? (v0 * 2654435761u) >> (32 - (ZE_HLOG - 1)) : 0;
                         u32 const hL = vaL ? (u32)((((u64)v1 << 32 | v0) * 0xCF1BBCDCB7A56463ull) >> (64 - (ZE_HLOG - 1))) : 0;
@@ -720,14 +728,14 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             }
         }
         __syncthreads();
-        if constexpr (DUAL) { if (D == 0) {
+        if constexpr (DUAL) { if (D == 0 || hist) {
             // every position takes its 8-byte-hash candidate when that one really matches 8 bytes (all threads, independent
             // per position); the parse below then sees one candidate per position, as before
             const u32* const Wd = (const u32*)((uintptr_t)in & ~(uintptr_t)3);
             const u32* const Wend = Wd + ((((u32)((uintptr_t)in & 3)) + n + 3) >> 2);
             for (u32 p = tid; p + 8 <= n; p += ZE_THREADS) {
                 u32 const dL = G.distL[p];
-                if (dL == 0 || dL > p) continue;
+                if (dL == 0 || dL > p + D) continue;
                 const u8* const qa = in + p; const u8* const qb = qa - dL;
                 const u32* const wa = (const u32*)((uintptr_t)qa & ~(uintptr_t)3); const u32* const wb = (const u32*)((uintptr_t)qb & ~(uintptr_t)3);
                 u32 const sa = (u32)((uintptr_t)qa & 3) * 8, sb = (u32)((uintptr_t)qb & 3) * 8;
@@ -751,7 +759,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
             u32 const ilimit = n >= 8 ? n - 8 : 0;
             u32 ip = u0, anchor = u0, r0 = 0, r1 = 0, r2 = 0;
             if (alive && ip == 0 && skip0) ip = 1;                 // the reference starts its search at position 1 (zstd/zstd.c:31075)
-            if (tid == 0 && D && dict.ent) { r0 = dict.ent->rep[0]; r1 = dict.ent->rep[1]; r2 = dict.ent->rep[2]; }   // a frame with a dictionary starts from its repcodes (ZSTD_loadCEntropy)
+            if (tid == 0 && dict_first && D && dict.ent) { r0 = dict.ent->rep[0]; r1 = dict.ent->rep[1]; r2 = dict.ent->rep[2]; }   // a frame with a dictionary starts from its repcodes (ZSTD_loadCEntropy)
             uint2* const rec = G.useq + tid * ZE_UNIT_SEQ;
             u32 mode = 0, m_start = 0, m_off = 0, m_len = 0;
             u32 d0 = 0, d1 = 0;
@@ -952,7 +960,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         ZE_MARK(3);
         // ---------------- E: entropy tables.  thread 0: LL, 32: OF, 64: ML (own scratch each), 96: literals mode + Huffman code
         if (nseq) {
-            const ZbDictDigest* const de = (D && dict.ent) ? dict.ent : nullptr;      // first block of a frame that has a full dictionary
+            const ZbDictDigest* const de = (dict_first && D && dict.ent) ? dict.ent : nullptr;      // first block of a frame that has a full dictionary
             if (tid == 0)  ze_make_table(S.ct[0], S.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.tmp_sym[0], de ? de->c_norm_ll : nullptr, de ? de->c_max_ll : 0, de ? de->ll_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 0 : nullptr);
             if (tid == 32) ze_make_table(S.ct[1], S.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.tmp_sym[1], de ? de->c_norm_of : nullptr, de ? de->c_max_of : 0, de ? de->of_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 1 : nullptr);
             if (tid == 64) ze_make_table(S.ct[2], S.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.tmp_sym[2], de ? de->c_norm_ml : nullptr, de ? de->c_max_ml : 0, de ? de->ml_log : 0, de && dict.cct ? (const ZeCTable*)dict.cct + 2 : nullptr);
@@ -960,7 +968,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
         if (tid == 96) {
             S.lit_mode = 0; S.huf_tbl_bytes = 0; S.lit_treeless = 0;
             u32 most = 0; for (u32 s = 0; s < 256; s++) if (S.hist[s] > most) most = S.hist[s];
-            const ZbDictDigest* const de = (D && dict.ent) ? dict.ent : nullptr;
+            const ZbDictDigest* const de = (dict_first && D && dict.ent) ? dict.ent : nullptr;
             if (nlit >= 8 && most == nlit) S.lit_mode = 1;                // RLE literals
             else {
                 u32 cost_new = 0xFFFFFFFFu;                              // bytes with a table of this block's own
