@@ -8,6 +8,8 @@ LIB = os.path.join(HERE, "libzb200.so")
 SOURCES = ["zb_decode.cu", "zb_encode.cu", "zb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math"]
+if os.environ.get("ZB200_PHASE_TIMERS"):          # tuning builds only: per-phase clock64 counters inside the kernels
+    NVCC_FLAGS.append("-DZB_PHASE_TIMERS")
 
 
 def _stale():
@@ -22,12 +24,15 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
-    for src in SOURCES:
+    objs, procs = [], []
+    for src in SOURCES:                                  # the three translation units compile side by side
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 

@@ -801,8 +801,12 @@ void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32
 
 void zb_entropy_phase_read(unsigned long long* out8, int reset)
 {
+#ifdef ZB_PHASE_TIMERS
     cudaMemcpyFromSymbol(out8, g_zb_ent_phase, sizeof(unsigned long long) * 8);
     if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_zb_ent_phase, z, sizeof z); }
+#else
+    for (int i = 0; i < 8; i++) out8[i] = 0; (void)reset;
+#endif
 }
 
 void zb_launch_digest_dict(const u8* dict, u32 n, ZbDictDigest* out, cudaStream_t st)

@@ -374,19 +374,13 @@ __device__ static void ze_huf_assign(ZeHuf& H, u32 max_sym, u32 maxnb)
     H.max_sym = max_sym; H.log = maxnb;
 }
 
-__device__ static bool ze_huf_build(ZeHuf& H, const u32* count, u32* wk /* >= 1600 u32 */)
+// tree construction from symbols already sorted by (count, symbol) ascending in wk[0..n): two-queue merge, depths,
+// depth limit, canonical codes.  One thread.
+__device__ static bool ze_huf_from_sorted(ZeHuf& H, const u32* count, u32* wk /* >= 1600 u32 */, u32 n, u32 max_sym)
 {
     u32* const sym = wk;                 // [256] symbols sorted by count ascending
     u32* const w = wk + 256;             // [512] node weights
     u16* const parent = (u16*)(wk + 768);// [512]
-    u32 n = 0, max_sym = 0;
-    for (u32 s = 0; s < 256; s++) if (count[s]) { sym[n++] = s; max_sym = s; }
-    if (n < 2) return false;
-    for (u32 i = 1; i < n; i++) {        // insertion sort by (count, symbol)
-        u32 const s = sym[i]; u32 const c = count[s]; int j = (int)i - 1;
-        while (j >= 0 && (count[sym[j]] > c)) { sym[j + 1] = sym[j]; j--; }
-        sym[j + 1] = s;
-    }
     for (u32 i = 0; i < n; i++) w[i] = count[sym[i]];
     u32 lo = 0, q = n, qe = n;           // leaves [lo, n), internal nodes [q, qe)
     while ((n - lo) + (qe - q) > 1) {
@@ -420,6 +414,20 @@ __device__ static bool ze_huf_build(ZeHuf& H, const u32* count, u32* wk /* >= 16
     for (u32 i = 0; i < n; i++) H.nb[sym[i]] = depth[i];
     ze_huf_assign(H, max_sym, maxnb);
     return true;
+}
+
+__device__ static bool ze_huf_build(ZeHuf& H, const u32* count, u32* wk /* >= 1600 u32 */)
+{
+    u32* const sym = wk;
+    u32 n = 0, max_sym = 0;
+    for (u32 s = 0; s < 256; s++) if (count[s]) { sym[n++] = s; max_sym = s; }
+    if (n < 2) return false;
+    for (u32 i = 1; i < n; i++) {        // insertion sort by (count, symbol)
+        u32 const s = sym[i]; u32 const c = count[s]; int j = (int)i - 1;
+        while (j >= 0 && (count[sym[j]] > c)) { sym[j + 1] = sym[j]; j--; }
+        sym[j + 1] = s;
+    }
+    return ze_huf_from_sorted(H, count, wk, n, max_sym);
 }
 
 // Huffman tree description: weights, FSE-compressed when that is smaller, else 4-bit (HUF_writeCTable_wksp :17005).
@@ -467,8 +475,13 @@ __device__ static u32 ze_huf_write_table(u8* out, const ZeHuf& H, ZeCTable& ct, 
 // ---------------------------------------------------------------------------
 // the block kernel
 // ---------------------------------------------------------------------------
-__device__ unsigned long long g_ze_phase[16];     // summed clock cycles per phase (thread 0 of every CTA), for tuning
+// per-phase cycle counters (thread 0 of every CTA) exist only in tuning builds (-DZB_PHASE_TIMERS)
+#ifdef ZB_PHASE_TIMERS
+__device__ unsigned long long g_ze_phase[16];
 #define ZE_MARK(k) do { if (tid == 0) { long long const t_ = clock64(); atomicAdd(&g_ze_phase[k], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
+#else
+#define ZE_MARK(k) do { (void)t_phase; } while (0)
+#endif
 struct ZeShared {
     // The hash heads live only in phase A; the entropy-stage tables and staging are first touched in phase D/E, so
     // the two share storage (36 KB per CTA instead of 51 KB: 6 CTAs per SM instead of 4 -- the kernel is bound by
@@ -1190,6 +1203,8 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
     }
 }
 
+#include "zb_encode2.cuh"
+
 // ===========================================================================
 // dictionary hash table: the block compressor's table state after "having seen" the dictionary tail
 // (restates what ZSTD_loadDictionaryContent leaves in the match-state tables, zstd/zstd.c:27900-27990)
@@ -1396,14 +1411,38 @@ void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* se
 }
 
 u32 zb_encode_smem_bytes() { return (u32)sizeof(ZeShared); }
+
+// round-2 kernel: one CTA per SM, block resident in shared memory (no dictionary, blocks compressed independently)
+size_t zb_encode2_scratch_bytes() { return sizeof(Z2Scratch); }
+u32 zb_encode2_smem_bytes() { return (u32)sizeof(Z2Shared); }
+void zb_launch_compress_smem(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes, void* outs, u32* work_counter,
+                             const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st)
+{
+    ZeUpload up; up.progress = upload_progress; up.total = upload_total; up.status = upload_status;
+    cudaFuncSetAttribute(zb_compress_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Z2Shared));
+    zb_compress_smem<<<n_ctas, Z2_NT, sizeof(Z2Shared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (Z2Scratch*)scratch, slots, slot_bytes, (ZeBlockOut*)outs, work_counter, up);
+}
 u32 zb_encode_small_max() { return ZE_SMALL_MAX; }
 u32 zb_encode_ctable_bytes() { return (u32)sizeof(ZeCTable); }
 void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st) { zb_dict_ctables<<<1, 96, 0, st>>>((const ZbDictDigest*)digest, (ZeCTable*)out3); }
 
 void zb_encode_phase_read(unsigned long long* out16, int reset)
 {
+#ifdef ZB_PHASE_TIMERS
     cudaMemcpyFromSymbol(out16, g_ze_phase, sizeof(unsigned long long) * 16);
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_ze_phase, z, sizeof z); }
+#else
+    for (int i = 0; i < 16; i++) out16[i] = 0; (void)reset;
+#endif
+}
+void zb_encode2_phase_read(unsigned long long* out16, int reset)
+{
+#ifdef ZB_PHASE_TIMERS
+    cudaMemcpyFromSymbol(out16, g_z2_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_z2_phase, z, sizeof z); }
+#else
+    for (int i = 0; i < 16; i++) out16[i] = 0; (void)reset;
+#endif
 }
 
 }  // extern "C"

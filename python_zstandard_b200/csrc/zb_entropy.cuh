@@ -235,8 +235,13 @@ __device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 m
     return used;
 }
 
-__device__ unsigned long long g_zb_ent_phase[8];      // summed cycles per phase (lane 0 of every warp), for tuning
+// per-phase cycle counters (lane 0 of every warp) exist only in tuning builds (-DZB_PHASE_TIMERS)
+#ifdef ZB_PHASE_TIMERS
+__device__ unsigned long long g_zb_ent_phase[8];
 #define ZB_EMARK(k) do { if (lane == 0) { long long const t_ = clock64(); atomicAdd(&g_zb_ent_phase[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
+#else
+#define ZB_EMARK(k) do { (void)t_ph; } while (0)
+#endif
 
 template <int ZB_ENT_WARPS>
 __global__ void __launch_bounds__(ZB_ENT_WARPS * 32)

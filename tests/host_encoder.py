@@ -210,6 +210,41 @@ extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u
     for (u32 i = 0; i < n_segs; i++) { out_off[i] = out_segs[i].offset; out_len[i] = out_segs[i].length; }
     return (long long)total;
 }
+
+// The round-2 kernel (zb_compress_smem: one CTA of 1024 threads per block, block resident in "shared memory") on the CPU.
+extern "C" long long t_compress_batch2(const u8* src, const u64* seg_off, const u64* seg_len, u32 n_segs, u32 checksum, u32 content_size,
+                                       u32 n_ctas, u8* out, u64 out_cap, u64* out_off, u64* out_len)
+{
+    std::vector<ZbSegment> segs(n_segs); std::vector<ZeBlockJob> jobs; std::vector<ZeSegInfo> info(n_segs);
+    u32 max_block = 0;
+    for (u32 i = 0; i < n_segs; i++) {
+        segs[i].offset = seg_off[i]; segs[i].length = seg_len[i];
+        info[i].first_job = jobs.size(); info[i].n_jobs = 0; info[i].pad = 0;
+        for (u64 pos = 0; pos < seg_len[i];) {
+            u32 const sz = (u32)(seg_len[i] - pos < ZE_BLOCK ? seg_len[i] - pos : ZE_BLOCK);
+            ZeBlockJob j; j.src_pos = seg_off[i] + pos; j.size = sz; j.seg = i; j.first = pos == 0; j.last = pos + sz == seg_len[i];
+            jobs.push_back(j); info[i].n_jobs++; pos += sz; if (sz > max_block) max_block = sz;
+        }
+    }
+    u32 const nj = (u32)jobs.size();
+    u64 const slot_bytes = ((u64)max_block + (max_block >> 7) + 64 + 15) & ~15ull;
+    u8* slots = (u8*)aligned_alloc(64, (size_t)(nj + 1) * slot_bytes + 64); std::vector<ZeBlockOut> outs(nj + 1);
+    if (n_ctas > nj) n_ctas = nj ? nj : 1;
+    Z2Scratch* scratch = (Z2Scratch*)aligned_alloc(64, ((sizeof(Z2Scratch) + 63) & ~(size_t)63) * n_ctas);
+    u32 counter = 0;
+    ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
+    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = 0; P.level = 3;
+    if (nj) simt::launch(n_ctas, Z2_NT, [&] { zb_compress_smem(src, jobs.data(), nj, scratch, slots, slot_bytes, outs.data(), &counter, up); });
+    std::vector<u64> sizes(n_segs); std::vector<ZbSegment> out_segs(n_segs); u64 total = 0;
+    simt::launch((n_segs + 255) / 256, 256, [&] { zb_frame_sizes(segs.data(), info.data(), outs.data(), n_segs, P, sizes.data()); });
+    simt::launch(1, 1024, [&] { zb_scan_sizes(sizes.data(), n_segs, out_segs.data(), &total); });
+    free(scratch);
+    if (total > out_cap) { free(slots); return -1; }
+    simt::launch((n_segs + 7) / 8, 256, [&] { zb_write_frames(src, segs.data(), info.data(), outs.data(), slots, slot_bytes, n_segs, P, out_segs.data(), out); });
+    free(slots);
+    for (u32 i = 0; i < n_segs; i++) { out_off[i] = out_segs[i].offset; out_len[i] = out_segs[i].length; }
+    return (long long)total;
+}
 """
 
 
@@ -224,7 +259,7 @@ def build_compress_sim():
     a = enc.index("\n", a) + 1
     b = enc.index('extern "C" {')
     b = enc.rindex("// ====", 0, enc.rindex("// ====", 0, b))
-    body = enc[a:b]
+    body = enc[a:b].replace('#include "zb_encode2.cuh"', open(os.path.join(csrc, "zb_encode2.cuh")).read().replace("#pragma once", ""))
     dec = open(os.path.join(csrc, "zb_decode.cu")).read()
     da = dec.index("\n", dec.index('#include "zb_common.cuh"')) + 1
     db = dec.index('extern "C" {')
@@ -243,6 +278,9 @@ def build_compress_sim():
     L.t_compress_batch.restype = C.c_longlong
     L.t_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.t_compress_batch2.restype = C.c_longlong
+    L.t_compress_batch2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     return L
 
 

@@ -127,6 +127,17 @@ static inline void __syncthreads()
     }
     T.cta_gen = my + 1;
 }
+static inline int __syncthreads_or(int p)
+{
+    static int acc = 0;                    // one CTA at a time
+    if (p) acc = 1;
+    __syncthreads();
+    int const r = acc;
+    __syncthreads();
+    if (simt::tid() == 0 || simt::g_threads[0].done) acc = 0;
+    __syncthreads();
+    return r;
+}
 static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu)
 {
     simt::collective(mask, 0, [](const unsigned long long*, unsigned, unsigned) { return 0ull; });
@@ -178,6 +189,7 @@ template <class T, class U> static inline T atomicMin(T* p, U v) { T o = *p; if 
 template <class T, class U> static inline T atomicMax(T* p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
 static inline void __nanosleep(unsigned) { simt::yield(); }
 static inline void __threadfence() {}
+static inline void __threadfence_block() {}
 static inline long long clock64() { return 0; }
 #define __log2f log2f
 
