@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libzb200.so")
+_LIB_PATH = os.environ.get("ZB200_LIB") or os.path.join(_HERE, "libzb200.so")     # ZB200_LIB: a tuning build (phase timers)
 
 K_COUNT = 16
 SRC_DEVICE = 1

@@ -23,25 +23,27 @@
 #pragma once
 
 #define Z2_NT       1024
-#define Z2_U        132                   // bytes per parse unit: 33 words, so the lanes of a warp start in 32 different banks
-#define Z2_Q        16384                 // positions per pass
-#define Z2_UPP      125                   // units per pass
-#define Z2_MAXU     1000
-#define Z2_RMAX     34                    // records per unit (a unit starts at most 33 matches)
+#define Z2_REG      288                   // positions per parse region (a warp walks one per pass)
+#define Z2_RPP      29                    // regions per pass
+#define Z2_Q        8192                  // positions per pass
+#define Z2_MAXU     512
+#define Z2_RMAX     76                    // records per region (at most 72 matches start in one)
 #define Z2_FARLOG   14
 #define Z2_MAXSEQ   33024
 #define Z2_STAGE    57344                 // bytes of staging / literal buffer in shared memory
 #define Z2_WARM     24                    // FSE warm-up symbols
 #define Z2_SEQ_SMEM 16384                 // sequence records that fit the (by then dead) input buffer
+#define Z2_MAXSUB   10                    // sub-blocks per chunk (3 chain lanes each: one warp)
+#define Z2_SUBSEQ   1536                  // sequences per sub-block aimed at
 
 struct Z2Scratch {
     u64 rec[Z2_MAXU * Z2_RMAX];           // unit records: start | len << 17 | dist << 35
     u64 fseq[Z2_MAXSEQ + 8];              // final sequences: ll | (ml - 3) << 17 | offBase << 34
     u8  lit[ZE_BLOCK + 64];               // gathered literals when they do not fit shared memory
-    u32 stage[(ZE_BLOCK + 4096) / 4];     // sequence-stream staging when it does not fit shared memory
 };
 
-struct Z2Mf { u16 far[1 << Z2_FARLOG]; u16 near[16][512]; u16 dist[Z2_Q + 16]; };
+static_assert(true, "");
+struct Z2Mf { u16 far[1 << Z2_FARLOG]; __align__(16) u16 hd[2][Z2_Q]; };
 struct Z2Ent {
     __align__(16) u32 stage[Z2_STAGE / 4];        // literals (gathered), later the sequence bitstream
     ZeCTable ct[4];                       // LL, OF, ML, Huffman-weight table
@@ -59,9 +61,14 @@ struct Z2Shared {
     u32 part[40];
     u8 llcode[64], mlcode[128];
     unsigned long long mbar;
-    u32 job, tail_from, bad, lit_mode, huf_tbl_bytes, seq_hdr_bytes, all_same;
-    u32 stream_bits[4];
+    u32 job, tail_from, bad, lit_mode, huf_tbl_bytes, seq_hdr_bytes, all_same, carry;
     u32 mtmp[36];
+    // sub-blocks and their literal streams
+    u32 sub_seq[Z2_MAXSUB + 1], sub_lit[Z2_MAXSUB + 1], sub_st0[Z2_MAXSUB + 1], sub_spre[Z2_MAXSUB + 1], sub_off[Z2_MAXSUB + 1];
+    u32 sub_mode[Z2_MAXSUB], sub_lh[Z2_MAXSUB], sub_pay[Z2_MAXSUB], sub_shb[Z2_MAXSUB], sub_spay[Z2_MAXSUB];
+    u32 fin[Z2_MAXSUB][3];
+    u32 st_start[4 * Z2_MAXSUB + 1], st_len[4 * Z2_MAXSUB + 1], st_cum[4 * Z2_MAXSUB + 1], st_pre[4 * Z2_MAXSUB + 1], st_byte[4 * Z2_MAXSUB + 1];
+    u32 n_streams;
 };
 
 // ---- shared-memory byte window helpers (buffer is 4-byte aligned, 12 bytes of slack after the last position read)
@@ -179,11 +186,30 @@ __device__ static bool z2_huf_build(ZeHuf& H, const u32* count, u32* wk, u32 lan
     return __shfl_sync(0xFFFFFFFFu, ok, 0) != 0;
 }
 
+// barrier over a subset of the CTA's warps (bar.sync id, threads); the CPU build of the kernels has its own
+#ifdef ZB_SIMT_EMULATION
+#define Z2_BAR_SYNC(id_, n_) simt_named_bar_sync(id_, n_)
+#elif defined(__CUDA_ARCH__)
+#define Z2_BAR_SYNC(id_, n_) asm volatile("bar.sync %0, %1;" :: "r"(id_), "r"(n_) : "memory")
+#else
+#define Z2_BAR_SYNC(id_, n_) do { } while (0)
+#endif
+
+#ifdef __CUDA_ARCH__
+#define Z2_OPAQUE8(a_) asm volatile("" : "+r"(a_[0]), "+r"(a_[1]), "+r"(a_[2]), "+r"(a_[3]), "+r"(a_[4]), "+r"(a_[5]), "+r"(a_[6]), "+r"(a_[7]) :: "memory")
+#else
+#define Z2_OPAQUE8(a_) do { } while (0)
+#endif
+
 #ifdef ZB_PHASE_TIMERS
 __device__ unsigned long long g_z2_phase[16];
 #define Z2_MARK(k) do { if (tid == 0) { long long const t_ = clock64(); atomicAdd(&g_z2_phase[k], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
+#define Z2_T0() t_aux = clock64()
+#define Z2_T1(k) atomicAdd(&g_z2_phase[k], (unsigned long long)(clock64() - t_aux))
 #else
 #define Z2_MARK(k) do { } while (0)
+#define Z2_T0() do { } while (0)
+#define Z2_T1(k) do { } while (0)
 #endif
 
 // records of one unit, four at a time (two 16-byte loads in flight) so that the L2 latency is paid once per four
@@ -203,7 +229,7 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
     Z2Scratch& G = scratch[blockIdx.x];
     u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef ZB_PHASE_TIMERS
-    long long t_phase = clock64();
+    long long t_phase = clock64(), t_aux = 0;
 #endif
 
     // symbol code look-up tables (ZSTD_LLcode / ZSTD_MLcode, zstd/zstd.c:19738,:19755), derived from the baselines
@@ -260,7 +286,7 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
         u32* const ow = (u32*)out;                                    // slots are 16-byte aligned
         const u8* const in = S.in;                                    // block byte i is in[skew + i]
         // while the copy is in flight: clear the far table
-        for (u32 i = tid; i < (1u << Z2_FARLOG) / 2; i += Z2_NT) ((u32*)S.mf.far)[i] = 0xFFFFFFFFu;
+        for (u32 i = tid; i < (1u << Z2_FARLOG) / 2; i += Z2_NT) ((u32*)S.mf.far)[i] = 0u;
         if (tid == 0) { S.bad = 0; S.all_same = 1; }
 #ifdef __CUDA_ARCH__
         if (n) { u32 ok = 0;
@@ -294,103 +320,136 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
         }
         Z2_MARK(0);
 
-        // ================================================================= match finding, a pass of Z2_Q positions at a time
-        u32 const npass = (n + Z2_Q - 1) / Z2_Q;
-        for (u32 ps = 0; ps < npass; ps++) {
-            u32 const q0 = ps * Z2_Q, npos = min((u32)Z2_Q, n - q0);
-            // ---- near links: warp w owns sub-chunk w
-            if (warp < ((npos + 1023) >> 10)) {
-                u16* const tab = S.mf.near[warp];
-                for (u32 i = lane; i < 256; i += 32) ((u32*)tab)[i] = 0xFFFFFFFFu;
-                __syncwarp();
-                u32 const c0 = q0 + (warp << 10), c1 = min(c0 + 1024u, q0 + npos);
-                for (u32 st = 0; st < 32; st++) {
-                    u32 const p = c0 + st * 32 + lane, pl = st * 32 + lane;
-                    bool const valid = p < c1 && p + 8 <= n;
-                    u32 const v = valid ? z2_ld32(in, skew + p) : 0u;
-                    u32 const h = (v * 2654435761u) >> 17;                       // 9 slot bits + 6 tag bits
-                    u32 const slot = h >> 6, tag = h & 63u, entry = (pl << 6) | tag;
-                    u32 dn = 0;
-                    if (lane < 16 && valid) { u32 const e = tab[slot]; if ((e & 63u) == tag && (e >> 6) < pl) dn = pl - (e >> 6); tab[slot] = (u16)entry; }
-                    __syncwarp();
-                    if (lane >= 16 && valid) { u32 const e = tab[slot]; if ((e & 63u) == tag && (e >> 6) < pl) dn = pl - (e >> 6); tab[slot] = (u16)entry; }
-                    __syncwarp();
-                    if (p < c1) S.mf.dist[p - q0] = (u16)dn;
-                }
-            }
-            __syncthreads();
-            // ---- far links + verification, rounds of 1024 positions
-            u32 const rounds = (npos + 1023) >> 10;
-            for (u32 r = 0; r < rounds; r++) {
-                u32 const p = q0 + (r << 10) + tid;
-                bool const inr = p < q0 + npos, valid = inr && p + 8 <= n;
-                u32 best = 0, bd = 0, hf = 0;
-                if (valid) {
-                    u64 const A = z2_ld64(in, skew + p);
-                    hf = z2_hash5(A);
-                    u32 const cf = S.mf.far[hf];
-                    u32 const df = (p - cf) & 0xFFFFu;
-                    if (cf != 0xFFFFu && df != 0 && df <= p) {
-                        u32 const m = z2_match16(in, skew, A, p, p - df, n);
-                        if (m >= 4) { best = m; bd = df; }
-                    }
-                    u32 const dn = S.mf.dist[p - q0];
-                    if (dn && dn != bd) {
-                        u32 const m = z2_match16(in, skew, A, p, p - dn, n);
-                        if (m >= 4 && m >= best) { best = m; bd = dn; }
-                    }
-                    if (p >= 4) {      // distances 1..4: the four bytes in front of p are next to A's
-                        u32 const W = z2_ld32(in, skew + p - 4);
-                        u64 const WA = (u64)W | ((u64)(u32)A << 32);
-                        #pragma unroll
-                        for (u32 d = 1; d <= 4; d++) {
-                            if ((u32)(WA >> (8 * (4 - d))) == (u32)A && d != bd) {
-                                u32 const m = z2_match16(in, skew, A, p, p - d, n);
-                                if (m > best) { best = m; bd = d; }
-                            }
-                        }
-                    }
-                    if (best > 15) best = 15;
-                }
-                u32 mn = __shfl_down_sync(0xFFFFFFFFu, best, 1);
-                if (lane == 0) S.mtmp[warp] = best;
-                __syncthreads();
-                if (lane == 31) mn = warp < 31 ? S.mtmp[warp + 1] : 0u;
-                bool const take = best >= 4 && !(best < 15 && mn > best + 1);        // one-step lazy
-                if (inr) S.mf.dist[p - q0] = (u16)(take ? bd : 0u);
-                if (valid && (p & 0xFFFFu) != 0xFFFFu) S.mf.far[hf] = (u16)p;
-                __syncthreads();
-            }
-            // ---- parse: thread t (< 125) walks unit ps * 125 + t
-            if (tid < Z2_UPP) {
-                u32 const u0 = q0 + tid * Z2_U;
-                if (u0 < q0 + npos) {
-                    u32 const u1 = min(u0 + (u32)Z2_U, q0 + npos);
-                    u64* const rec = G.rec + (u64)(ps * Z2_UPP + tid) * Z2_RMAX;
-                    u32 ip = u0 ? u0 : 1u, anchor = u0, cnt = 0, endm = 0;
-                    while (ip < u1) {
-                        u32 const d = S.mf.dist[ip - q0];
-                        if (!d) { ip++; continue; }
-                        u32 start = ip, a = ip, c = ip - d;
-                        for (;;) {          // forward length, 8 bytes at a time, never past n
-                            if (a + 8 > n) { while (a < n && in[skew + a] == in[skew + c]) { a++; c++; } break; }
-                            u64 const x = z2_ld64(in, skew + a) ^ z2_ld64(in, skew + c);
-                            if (x) { a += ze_common8(0, x); break; }
-                            a += 8; c += 8;
-                        }
-                        while (start > anchor && start > d && in[skew + start - 1] == in[skew + start - 1 - d]) start--;
-                        u32 const len = a - start;
-                        if (len < 4 || cnt >= Z2_RMAX - 1) { ip++; continue; }            // (verified >= 4 bytes: does not happen)
-                        rec[cnt++] = (u64)start | ((u64)len << 17) | ((u64)d << 35);
-                        ip = a; anchor = a; endm = a;
-                    }
-                    S.x0[ps * Z2_UPP + tid] = endm; S.x1[ps * Z2_UPP + tid] = cnt;        // for the unit's own thread
-                }
-            }
-            __syncthreads();
-        }
+        // ================================================================= match finding
+        // Positions are offsets into the shared-memory buffer here (s = skew + block position), so that groups of four and
+        // eight positions are word-aligned whatever the block's alignment in global memory.  A pass covers Z2_Q positions:
+        //   H  all threads: 14-bit hash of the five bytes at every position -> hd[]
+        //   L  warp 0, 32 positions per step, in order: hd[s] = distance to the previous position with the same hash
+        //      (one table for the whole block: the positions of a step do not see each other, everything earlier is exact)
+        //   V  warps 1-31, four positions per thread: common prefix with the candidate, 4..15 (15 = "15 or more") -> ml[]
+        //   P  warps 1-2, a lane per 132-byte unit: lazy greedy walk over ml[]; long matches are extended by the whole warp
+        // L of pass k+1 runs beside V and P of pass k (hd[] and ml[] are double-buffered).
+        u32 const e_end = skew + n;
+        u32 const npass = (e_end + Z2_Q - 1) / Z2_Q;
+        if (tid == 0) S.carry = 0;
+        #define Z2_HASH_PASS(k_) do { \
+            u32 const s0_ = (k_) * Z2_Q + 8 * tid; \
+            uint2 const w01_ = *(const uint2*)(in + s0_); u32 const w2_ = *(const u32*)(in + s0_ + 8); \
+            u32 wj_[9]; \
+            wj_[0] = w01_.x; wj_[1] = __funnelshift_r(w01_.x, w01_.y, 8); wj_[2] = __funnelshift_r(w01_.x, w01_.y, 16); wj_[3] = __funnelshift_r(w01_.x, w01_.y, 24); \
+            wj_[4] = w01_.y; wj_[5] = __funnelshift_r(w01_.y, w2_, 8); wj_[6] = __funnelshift_r(w01_.y, w2_, 16); wj_[7] = __funnelshift_r(w01_.y, w2_, 24); wj_[8] = w2_; \
+            u32 hh_[8]; \
+            _Pragma("unroll") for (u32 q_ = 0; q_ < 8; q_++) hh_[q_] = ((wj_[q_] * 2654435761u) ^ ((wj_[q_ + 1] >> 24) * 0x9E3779B1u)) >> (32 - Z2_FARLOG); \
+            *(uint4*)&S.mf.hd[(k_) & 1][8 * tid] = make_uint4(hh_[0] | (hh_[1] << 16), hh_[2] | (hh_[3] << 16), hh_[4] | (hh_[5] << 16), hh_[6] | (hh_[7] << 16)); \
+        } while (0)
+        // eight steps' table accesses are issued back to back (the stores do not need the loads' results); the distances are
+        // worked out afterwards (the empty asm keeps the compiler from pulling that work up between the loads)
+        #define Z2_LG 8
+        #define Z2_LINK_PASS(k_) do { \
+            u16* const hd_ = S.mf.hd[(k_) & 1]; \
+            u32 hq_[Z2_LG]; \
+            _Pragma("unroll") for (u32 u_ = 0; u_ < Z2_LG; u_++) hq_[u_] = hd_[u_ * 32 + lane]; \
+            for (u32 st_ = 0; st_ < Z2_Q / 32; st_ += Z2_LG) { \
+                u32 hn_[Z2_LG], cc_[Z2_LG]; \
+                _Pragma("unroll") for (u32 u_ = 0; u_ < Z2_LG; u_++) hn_[u_] = st_ + Z2_LG < Z2_Q / 32 ? (u32)hd_[(st_ + Z2_LG + u_) * 32 + lane] : 0u; \
+                _Pragma("unroll") for (u32 u_ = 0; u_ < Z2_LG; u_++) { \
+                    u32 const s_ = (k_) * Z2_Q + (st_ + u_) * 32 + lane; \
+                    cc_[u_] = S.mf.far[hq_[u_]]; \
+                    ZB_SIMT_STEP(); \
+                    if (s_ >= skew && s_ + 8 <= e_end) S.mf.far[hq_[u_]] = (u16)s_; \
+                    ZB_SIMT_STEP(); \
+                } \
+                Z2_OPAQUE8(cc_); \
+                _Pragma("unroll") for (u32 u_ = 0; u_ < Z2_LG; u_++) { \
+                    u32 const s_ = (k_) * Z2_Q + (st_ + u_) * 32 + lane; \
+                    u32 const d_ = (s_ - cc_[u_]) & 0xFFFFu; \
+                    hd_[(st_ + u_) * 32 + lane] = (u16)(s_ >= skew && s_ + 8 <= e_end && d_ + skew <= s_ ? d_ : 0u); \
+                    hq_[u_] = hn_[u_]; \
+                } \
+            } \
+        } while (0)
+        Z2_HASH_PASS(0);
+        __syncthreads();
+        if (warp == 0) Z2_LINK_PASS(0);
+        __syncthreads();
         Z2_MARK(1);
-        u32 const nunits = (npass - 1) * Z2_UPP + ((n - (npass - 1) * Z2_Q) + Z2_U - 1) / Z2_U;
+        for (u32 ps = 0; ps < npass; ps++) {
+            u32 const q0 = ps * Z2_Q;
+            if (ps + 1 < npass) Z2_HASH_PASS(ps + 1);
+            __syncthreads();
+            if (warp == 0) { if (ps + 1 < npass) Z2_LINK_PASS(ps + 1); }
+            else {
+                // ---- V + P: warp w owns the w-th region of Z2_REG positions of the pass and walks it in steps of 32: every lane
+                // verifies its position's candidate (common prefix 4..15, 15 = "15 or more"), then the warp takes the matches
+                // of the step greedily from the left (one-step lazy), extending long ones 256 bytes per vote
+                if (tid == 32) Z2_T0();
+                const u16* const hd = S.mf.hd[ps & 1];
+                u32 const carry = S.carry;                                    // end of the longest match of the earlier passes (buffer offset)
+                u32 const reg = warp - 1;
+                u32 const r0 = q0 + reg * Z2_REG, r1 = min(min(r0 + (u32)Z2_REG, q0 + (u32)Z2_Q), e_end);
+                if (reg < Z2_RPP && r0 < r1) {
+                    u32 const unit = ps * Z2_RPP + reg;
+                    u64* const rec = G.rec + (u64)unit * Z2_RMAX;
+                    u32 cover = max(max(r0, skew), carry), cnt = 0, endm = 0;
+                    // the candidate of position pos_ (0 = none) and the bytes it shares with it, 4..15
+                    #define Z2_VERIFY(pos_, m_, d_) { \
+                        m_ = 0; d_ = 0; \
+                        if ((pos_) < r1 && (pos_) > skew && (pos_) >= cover && (pos_) + 8 <= e_end) { \
+                            d_ = hd[(pos_) - q0]; \
+                            if (d_) { \
+                                u64 const x_ = z2_ld64(in, (pos_)) ^ z2_ld64(in, (pos_) - d_); \
+                                if (x_) m_ = ze_common8(0, x_); \
+                                else m_ = 8 + ze_common8(z2_ld64(in, (pos_) + 8), z2_ld64(in, (pos_) + 8 - d_)); \
+                                m_ = min(m_, min(15u, e_end - (pos_))); \
+                                if (m_ < 4) m_ = 0; \
+                            } \
+                        } }
+                    u32 m, d;
+                    Z2_VERIFY(r0 + lane, m, d)
+                    for (u32 b = r0; b < r1 && cover < r1; b += 32) {
+                        u32 const pos = b + lane;
+                        u32 m_nx, d_nx;                                       // the next step's candidates: their loads overlap this step's matches
+                        Z2_VERIFY(pos + 32, m_nx, d_nx)
+                        u32 mn = __shfl_down_sync(0xFFFFFFFFu, m, 1); if (lane == 31) mn = 0;
+                        bool const take = m >= 4 && !(m < 15 && mn > m + 1);                 // one-step lazy
+                        for (;;) {
+                            u32 const mask = __ballot_sync(0xFFFFFFFFu, take && pos >= cover);
+                            if (!mask) break;
+                            u32 const L = (u32)__ffs((int)mask) - 1;
+                            u32 const p = b + L, mL = __shfl_sync(0xFFFFFFFFu, m, (int)L), dL = __shfl_sync(0xFFFFFFFFu, d, (int)L);
+                            // backwards, down to the end of the previous match (all lanes compute the same); loads first
+                            bool const bk = p > cover && p >= dL + 4 + skew;
+                            u32 const xb = bk ? z2_ld32(in, p - 4) ^ z2_ld32(in, p - 4 - dL) : 1u << 31;
+                            u32 end = p + mL;
+                            if (mL == 15) {                     // bytes [p, p + 15) match: compare on from p + 8, eight bytes per lane
+                                u32 a = p + 8;
+                                for (;;) {
+                                    u32 const my = a + 8 * lane;
+                                    u32 cm = 8;                 // bytes of my window that match
+                                    if (my + 8 <= e_end) { u64 const x = z2_ld64(in, my) ^ z2_ld64(in, my - dL); if (x) cm = ze_common8(0, x); }
+                                    else { cm = 0; while (my + cm < e_end && in[my + cm] == in[my + cm - dL]) cm++; }
+                                    u32 const stop = __ballot_sync(0xFFFFFFFFu, cm < 8);
+                                    if (stop) { u32 const fl = (u32)__ffs((int)stop) - 1; end = a + 8 * fl + __shfl_sync(0xFFFFFFFFu, cm, (int)fl); break; }
+                                    a += 256;
+                                }
+                            }
+                            u32 start = p;
+                            if (bk) { u32 const same = xb ? ((u32)__clz((int)xb) >> 3) : 4u; start -= min(same, start - cover); }
+                            else while (start > cover && start > dL + skew && in[start - 1] == in[start - 1 - dL]) start--;
+                            if (cnt >= Z2_RMAX - 1) { cover = r1; break; }
+                            if (lane == 0) rec[cnt] = (u64)(start - skew) | ((u64)(end - start) << 17) | ((u64)dL << 35);
+                            cnt++; cover = end; endm = end - skew;
+                        }
+                        m = pos + 32 >= cover ? m_nx : 0u; d = d_nx;
+                    }
+                    if (lane == 0) { S.x0[unit] = endm; S.x1[unit] = cnt; if (endm) atomicMax(&S.carry, endm + skew); }
+                }
+                if (tid == 32) Z2_T1(13);
+            }
+            __syncthreads();
+            Z2_MARK(8);
+        }
+        u32 const nunits = (npass - 1) * Z2_RPP + ((e_end - (npass - 1) * Z2_Q) + Z2_REG - 1) / Z2_REG;
         u32 const my_cnt = tid < nunits ? S.x1[tid] : 0u;
         __syncthreads();
 
@@ -441,6 +500,7 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
                 z2_rep_apply(e0, e1, e2, a, b, c);
             }
         }
+        Z2_MARK(9);
         for (u32 i = tid; i < 8 * 256; i += Z2_NT) ((u32*)S.en.hist)[i] = 0;
         if (tid < 36) S.en.hLL[tid] = 0;
         if (tid < 32) S.en.hOF[tid] = 0;
@@ -459,8 +519,8 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
                 u32 const ll = s - cover, ml = e - s;
                 if (ll == 0 && d == r0) S.bad = 1;         // two adjacent matches with one offset: cannot be formed (see the notes); raw block if it ever is
                 u32 const ob = ze_off_code(d, ll, r0, r1, r2);
-                G.fseq[seq_base + (q - first_k)] = (u64)ll | ((u64)(ml - 3) << 17) | ((u64)ob << 34);
                 u32 const lc = ll < 64 ? S.llcode[ll] : ze_hibit(ll) + 19, mc = ml - 3 < 128 ? S.mlcode[ml - 3] : ze_hibit(ml - 3) + 36, oc = ze_hibit(ob);
+                G.fseq[seq_base + (q - first_k)] = (u64)ll | ((u64)(ml - 3) << 17) | ((u64)ob << 34) | ((u64)lc << 52) | ((u64)mc << 58);
                 atomicAdd(&S.en.hLL[lc], 1u); atomicAdd(&S.en.hML[mc], 1u); atomicAdd(&S.en.hOF[oc], 1u);
                 for (u32 k = 0; k < ll; k++) { u8 const b = in[skew + cover + k]; lit[lp + k] = b; atomicAdd(&hist[b], 1u); }
                 lp += ll; cover = e;
@@ -476,12 +536,14 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
         Z2_MARK(2);
 
         // ================================================================= entropy tables: four warps
+        Z2_T0();
         if (nseq) {
             if (tid == 0)  ze_make_table(S.en.ct[0], S.en.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.en.tmp_sym[0]);
             if (tid == 32) ze_make_table(S.en.ct[1], S.en.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.en.tmp_sym[1]);
             if (tid == 64) ze_make_table(S.en.ct[2], S.en.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.en.tmp_sym[2]);
         }
         if (warp == 3) {
+            Z2_T0();
             u32 mode = 0, tb = 0;
             u32 most = 0; for (u32 s = lane; s < 256; s += 32) most = max(most, S.en.hist[0][s]);
             #pragma unroll
@@ -492,205 +554,295 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
                 if (lane == 0 && ok) { tb = ze_huf_write_table(S.en.huf_tbl, S.en.huf, S.en.ct[3], S.en.tmp_sym[3]); if (tb) mode = 2; }
             }
             if (lane == 0) { S.lit_mode = mode; S.huf_tbl_bytes = tb; }
+            if (lane == 0) Z2_T1(15);
         }
+        if (tid == 0) Z2_T1(7);
         __syncthreads();
         Z2_MARK(3);
 
-        // ================================================================= literals section, written straight into the slot
-        bool const four = nlit >= 256;
-        u32 const seg = four ? (nlit + 3) / 4 : nlit, nstreams = four ? 4u : 1u;
-        u32 const nchunks = (nlit + 31) / 32, lrounds = (nchunks + Z2_NT - 1) / Z2_NT;
-        u32 lit_mode = S.lit_mode, lit_payload = 0, lh = 0;
-        u32 const tb = S.huf_tbl_bytes;
-        // one chunk = 32 literals at an aligned index (two 16-byte loads); a chunk meets at most one stream border
-        #define Z2_CHUNK_BITS(g_, sA_, bnd_, bA_, bB_, c_) \
-            uint4 c_[2]; u32 sA_ = 0, bnd_ = 0xFFFFFFFFu, bA_ = 0, bB_ = 0; \
-            if ((g_) < nchunks) { \
-                c_[0] = *(const uint4*)(lit + 32 * (g_)); c_[1] = *(const uint4*)(lit + 32 * (g_) + 16); \
-                if (four) { sA_ = min(32 * (g_) / seg, 3u); if (sA_ < 3 && (sA_ + 1) * seg < 32 * (g_) + 32) bnd_ = (sA_ + 1) * seg; } \
-                const u32* const cw_ = (const u32*)c_; \
-                _Pragma("unroll") for (u32 k_ = 0; k_ < 32; k_++) { u32 const i_ = 32 * (g_) + k_; if (i_ < nlit) { u32 const nb_ = S.en.huf.nb[(cw_[k_ >> 2] >> ((k_ & 3) * 8)) & 255u]; if (i_ < bnd_) bA_ += nb_; else bB_ += nb_; } } \
-            } else { c_[0] = make_uint4(0, 0, 0, 0); c_[1] = c_[0]; }
-        if (lit_mode == 2) {
-            u32 run[4] = {0, 0, 0, 0};
-            for (u32 rd = 0; rd < lrounds; rd++) {
-                u32 const g = rd * Z2_NT + tid;
-                Z2_CHUNK_BITS(g, sA, bnd, bA, bB, cdat)
-                (void)cdat;
-                for (u32 st = 0; st < nstreams; st++) {
-                    u32 const v = (sA == st ? bA : 0u) + (sA + 1 == st ? bB : 0u);
-                    u32 tot; (void)z2_scan(v, S.part, tot); run[st] += tot;
-                }
-            }
-            if (tid < 4) S.stream_bits[tid] = run[tid];
-            u32 est = tb + (four ? 6u : 0u);
-            for (u32 st = 0; st < nstreams; st++) est += (run[st] + 1 + 7) / 8;
-            if (est + (nlit >> 6) + 2 >= nlit) lit_mode = 0;                      // ZSTD_minGain, zstd/zstd.c:19831 (uniform: every thread holds the totals)
-            else lit_payload = est;
-            __syncthreads();
-        }
-        if (lit_mode == 2) {
-            lh = 3 + (nlit >= 1024) + (nlit >= 16384);
-            u32 sbyte[4], sbytes[4]; { u32 o = tb + (four ? 6u : 0u); for (u32 st = 0; st < nstreams; st++) { sbytes[st] = (S.stream_bits[st] + 1 + 7) / 8; sbyte[st] = o; o += sbytes[st]; } }
-            u32 const o_pl = 3 + lh;                                                  // byte offset of the payload in the slot
-            for (u32 i = tid; i < (o_pl + lit_payload) / 4 + 2; i += Z2_NT) ow[i] = 0;
-            __syncthreads();
-            for (u32 i = tid; i < tb; i += Z2_NT) z2_or_byte(ow, o_pl + i, S.en.huf_tbl[i]);
-            if (four && tid < 3) { z2_or_byte(ow, o_pl + tb + 2 * tid, sbytes[tid]); z2_or_byte(ow, o_pl + tb + 2 * tid + 1, sbytes[tid] >> 8); }
-            if (tid < nstreams) { Z2Bits w; w.init(ow, (o_pl + sbyte[tid]) * 8 + S.stream_bits[tid]); w.put(1, 1); w.flush(); }     // end marks
-            u32 run[4] = {0, 0, 0, 0};
-            for (u32 rd = 0; rd < lrounds; rd++) {
-                u32 const g = rd * Z2_NT + tid;
-                Z2_CHUNK_BITS(g, sA, bnd, bA, bB, cdat)
-                u32 pA = 0, pB = 0;
-                for (u32 st = 0; st < nstreams; st++) {
-                    u32 const v = (sA == st ? bA : 0u) + (sA + 1 == st ? bB : 0u);
-                    u32 tot; u32 const pre = z2_scan(v, S.part, tot) + run[st]; run[st] += tot;
-                    if (sA == st) pA = pre;
-                    if (sA + 1 == st) pB = pre;
-                }
-                if (g < nchunks) {      // symbols are written last to first: a span ends at (stream total - bits before it)
-                    const u32* const cw = (const u32*)cdat;
-                    if (bB) {
-                        Z2Bits w; w.init(ow, (o_pl + sbyte[sA + 1]) * 8 + (S.stream_bits[sA + 1] - pB - bB));
-                        #pragma unroll
-                        for (u32 kk = 0; kk < 32; kk++) { u32 const k = 31 - kk, i = 32 * g + k; if (i < nlit && i >= bnd) { u32 const sym = (cw[k >> 2] >> ((k & 3) * 8)) & 255u; w.put(S.en.huf.code[sym], S.en.huf.nb[sym]); } }
-                        w.flush();
-                    }
-                    if (bA) {
-                        Z2Bits w; w.init(ow, (o_pl + sbyte[sA]) * 8 + (S.stream_bits[sA] - pA - bA));
-                        #pragma unroll
-                        for (u32 kk = 0; kk < 32; kk++) { u32 const k = 31 - kk, i = 32 * g + k; if (i < nlit && i < bnd) { u32 const sym = (cw[k >> 2] >> ((k & 3) * 8)) & 255u; w.put(S.en.huf.code[sym], S.en.huf.nb[sym]); } }
-                        w.flush();
-                    }
-                }
-            }
-            if (tid == 0) {      // section header (ZSTD_compressLiterals, zstd/zstd.c:20932-21038), OR-ed: its word also holds payload bits
-                u32 v; u32 hb[5];
-                if (lh == 3) { v = 2u | ((four ? 1u : 0u) << 2) | (nlit << 4) | (lit_payload << 14); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; }
-                else if (lh == 4) { v = 2u | (2u << 2) | (nlit << 4) | (lit_payload << 18); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; hb[3] = v >> 24; }
-                else { v = 2u | (3u << 2) | (nlit << 4) | (lit_payload << 22); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; hb[3] = v >> 24; hb[4] = lit_payload >> 10; }
-                for (u32 k = 0; k < lh; k++) z2_or_byte(ow, 3 + k, hb[k]);
-            }
-        } else {
-            lh = 1 + (nlit > 31) + (nlit > 4095);
-            u8* const o = out + 3;
-            if (lit_mode == 0) { for (u32 i = tid; i < nlit; i += Z2_NT) o[lh + i] = lit[i]; lit_payload = nlit; }
-            else { if (tid == 0) o[lh] = lit[0]; lit_payload = 1; }
-            if (tid == 0) {      // ZSTD_noCompressLiterals / ZSTD_compressRleLiteralsBlock, zstd/zstd.c:20851-20930
-                u32 const t = lit_mode;
-                if (lh == 1) o[0] = (u8)(t | (nlit << 3));
-                else if (lh == 2) { u32 const v = t | (1u << 2) | (nlit << 4); o[0] = (u8)v; o[1] = (u8)(v >> 8); }
-                else { u32 const v = t | (3u << 2) | (nlit << 4); o[0] = (u8)v; o[1] = (u8)(v >> 8); o[2] = (u8)(v >> 16); }
-            }
-        }
-        __syncthreads();
-        Z2_MARK(4);
-
-        // ================================================================= sequences section
-        u32 seq_payload = 0;
-        if (tid == 0) {      // header (ZSTD_entropyCompressSeqStore_internal, zstd/zstd.c:25893-25926)
-            u8* const q = S.en.seq_hdr_buf; u32 k = 0;
-            if (nseq < 128) q[k++] = (u8)nseq;
-            else if (nseq < 0x7F00) { q[k++] = (u8)((nseq >> 8) + 0x80); q[k++] = (u8)nseq; }
-            else { q[k++] = 0xFF; q[k++] = (u8)(nseq - 0x7F00); q[k++] = (u8)((nseq - 0x7F00) >> 8); }
-            if (nseq) {
-                q[k++] = (u8)((S.en.ct[0].mode << 6) | (S.en.ct[1].mode << 4) | (S.en.ct[2].mode << 2));
-                for (int t = 0; t < 3; t++) for (u32 i = 0; i < S.en.ct[t].hdr_bytes; i++) q[k++] = S.en.ct[t].hdr[i];
-            }
-            S.seq_hdr_bytes = k;
-        }
-        // the input is no longer needed (a raw block is copied from global memory): its buffer takes the sequence records
+        // ================================================================= sub-blocks
+        // The chunk's sequences are cut into up to Z2_MAXSUB runs of equal length and every run becomes a zstd block of its
+        // own (its literals are a contiguous range of the gathered literals).  The FSE state chains -- three strictly serial
+        // recurrences per block -- then run side by side, one lane per (sub-block, table), each over ~nseq / nsub
+        // sequences.  The first sub-block carries the tables; the others say "repeat" (sequences) / "treeless" (literals).
+        // The input buffer is dead from here on (a raw block is copied from global memory): it takes the sequence records.
         u64* const sq = (u64*)S.in;
         for (u32 i = tid; i < nseq && i < Z2_SEQ_SMEM; i += Z2_NT) sq[i] = G.fseq[i];
+        #define Z2_SEQ(i_) ((i_) < Z2_SEQ_SMEM ? sq[i_] : G.fseq[i_])
+        u32 const K = nseq ? (nseq + Z2_NT - 1) / Z2_NT : 1u;
+        u32 const nthr = (nseq + K - 1) / K;                                   // threads that own sequences
+        u32 const want = nseq ? min((u32)Z2_MAXSUB, (nseq + Z2_SUBSEQ - 1) / Z2_SUBSEQ) : 1u;
+        u32 const tps = nseq ? (nthr + want - 1) / want : 1u;                  // threads per sub-block
+        u32 const nsub = nseq ? (nthr + tps - 1) / tps : 1u;
+        u32 const lo = tid * K, hi = min(lo + K, nseq);
+        bool const act = lo < nseq;
+        u32 const mysub = act ? tid / tps : 0u;
         __syncthreads();
-        u32 const shb = S.seq_hdr_bytes;
-        u32 const o_sh = 3 + lh + lit_payload;
-        if (nseq) {
-            ZeCTable const& cL = S.en.ct[0]; ZeCTable const& cO = S.en.ct[1]; ZeCTable const& cM = S.en.ct[2];
-            bool const rL = cL.mode == 1, rO = cO.mode == 1, rM = cM.mode == 1;
-            u32 const K = (nseq + Z2_NT - 1) / Z2_NT;
-            u32 const lo = tid * K, hi = min(lo + K, nseq);
-            bool const act = lo < nseq;
-            #define Z2_SEQ(i_) ((i_) < Z2_SEQ_SMEM ? sq[i_] : G.fseq[i_])
-            #define Z2_CODES(r_, lc_, oc_, mc_, ll_, mb_, ob_) \
-                u32 const ll_ = (u32)(r_) & 0x1FFFFu, mb_ = (u32)((r_) >> 17) & 0x1FFFFu, ob_ = (u32)((r_) >> 34); \
-                u32 const lc_ = ll_ < 64 ? S.llcode[ll_] : ze_hibit(ll_) + 19, mc_ = mb_ < 128 ? S.mlcode[mb_] : ze_hibit(mb_) + 36, oc_ = ze_hibit(ob_);
-            // states on entry of this lane's range (= after encoding sequence `hi`): exact for the last range, a guess otherwise
-            u32 inL = 0, inO = 0, inM = 0;
-            if (act) {
-                u32 const ws = hi == nseq ? nseq - 1 : min(nseq - 1, hi + Z2_WARM - 1);
-                { u64 const r = Z2_SEQ(ws); Z2_CODES(r, lc, oc, mc, ll, mb, ob) (void)ll; (void)mb; (void)ob;
-                  inL = rL ? 0u : z2_fse_init(cL, lc); inO = rO ? 0u : z2_fse_init(cO, oc); inM = rM ? 0u : z2_fse_init(cM, mc); }
-                if (hi != nseq) for (u32 i = ws; i-- > hi;) {
-                    u64 const r = Z2_SEQ(i); Z2_CODES(r, lc, oc, mc, ll, mb, ob) (void)ll; (void)mb; (void)ob;
-                    if (!rO) { u32 const nb = (inO + (u32)cO.dnb[oc]) >> 16; inO = cO.state[(inO >> nb) + cO.dfs[oc]]; }
-                    if (!rM) { u32 const nb = (inM + (u32)cM.dnb[mc]) >> 16; inM = cM.state[(inM >> nb) + cM.dfs[mc]]; }
-                    if (!rL) { u32 const nb = (inL + (u32)cL.dnb[lc]) >> 16; inL = cL.state[(inL >> nb) + cL.dfs[lc]]; }
-                }
-            }
-            u32 bits = 0;
-            for (;;) {
-                // run the range from its entry states: bit count and exit states
-                u32 sL = inL, sO = inO, sM = inM; bits = 0;
-                if (act) for (u32 i = hi; i-- > lo;) {
-                    u64 const r = Z2_SEQ(i); Z2_CODES(r, lc, oc, mc, ll, mb, ob) (void)ll; (void)mb; (void)ob;
-                    bits += e_LL_bits[lc] + e_ML_bits[mc] + oc;
-                    if (i == nseq - 1) continue;                                         // the last sequence only initialises the states
-                    if (!rO) { u32 const nb = (sO + (u32)cO.dnb[oc]) >> 16; bits += nb; sO = cO.state[(sO >> nb) + cO.dfs[oc]]; }
-                    if (!rM) { u32 const nb = (sM + (u32)cM.dnb[mc]) >> 16; bits += nb; sM = cM.state[(sM >> nb) + cM.dfs[mc]]; }
-                    if (!rL) { u32 const nb = (sL + (u32)cL.dnb[lc]) >> 16; bits += nb; sL = cL.state[(sL >> nb) + cL.dfs[lc]]; }
-                }
-                S.x0[tid] = sL; S.x1[tid] = sO; S.x2[tid] = sM;
-                __syncthreads();
-                bool wrong = false;
-                if (act && hi != nseq) {       // the lane above me ends where I begin
-                    u32 const tL = S.x0[tid + 1], tO = S.x1[tid + 1], tM = S.x2[tid + 1];
-                    if (tL != inL || tO != inO || tM != inM) { wrong = true; inL = tL; inO = tO; inM = tM; }
-                }
-                if (!__syncthreads_or(wrong ? 1 : 0)) break;
-            }
-            // bit offset of this range: ranges are written from the last sequence down, so everything above me comes first
-            u32 total_bits; u32 const before_fwd = z2_scan(bits, S.part, total_bits);
-            u32 const my_off = total_bits - before_fwd - bits;
-            u32 const logL = rL ? 0u : cL.log, logO = rO ? 0u : cO.log, logM = rM ? 0u : cM.log;
-            seq_payload = (total_bits + logM + logO + logL + 1 + 7) / 8;
-            u32* const stage = seq_payload + 8 <= Z2_STAGE ? S.en.stage : G.stage;
-            for (u32 i = tid; i < seq_payload / 4 + 2; i += Z2_NT) stage[i] = 0;
-            __syncthreads();
-            if (act) {
-                Z2Bits w; w.init(stage, my_off);
-                u32 sL = inL, sO = inO, sM = inM;
-                for (u32 i = hi; i-- > lo;) {
-                    u64 const r = Z2_SEQ(i); Z2_CODES(r, lc, oc, mc, ll, mb, ob)
-                    if (i != nseq - 1) {
-                        if (!rO) { u32 const nb = (sO + (u32)cO.dnb[oc]) >> 16; w.put(sO, nb); sO = cO.state[(sO >> nb) + cO.dfs[oc]]; }
-                        if (!rM) { u32 const nb = (sM + (u32)cM.dnb[mc]) >> 16; w.put(sM, nb); sM = cM.state[(sM >> nb) + cM.dfs[mc]]; }
-                        if (!rL) { u32 const nb = (sL + (u32)cL.dnb[lc]) >> 16; w.put(sL, nb); sL = cL.state[(sL >> nb) + cL.dfs[lc]]; }
-                    }
-                    w.put(ll, e_LL_bits[lc]); w.put(mb, e_ML_bits[mc]); w.put(ob, oc);
-                }
-                if (lo == 0) { w.put(sM, logM); w.put(sO, logO); w.put(sL, logL); w.put(1, 1); }      // flush ML, OF, LL states + end mark
-                w.flush();
-            }
-            __syncthreads();
-            const u8* const ps8 = (const u8*)stage;
-            for (u32 i = tid; i < seq_payload; i += Z2_NT) out[o_sh + shb + i] = ps8[i];
+        {   // where every sub-block's literals start
+            u32 lsum = 0;
+            if (act) for (u32 i = lo; i < hi; i++) lsum += (u32)Z2_SEQ(i) & 0x1FFFFu;
+            u32 tot; u32 const lpre = z2_scan(lsum, S.part, tot);
+            if (act && tid % tps == 0) { S.sub_lit[mysub] = lpre; S.sub_seq[mysub] = lo; }
+            if (tid == 0) { S.sub_lit[nsub] = nlit; S.sub_seq[nsub] = nseq; if (!nseq) { S.sub_lit[0] = 0; S.sub_seq[0] = 0; } }
         }
-        for (u32 i = tid; i < shb; i += Z2_NT) out[o_sh + i] = S.en.seq_hdr_buf[i];
-        Z2_MARK(5);
-        // ================================================================= block header; raw fallback (cSize >= srcSize - minGain, zstd/zstd.c:25987)
-        u32 const body = lh + lit_payload + shb + seq_payload;
-        bool const use_raw = S.bad || body + (n >> 7) + 2 >= n || body >= ZE_BLOCK;
         __syncthreads();
-        if (use_raw) for (u32 i = tid; i < n; i += Z2_NT) out[3 + i] = gsrc[i];
+        u32 const chunk_lit_mode = S.lit_mode, tb = S.huf_tbl_bytes;
+        // ---- Huffman streams: every sub-block with >= 64 literals gets one (< 256 literals) or four streams
         if (tid == 0) {
-            u32 const bsz = use_raw ? n : body;
-            u32 const bh = job.last | ((use_raw ? 0u : 2u) << 1) | (bsz << 3);
-            out[0] = (u8)bh; out[1] = (u8)(bh >> 8); out[2] = (u8)(bh >> 16);
-            outs[j].csize = 3 + bsz;
+            u32 ns = 0, cum = 0;
+            for (u32 sb = 0; sb < nsub; sb++) {
+                u32 const l0 = S.sub_lit[sb], nl = S.sub_lit[sb + 1] - l0;
+                S.sub_st0[sb] = ns;
+                if (chunk_lit_mode == 2 && nl >= 64) {
+                    u32 const nst = nl >= 256 ? 4u : 1u, seg = nst == 4 ? (nl + 3) / 4 : nl;
+                    for (u32 k = 0; k < nst; k++) {
+                        u32 const a0 = k * seg, a1 = k == nst - 1 ? nl : (k + 1) * seg;
+                        S.st_start[ns] = l0 + a0; S.st_len[ns] = a1 - a0; S.st_cum[ns] = cum; cum += (a1 - a0 + 31) / 32; ns++;
+                    }
+                }
+            }
+            S.sub_st0[nsub] = ns; S.st_cum[ns] = cum; S.n_streams = ns;
         }
+        __syncthreads();
+        u32 const n_streams = S.n_streams, n_chunks = S.st_cum[n_streams];
+        // a chunk = 32 literals of one stream; its bytes come as nine aligned words
+        #define Z2_CHUNK_LOAD(g_, k_, c_, cnt_, cw_) \
+            u32 k_ = 0, c_ = 0, cnt_ = 0; u32 cw_[8]; \
+            if ((g_) < n_chunks) { \
+                { u32 a_ = 0, b_ = n_streams; while (b_ - a_ > 1) { u32 const m_ = (a_ + b_) >> 1; if (S.st_cum[m_] <= (g_)) a_ = m_; else b_ = m_; } k_ = a_; } \
+                c_ = (g_) - S.st_cum[k_]; cnt_ = min(32u, S.st_len[k_] - 32 * c_); \
+                u32 const off_ = S.st_start[k_] + 32 * c_; const u32* const wp_ = (const u32*)lit + (off_ >> 2); u32 const sh_ = (off_ & 3) * 8; \
+                u32 prev_ = wp_[0]; \
+                _Pragma("unroll") for (u32 q_ = 0; q_ < 8; q_++) { u32 const nx_ = wp_[q_ + 1]; cw_[q_] = __funnelshift_r(prev_, nx_, sh_); prev_ = nx_; } \
+            } else { _Pragma("unroll") for (u32 q_ = 0; q_ < 8; q_++) cw_[q_] = 0; }
+        u32 const lrounds = (n_chunks + Z2_NT - 1) / Z2_NT;                     // <= 5
+        u32 cbits[5] = {0, 0, 0, 0, 0}, cpre[5] = {0, 0, 0, 0, 0};
+        {
+            u32 running = 0;
+            #pragma unroll
+            for (u32 rd = 0; rd < 5; rd++) if (rd < lrounds) {
+                u32 const g = rd * Z2_NT + tid;
+                Z2_CHUNK_LOAD(g, k, c, cnt, cw)
+                u32 bits = 0;
+                #pragma unroll
+                for (u32 q = 0; q < 32; q++) if (q < cnt) bits += S.en.huf.nb[(cw[q >> 2] >> ((q & 3) * 8)) & 255u];
+                u32 tot; u32 const pre = z2_scan(bits, S.part, tot) + running;
+                cbits[rd] = bits; cpre[rd] = pre;
+                if (g < n_chunks && c == 0) S.st_pre[k] = pre;
+                running += tot;
+            }
+            if (tid == 0) S.st_pre[n_streams] = running;
+        }
+        __syncthreads();
+        Z2_MARK(11);
+        // ---- FSE state chains: warp 0, lane 3 * sub-block + table (0 LL, 1 OF, 2 ML) walks its sub-block from the last
+        // sequence to the first and leaves the state on entry of every thread's range in x0 / x1 / x2 (the ranges are then
+        // re-run by their threads, all at once, to count and to write the bits)
+        if (warp == 0 && nseq) {
+            u32 const sb = lane / 3, t = lane - 3 * sb;
+            if (sb < nsub) {
+                ZeCTable const& ct = S.en.ct[t];
+                if (ct.mode == 1) S.fin[sb][t] = 0;            // RLE: no state bits
+                else {
+                    u32* const xb = t == 0 ? S.x0 : t == 1 ? S.x1 : S.x2;
+                    u32 const s_lo = S.sub_seq[sb], s_hi = S.sub_seq[sb + 1];
+                    u32 const sh = t == 0 ? 52u : 58u;
+                    u32 const m_of = t == 1 ? 0xFFFFFFFFu : 0u;           // branch-free selection: the three lanes of a sub-block stay converged
+                    #define Z2_CODE_OF(r_) ((ze_hibit(((u32)((r_) >> 34) & 0x3FFFFu) | 1u) & m_of) | ((u32)((r_) >> sh) & 63u & ~m_of))
+                    u32 i = s_hi - 1;
+                    u32 q = i / K, r = i - q * K;
+                    u32 state = z2_fse_init(ct, Z2_CODE_OF(Z2_SEQ(i)));
+                    int dnb = 0, dfs = 0;
+                    if (i > s_lo) { u32 const sym = Z2_CODE_OF(Z2_SEQ(i - 1)); dnb = ct.dnb[sym]; dfs = ct.dfs[sym]; }
+                    // two sequences ahead: the record; one ahead: its symbol's deltas; now: the state transition
+                    #define Z2_CHAIN_LOOP(SEQ_) { \
+                        u64 rr1_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
+                        while (i > s_lo) { \
+                            i--; if (r == 0) { r = K - 1; q--; } else r--; \
+                            u64 const rr2_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
+                            u32 const nsym_ = Z2_CODE_OF(rr1_); \
+                            int const ndnb_ = ct.dnb[nsym_], ndfs_ = ct.dfs[nsym_]; \
+                            if (r == K - 1) xb[q] = state; \
+                            u32 const nb_ = (state + (u32)dnb) >> 16; \
+                            state = ct.state[(state >> nb_) + dfs]; \
+                            dnb = ndnb_; dfs = ndfs_; rr1_ = rr2_; \
+                        } }
+                    #define Z2_SEQ_S(i_) sq[i_]
+                    if (s_hi <= Z2_SEQ_SMEM) Z2_CHAIN_LOOP(Z2_SEQ_S) else Z2_CHAIN_LOOP(Z2_SEQ)
+                    S.fin[sb][t] = state;
+                }
+            }
+        }
+        __syncthreads();
+        Z2_MARK(10);
+        // ---- every thread re-runs its range from the recorded states: bit count, then (below) the bits themselves
+        ZeCTable const& cL = S.en.ct[0]; ZeCTable const& cO = S.en.ct[1]; ZeCTable const& cM = S.en.ct[2];
+        bool const rL = cL.mode == 1, rO = cO.mode == 1, rM = cM.mode == 1;
+        u32 const my_shi = act ? S.sub_seq[mysub + 1] : 0u;
+        u32 inL = 0, inO = 0, inM = 0;
+        if (act) {
+            if (hi == my_shi) { u64 const r = Z2_SEQ(hi - 1); u32 const lc = (u32)(r >> 52) & 63u, mc = (u32)(r >> 58), oc = ze_hibit((u32)(r >> 34) & 0x3FFFFu);
+                                inL = rL ? 0u : z2_fse_init(cL, lc); inO = rO ? 0u : z2_fse_init(cO, oc); inM = rM ? 0u : z2_fse_init(cM, mc); }
+            else { inL = S.x0[tid]; inO = S.x1[tid]; inM = S.x2[tid]; }
+        }
+        u32 sbits = 0;
+        if (act) {
+            u32 sL = inL, sO = inO, sM = inM;
+            for (u32 i = hi; i-- > lo;) {
+                u64 const r = Z2_SEQ(i);
+                u32 const lc = (u32)(r >> 52) & 63u, mc = (u32)(r >> 58), oc = ze_hibit((u32)(r >> 34) & 0x3FFFFu);
+                sbits += e_LL_bits[lc] + e_ML_bits[mc] + oc;
+                if (i == my_shi - 1) continue;                                       // the last sequence only initialises the states
+                if (!rO) { u32 const nb = (sO + (u32)cO.dnb[oc]) >> 16; sbits += nb; sO = cO.state[(sO >> nb) + cO.dfs[oc]]; }
+                if (!rM) { u32 const nb = (sM + (u32)cM.dnb[mc]) >> 16; sbits += nb; sM = cM.state[(sM >> nb) + cM.dfs[mc]]; }
+                if (!rL) { u32 const nb = (sL + (u32)cL.dnb[lc]) >> 16; sbits += nb; sL = cL.state[(sL >> nb) + cL.dfs[lc]]; }
+            }
+        }
+        u32 seq_tot; u32 const spre = z2_scan(sbits, S.part, seq_tot);
+        if (act && tid % tps == 0) S.sub_spre[mysub] = spre;
+        if (tid == 0) S.sub_spre[nsub] = seq_tot;
+        __syncthreads();
+        // ---- layout (thread 0): literal mode, header sizes and byte offset of every sub-block
+        if (tid == 0) {
+            bool have_tree = false; u32 off = 0;
+            u32 const logsum = nseq ? (S.en.ct[0].mode == 1 ? 0u : S.en.ct[0].log) + (S.en.ct[1].mode == 1 ? 0u : S.en.ct[1].log) + (S.en.ct[2].mode == 1 ? 0u : S.en.ct[2].log) : 0u;
+            u32 hdr_first = 0, hdr_next = 0;               // table descriptions in the first / the following sub-blocks
+            if (nseq) for (int t = 0; t < 3; t++) { hdr_first += S.en.ct[t].hdr_bytes; if (S.en.ct[t].mode == 1) hdr_next += 1; }
+            for (u32 sb = 0; sb < nsub; sb++) {
+                u32 const nl = S.sub_lit[sb + 1] - S.sub_lit[sb];
+                u32 mode = 0, pay = nl, lh;
+                if (chunk_lit_mode == 1 && nl) { mode = 1; pay = 1; }
+                else if (chunk_lit_mode == 2 && nl >= 64) {
+                    u32 const k0 = S.sub_st0[sb], k1 = S.sub_st0[sb + 1];
+                    u32 est = (have_tree ? 0u : tb) + (k1 - k0 == 4 ? 6u : 0u);
+                    for (u32 k = k0; k < k1; k++) est += (S.st_pre[k + 1] - S.st_pre[k] + 1 + 7) / 8;
+                    if (est < nl) { mode = have_tree ? 3u : 2u; have_tree = true; pay = est; }
+                }
+                if (mode >= 2) lh = 3 + (nl >= 1024) + (nl >= 16384); else lh = 1 + (nl > 31) + (nl > 4095);
+                u32 const ns = S.sub_seq[sb + 1] - S.sub_seq[sb];
+                u32 shb = ns < 128 ? 1u : (ns < 0x7F00 ? 2u : 3u);
+                u32 spay = 0;
+                if (ns) { shb += 1 + (sb == 0 ? hdr_first : hdr_next); spay = (S.sub_spre[sb + 1] - S.sub_spre[sb] + logsum + 1 + 7) / 8; }
+                S.sub_mode[sb] = mode; S.sub_lh[sb] = lh; S.sub_pay[sb] = pay; S.sub_shb[sb] = shb; S.sub_spay[sb] = spay; S.sub_off[sb] = off;
+                off += 3 + lh + pay + shb + spay;
+            }
+            S.sub_off[nsub] = off;
+        }
+        __syncthreads();
+        Z2_MARK(12);
+        u32 const body_total = S.sub_off[nsub];
+        bool const use_raw = S.bad || body_total + (n >> 7) + 2 >= n + 3 * nsub || body_total >= slot_bytes;
+        if (use_raw) {          // cSize >= srcSize - minGain (zstd/zstd.c:25987): one raw block
+            for (u32 i = tid; i < n; i += Z2_NT) out[3 + i] = gsrc[i];
+            if (tid == 0) { u32 const bh = job.last | (n << 3); out[0] = (u8)bh; out[1] = (u8)(bh >> 8); out[2] = (u8)(bh >> 16); outs[j].csize = 3 + n; }
+            Z2_MARK(5);
+            __syncthreads();
+            continue;
+        }
+        for (u32 i = tid; i < body_total / 4 + 2; i += Z2_NT) ow[i] = 0;
+        __syncthreads();
+        // ---- headers: block, literals section, sequences section (OR-ed: their words also hold payload bits)
+        if (tid < nsub) {
+            u32 const sb = tid, o = S.sub_off[sb], mode = S.sub_mode[sb], lh = S.sub_lh[sb], pay = S.sub_pay[sb];
+            u32 const nl = S.sub_lit[sb + 1] - S.sub_lit[sb], ns = S.sub_seq[sb + 1] - S.sub_seq[sb];
+            u32 const bsz = S.sub_off[sb + 1] - o - 3;
+            u32 const bh = ((job.last && sb == nsub - 1) ? 1u : 0u) | (2u << 1) | (bsz << 3);
+            z2_or_byte(ow, o, bh); z2_or_byte(ow, o + 1, bh >> 8); z2_or_byte(ow, o + 2, bh >> 16);
+            u32 hb[5] = {0, 0, 0, 0, 0};
+            if (mode >= 2) {        // ZSTD_compressLiterals, zstd/zstd.c:20932-21038
+                bool const four = S.sub_st0[sb + 1] - S.sub_st0[sb] == 4;
+                if (lh == 3) { u32 const v = mode | ((four ? 1u : 0u) << 2) | (nl << 4) | (pay << 14); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; }
+                else if (lh == 4) { u32 const v = mode | (2u << 2) | (nl << 4) | (pay << 18); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; hb[3] = v >> 24; }
+                else { u32 const v = mode | (3u << 2) | (nl << 4) | (pay << 22); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; hb[3] = v >> 24; hb[4] = pay >> 10; }
+            } else {                // ZSTD_noCompressLiterals / ZSTD_compressRleLiteralsBlock, zstd/zstd.c:20851-20930
+                if (lh == 1) hb[0] = mode | (nl << 3);
+                else if (lh == 2) { u32 const v = mode | (1u << 2) | (nl << 4); hb[0] = v; hb[1] = v >> 8; }
+                else { u32 const v = mode | (3u << 2) | (nl << 4); hb[0] = v; hb[1] = v >> 8; hb[2] = v >> 16; }
+            }
+            for (u32 k = 0; k < lh; k++) z2_or_byte(ow, o + 3 + k, hb[k]);
+            if (mode == 1) z2_or_byte(ow, o + 3 + lh, lit[S.sub_lit[sb]]);
+            // sequences section header (ZSTD_entropyCompressSeqStore_internal, zstd/zstd.c:25893-25926)
+            u32 q = o + 3 + lh + pay;
+            if (ns < 128) z2_or_byte(ow, q++, ns);
+            else if (ns < 0x7F00) { z2_or_byte(ow, q++, (ns >> 8) + 0x80); z2_or_byte(ow, q++, ns); }
+            else { z2_or_byte(ow, q++, 0xFF); z2_or_byte(ow, q++, ns - 0x7F00); z2_or_byte(ow, q++, (ns - 0x7F00) >> 8); }
+            if (ns) {
+                u32 md = 0;
+                for (int t = 0; t < 3; t++) { u32 const m = S.en.ct[t].mode; md |= (sb == 0 || m != 2 ? m : 3u) << (6 - 2 * t); }
+                z2_or_byte(ow, q++, md);
+                for (int t = 0; t < 3; t++) {
+                    u32 const nb = sb == 0 ? S.en.ct[t].hdr_bytes : (S.en.ct[t].mode == 1 ? 1u : 0u);
+                    for (u32 i = 0; i < nb; i++) z2_or_byte(ow, q++, S.en.ct[t].hdr[i]);
+                }
+            }
+        }
+        // ---- literal payloads
+        for (u32 sb = 0; sb < nsub; sb++) {
+            u32 const mode = S.sub_mode[sb], o_pl = S.sub_off[sb] + 3 + S.sub_lh[sb], l0 = S.sub_lit[sb], nl = S.sub_lit[sb + 1] - l0;
+            if (mode == 0) { for (u32 i = tid; i < nl; i += Z2_NT) z2_or_byte(ow, o_pl + i, lit[l0 + i]); }
+            else if (mode >= 2) {
+                u32 const k0 = S.sub_st0[sb], k1 = S.sub_st0[sb + 1];
+                u32 o = o_pl;
+                if (mode == 2) { for (u32 i = tid; i < tb; i += Z2_NT) z2_or_byte(ow, o + i, S.en.huf_tbl[i]); o += tb; }
+                if (tid == 0) {         // jump table, stream positions, end marks
+                    u32 q = o + (k1 - k0 == 4 ? 6u : 0u);
+                    for (u32 k = k0; k < k1; k++) {
+                        u32 const bits = S.st_pre[k + 1] - S.st_pre[k], bytes = (bits + 1 + 7) / 8;
+                        if (k1 - k0 == 4 && k < k1 - 1) { z2_or_byte(ow, o + 2 * (k - k0), bytes); z2_or_byte(ow, o + 2 * (k - k0) + 1, bytes >> 8); }
+                        S.st_byte[k] = q;
+                        atomicOr(&ow[(q * 8 + bits) >> 5], 1u << ((q * 8 + bits) & 31));
+                        q += bytes;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (u32 rd = 0; rd < 5; rd++) if (rd < lrounds) {
+            u32 const g = rd * Z2_NT + tid;
+            Z2_CHUNK_LOAD(g, k, c, cnt, cw)
+            (void)c;
+            if (g < n_chunks) {
+                // the sub-block of stream k; symbols are written last to first: a chunk's span ends where the bits before it begin
+                u32 sb = 0; while (S.sub_st0[sb + 1] <= k) sb++;
+                if (S.sub_mode[sb] >= 2) {
+                    u32 const tot = S.st_pre[k + 1] - S.st_pre[k];
+                    Z2Bits w; w.init(ow, S.st_byte[k] * 8 + (tot - (cpre[rd] - S.st_pre[k]) - cbits[rd]));
+                    #pragma unroll
+                    for (u32 qq = 0; qq < 32; qq++) { u32 const q = 31 - qq; if (q < cnt) { u32 const sym = (cw[q >> 2] >> ((q & 3) * 8)) & 255u; w.put(S.en.huf.code[sym], S.en.huf.nb[sym]); } }
+                    w.flush();
+                }
+            }
+        }
+        Z2_MARK(4);
+        // ---- sequence streams: every thread packs its own span
+        if (act) {
+            u32 const sb = mysub;
+            u32 const o_st = S.sub_off[sb] + 3 + S.sub_lh[sb] + S.sub_pay[sb] + S.sub_shb[sb];
+            u32 const tot = S.sub_spre[sb + 1] - S.sub_spre[sb];
+            Z2Bits w; w.init(ow, o_st * 8 + (tot - (spre - S.sub_spre[sb]) - sbits));
+            u32 sL = inL, sO = inO, sM = inM;
+            for (u32 i = hi; i-- > lo;) {
+                u64 const r = Z2_SEQ(i);
+                u32 const ll = (u32)r & 0x1FFFFu, mb = (u32)(r >> 17) & 0x1FFFFu, ob = (u32)(r >> 34) & 0x3FFFFu;
+                u32 const lc = (u32)(r >> 52) & 63u, mc = (u32)(r >> 58), oc = ze_hibit(ob);
+                if (i != my_shi - 1) {
+                    if (!rO) { u32 const nb = (sO + (u32)cO.dnb[oc]) >> 16; w.put(sO, nb); sO = cO.state[(sO >> nb) + cO.dfs[oc]]; }
+                    if (!rM) { u32 const nb = (sM + (u32)cM.dnb[mc]) >> 16; w.put(sM, nb); sM = cM.state[(sM >> nb) + cM.dfs[mc]]; }
+                    if (!rL) { u32 const nb = (sL + (u32)cL.dnb[lc]) >> 16; w.put(sL, nb); sL = cL.state[(sL >> nb) + cL.dfs[lc]]; }
+                }
+                w.put(ll, e_LL_bits[lc]); w.put(mb, e_ML_bits[mc]); w.put(ob, oc);
+            }
+            if (tid % tps == 0) {       // flush ML, OF, LL states + end mark
+                u32 const logL = rL ? 0u : cL.log, logO = rO ? 0u : cO.log, logM = rM ? 0u : cM.log;
+                w.put(sM, logM); w.put(sO, logO); w.put(sL, logL); w.put(1, 1);
+            }
+            w.flush();
+        }
+        if (tid == 0) outs[j].csize = body_total;
+        Z2_MARK(5);
         Z2_MARK(6);
         __syncthreads();
     }
 }
+static_assert(sizeof(Z2Shared) <= 227 * 1024, "Z2Shared exceeds the 227 KB a CTA may own");

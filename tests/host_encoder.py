@@ -268,7 +268,7 @@ def build_compress_sim():
     body = dbody + body                                      # the dictionary digest lives with the decoder
     body = re.sub(r"extern __shared__ __align__\(16\) u8 (\w+)\[\];", r"u8* const \1 = simt_dyn_smem;", body)
     text = (LIT_PRELUDE + "#include <cmath>\n#include <vector>\n" + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh")
-            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n#define ZB_SIMT_STEP() __syncwarp()\n" + body + SIM_WRAPPERS)
+            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n#define ZB_SIMT_STEP() __syncwarp()\n#define ZB_SIMT_EMULATION 1\n" + body + SIM_WRAPPERS)
     cpp = os.path.join(BUILD, "zs_host.cpp")
     if not (os.path.exists(SIM_LIB) and os.path.exists(cpp) and open(cpp).read() == text
             and os.path.getmtime(SIM_LIB) >= os.path.getmtime(os.path.join(HERE, "simt.h"))):

@@ -23,7 +23,8 @@ namespace simt {
 struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 static Dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
-struct Thread { ucontext_t ctx; char* stack = nullptr; bool done = false; unsigned warp_gen = 0, cta_gen = 0; };
+struct Thread { ucontext_t ctx; char* stack = nullptr; bool done = false; unsigned warp_gen = 0, cta_gen = 0;
+                unsigned wait = 0, wait_mask = 0, nb_gen = 0; };      // wait 4: named barrier wait_mask (id)      // wait: 0 runnable, 1 CTA barrier, 2 previous collective being read, 3 collective arrivals
 struct Warp {
     unsigned gen = 0, arrived = 0, read = 0;
     unsigned long long val[32];                 // operands of the collective in flight
@@ -31,6 +32,7 @@ struct Warp {
 static std::vector<Thread> g_threads;
 static std::vector<Warp> g_warps;
 static unsigned g_cta_gen = 0, g_cta_arrived = 0;
+static unsigned g_nb_gen[16], g_nb_arrived[16];             // named barriers (bar.sync id, count)
 static int g_cur = 0;
 static ucontext_t g_sched;
 static std::function<void()> g_body;
@@ -51,9 +53,10 @@ static inline unsigned long long collective(unsigned mask, unsigned long long mi
 {
     unsigned const t = tid(), w = t >> 5, lane = t & 31;
     Warp& W = g_warps[w]; Thread& T = g_threads[t];
-    while (W.gen != T.warp_gen) yield();                       // the previous collective is still being read
+    while (W.gen != T.warp_gen) { T.wait = 2; yield(); }       // the previous collective is still being read
     W.val[lane] = mine; W.arrived |= 1u << lane;
-    for (;;) { unsigned const need = mask & alive_mask(w); if ((W.arrived & need) == need) break; yield(); }
+    for (;;) { unsigned const need = mask & alive_mask(w); if ((W.arrived & need) == need) break; T.wait = 3; T.wait_mask = mask; yield(); }
+    T.wait = 0;
     unsigned const part = W.arrived;                          // the participants: everybody who deposited (a lane may
     unsigned long long const r = f(W.val, part, lane);        //   finish the kernel before the others have read its value)
     W.read |= 1u << lane; T.warp_gen++;
@@ -72,6 +75,7 @@ static void launch(unsigned grid, unsigned block, std::function<void()> body)
         g_blockIdx.x = b;
         g_threads.assign(block, Thread()); g_warps.assign((block + 31) / 32, Warp());
         g_cta_gen = 0; g_cta_arrived = 0;
+        for (int q = 0; q < 16; q++) { g_nb_gen[q] = 0; g_nb_arrived[q] = 0; }
         for (unsigned t = 0; t < block; t++) {
             Thread& T = g_threads[t]; T.stack = (char*)malloc(STACK);
             getcontext(&T.ctx); T.ctx.uc_stack.ss_sp = T.stack; T.ctx.uc_stack.ss_size = STACK; T.ctx.uc_link = &g_sched;
@@ -82,8 +86,16 @@ static void launch(unsigned grid, unsigned block, std::function<void()> body)
         while (live) {
             unsigned long long const before = g_progress;
             unsigned done_now = 0;
+            // the CTA barrier is released here as well (threads that exit shrink the quorum), so that waiting fibers need
+            // not be resumed just to look at it
+            if (g_cta_arrived) { unsigned lv = 0; for (auto& q : g_threads) lv += !q.done; if (g_cta_arrived >= lv) { g_cta_arrived = 0; g_cta_gen++; g_progress++; } }
             for (unsigned t = 0; t < block; t++) {
-                if (g_threads[t].done) continue;
+                Thread& Q = g_threads[t];
+                if (Q.done) continue;
+                if (Q.wait == 1 && g_cta_gen == Q.cta_gen) continue;                     // still at the barrier
+                if (Q.wait == 2 && g_warps[t >> 5].gen != Q.warp_gen) continue;
+                if (Q.wait == 4 && g_nb_gen[Q.wait_mask] == Q.nb_gen) continue;
+                if (Q.wait == 3) { Warp& W = g_warps[t >> 5]; unsigned const need = Q.wait_mask & alive_mask(t >> 5); if ((W.arrived & need) != need) continue; }
                 g_cur = (int)t; g_threadIdx.x = t;
                 swapcontext(&g_sched, &g_threads[t].ctx);
                 if (g_threads[t].done) done_now++;
@@ -123,9 +135,19 @@ static inline void __syncthreads()
     for (;;) {
         if (g_cta_gen != my) break;
         if (g_cta_arrived >= live()) { g_cta_arrived = 0; g_cta_gen++; g_progress++; break; }
-        yield();
+        T.wait = 1; yield();
     }
-    T.cta_gen = my + 1;
+    T.wait = 0; T.cta_gen = my + 1;
+}
+static inline void simt_named_bar_sync(unsigned id, unsigned count)
+{
+    using namespace simt;
+    Thread& T = g_threads[tid()];
+    unsigned const my = g_nb_gen[id];
+    if (++g_nb_arrived[id] >= count) { g_nb_arrived[id] = 0; g_nb_gen[id]++; g_progress++; return; }
+    T.wait = 4; T.wait_mask = id; T.nb_gen = my;
+    while (g_nb_gen[id] == my) yield();
+    T.wait = 0;
 }
 static inline int __syncthreads_or(int p)
 {
