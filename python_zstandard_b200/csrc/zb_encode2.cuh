@@ -27,7 +27,7 @@
 #define Z2_RPP      29                    // regions per pass
 #define Z2_Q        8192                  // positions per pass
 #define Z2_MAXU     512
-#define Z2_RMAX     76                    // records per region (at most 72 matches start in one)
+#define Z2_RMAX     76                    // records per region (at most 72 matches start in one: they are >= 4 bytes and do not overlap)
 #define Z2_FARLOG   14
 #define Z2_MAXSEQ   33024
 #define Z2_STAGE    57344                 // bytes of staging / literal buffer in shared memory
@@ -53,6 +53,7 @@ struct Z2Ent {
     u8 huf_tbl[160]; u8 seq_hdr_buf[256];
     u32 hist[8][256];
     u32 hLL[36], hOF[32], hML[56];
+    short nrm[3][64]; u16 cum[3][64];
 };
 struct Z2Shared {
     __align__(16) u8 in[ZE_BLOCK + 48];   // the block, at in[skew ..]; after the literals section: the sequence records
@@ -159,6 +160,152 @@ __device__ __forceinline__ u32 z2_fse_init(const ZeCTable& ct, u32 s)      // FS
     return ct.state[(v >> nbo) + ct.dfs[s]];
 }
 
+
+// ---- FSE table of one symbol stream, built by a whole warp (lane l looks after symbols l and l + 32).  Same decisions as
+// ze_make_table (mode by cost, normalisation, NCount header) except that the costs are summed in another order.
+// nrm: 64 shorts, cum: 64 u16 of shared memory.
+__device__ static void z2_build_ctable_warp(ZeCTable& ct, const short* nrm, u32 max_sym, u32 log, u8* tmp_sym, u16* cum, u32 lane)
+{
+    // restates FSE_buildCTable_wksp (zstd/zstd.c:16005-16155) for tables without "less than one" cells
+    u32 const size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    u32 const n0 = lane <= max_sym ? (u32)nrm[lane] : 0u, n1 = lane + 32 <= max_sym ? (u32)nrm[lane + 32] : 0u;
+    u32 x0 = n0, x1 = n1;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 const y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d); if (lane >= (u32)d) { x0 += y0; x1 += y1; } }
+    u32 const tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+    u32 const pre0 = x0 - n0, pre1 = tot0 + x1 - n1;                  // cells in front of my symbols
+    cum[lane] = (u16)pre0; cum[lane + 32] = (u16)pre1;
+    __syncwarp();
+    for (u32 s = 0; s <= max_sym; s++) {                              // spread: cell k of the cumulative order sits at (k * step) & mask
+        u32 const c0 = cum[s], n = (u32)nrm[s];
+        for (u32 i = lane; i < n; i += 32) tmp_sym[((c0 + i) * step) & mask] = (u8)s;
+    }
+    __syncwarp();
+    for (u32 u0 = 0; u0 < size; u0 += 32) {                           // every symbol's cells in ascending table order
+        u32 const u = u0 + lane, sy = tmp_sym[u];
+        u32 const peers = __match_any_sync(0xFFFFFFFFu, sy);
+        u32 const rank = (u32)__popc(peers & ((1u << lane) - 1u));
+        u32 const base = cum[sy];
+        ct.state[base + rank] = (u16)(size + u);
+        __syncwarp();
+        if (rank == 0) cum[sy] = (u16)(base + (u32)__popc(peers));
+        __syncwarp();
+    }
+    #pragma unroll
+    for (u32 h = 0; h < 2; h++) {
+        u32 const sy = lane + 32 * h, c = h ? n1 : n0, pre = h ? pre1 : pre0;
+        if (sy < 56) {
+            int dnb = 0, dfs = 0;
+            if (sy <= max_sym) {
+                if (c == 0) { dnb = (int)(((log + 1) << 16) - size); dfs = 0; }
+                else if (c == 1) { dnb = (int)((log << 16) - size); dfs = (int)pre - 1; }
+                else { u32 const maxBitsOut = log - ze_hibit(c - 1), minStatePlus = c << maxBitsOut; dnb = (int)((maxBitsOut << 16) - minStatePlus); dfs = (int)pre - (int)c; }
+            }
+            ct.dnb[sy] = dnb; ct.dfs[sy] = dfs;
+        }
+    }
+    if (lane == 0) ct.log = log;
+    __syncwarp();
+}
+
+__device__ static float z2_cost_warp(u32 c0, u32 c1, int n0, int n1, u32 log, bool& bad)
+{
+    float bits = 0.f; bool b = false;
+    if (c0) { int n = n0 == -1 ? 1 : n0; if (n <= 0) b = true; else bits += (float)c0 * ((float)log - __log2f((float)n)); }
+    if (c1) { int n = n1 == -1 ? 1 : n1; if (n <= 0) b = true; else bits += (float)c1 * ((float)log - __log2f((float)n)); }
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+    bad = __any_sync(0xFFFFFFFFu, b);
+    return bits;
+}
+
+__device__ static void z2_make_table_warp(ZeCTable& ct, const u32* count, u32 kind_max, u32 nseq, u32 max_log, u32 def_log,
+                                          const short* defnorm, u32 def_max, u8* tmp_sym, short* nrm, u16* cum, u32 lane)
+{
+    u32 const c0 = lane <= kind_max ? count[lane] : 0u, c1 = lane + 32 <= kind_max ? count[lane + 32] : 0u;
+    u32 present = (c0 ? 1u : 0u) + (c1 ? 1u : 0u), most = max(c0, c1), max_sym = c1 ? lane + 32 : (c0 ? lane : 0u);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        present += __shfl_xor_sync(0xFFFFFFFFu, present, d);
+        most = max(most, __shfl_xor_sync(0xFFFFFFFFu, most, d)); max_sym = max(max_sym, __shfl_xor_sync(0xFFFFFFFFu, max_sym, d));
+    }
+    if (most == nseq && nseq > 2) {                       // one symbol only: RLE (ZSTD_selectEncodingType, zstd/zstd.c:21262)
+        if (lane < 28) { ct.dnb[lane] = 0; ct.dfs[lane] = 0; ct.dnb[lane + 28] = 0; ct.dfs[lane + 28] = 0; }
+        if (lane == 0) { ct.mode = 1; ct.rle_sym = max_sym; ct.hdr[0] = (u8)max_sym; ct.hdr_bytes = 1; ct.log = 0; ct.state[0] = 1; }
+        __syncwarp();
+        return;
+    }
+    // predefined table usable?  every present symbol must have a cell in it
+    int const dn0 = lane <= def_max ? (int)defnorm[lane] : 0, dn1 = lane + 32 <= def_max ? (int)defnorm[lane + 32] : 0;
+    bool const def_ok = !__any_sync(0xFFFFFFFFu, (c0 && dn0 == 0) || (c1 && dn1 == 0));
+    u32 cost_def = 0xFFFFFFFFu;
+    if (def_ok) { bool bad; float const f = z2_cost_warp(c0, c1, dn0, dn1, def_log, bad); if (!bad) cost_def = (u32)(f + 0.5f); }
+    // compressed table: log as FSE_optimalTableLog (zstd/zstd.c:16308)
+    u32 log = max_log;
+    if (nseq > 1) {
+        u32 const maxBitsSrc = ze_hibit(nseq - 1) >= 2 ? ze_hibit(nseq - 1) - 2 : 0;
+        u32 minBits = ze_hibit(nseq) + 1; u32 const mb2 = ze_hibit(max_sym ? max_sym : 1) + 2; if (mb2 < minBits) minBits = mb2;
+        if (maxBitsSrc < log) log = maxBitsSrc;
+        if (log < minBits) log = minBits;
+        if (log < 5) log = 5;
+        if (log > max_log) log = max_log;
+    }
+    u32 cost_cmp = 0xFFFFFFFFu, nc_bytes = 0;
+    bool ok = nseq >= 32 && (1u << log) >= present;
+    if (ok) {        // normalise to 2^log, every present symbol >= 1, remainder to the most frequent symbol (ze_normalize)
+        u32 const size = 1u << log;
+        u64 const scale = ((u64)size << 20) / nseq;
+        u32 p0 = 0, p1 = 0;
+        if (c0) { p0 = (u32)(((u64)c0 * scale + (1u << 19)) >> 20); if (!p0) p0 = 1; }
+        if (c1) { p1 = (u32)(((u64)c1 * scale + (1u << 19)) >> 20); if (!p1) p1 = 1; }
+        u32 used = p0 + p1, key = max(c0 ? (c0 << 6) | (63u - lane) : 0u, c1 ? (c1 << 6) | (31u - lane) : 0u);
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { used += __shfl_xor_sync(0xFFFFFFFFu, used, d); key = max(key, __shfl_xor_sync(0xFFFFFFFFu, key, d)); }
+        u32 const largest = 63u - (key & 63u);
+        int const diff = (int)size - (int)used;
+        int const nl = (int)__shfl_sync(0xFFFFFFFFu, largest < 32 ? p0 : p1, (int)(largest & 31u));
+        if (nl + diff < 1) {                              // rare: too many rare symbols rounded up -- the serial routine sorts it out
+            u32 r = 0;
+            if (lane == 0) r = ze_normalize(nrm, count, max_sym, nseq, log) ? 1u : 0u;
+            ok = __shfl_sync(0xFFFFFFFFu, r, 0) != 0;
+        } else {
+            if (largest == lane) p0 = (u32)((int)p0 + diff);
+            if (largest == lane + 32) p1 = (u32)((int)p1 + diff);
+            nrm[lane] = (short)p0; nrm[lane + 32] = (short)p1;
+        }
+        __syncwarp();
+        if (ok) {
+            u32 nb = 0;
+            if (lane == 0) nb = ze_write_ncount(ct.hdr, nrm, max_sym, log);
+            nc_bytes = __shfl_sync(0xFFFFFFFFu, nb, 0);
+            bool bad; float const f = z2_cost_warp(c0, c1, (int)nrm[lane], (int)nrm[lane + 32], log, bad);
+            if (!bad) cost_cmp = (u32)(f + 0.5f) + nc_bytes * 8;
+        }
+    }
+    if (ok && cost_cmp < cost_def) {
+        z2_build_ctable_warp(ct, nrm, max_sym, log, tmp_sym, cum, lane);
+        if (lane == 0) { ct.mode = 2; ct.hdr_bytes = nc_bytes; }
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) {                                      // predefined table, or a flat one: the serial builders
+        short norm[56];
+        if (!def_ok) {     // neither fits (tiny block with a symbol outside the predefined alphabet): flat table over present symbols
+            u32 lg = 5; while ((1u << lg) < present) lg++;
+            u32 k = 0, per = (1u << lg) / present, extra = (1u << lg) - per * present;
+            for (u32 s = 0; s <= max_sym; s++) { norm[s] = count[s] ? (short)(per + (k < extra ? 1 : 0)) : 0; if (count[s]) k++; }
+            ct.mode = 2; ct.hdr_bytes = ze_write_ncount(ct.hdr, norm, max_sym, lg); ze_build_ctable(ct, norm, max_sym, lg, tmp_sym);
+            for (u32 s = max_sym + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+        } else {
+            ct.mode = 0; ct.hdr_bytes = 0;
+            for (u32 s = 0; s <= def_max; s++) norm[s] = defnorm[s];
+            ze_build_ctable(ct, norm, def_max, def_log, tmp_sym);
+            for (u32 s = def_max + 1; s < 56; s++) { ct.dnb[s] = 0; ct.dfs[s] = 0; }
+        }
+    }
+    __syncwarp();
+}
+
 // Huffman code lengths, warp-cooperative front end: rank the present symbols by (count, symbol) -- every lane ranks
 // eight of them against all 256 -- then lane 0 runs the serial tree construction of ze_huf_from_sorted
 __device__ static bool z2_huf_build(ZeHuf& H, const u32* count, u32* wk, u32 lane)
@@ -224,7 +371,7 @@ __global__ void __launch_bounds__(Z2_NT, 1)
 zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs, u32 n_jobs, Z2Scratch* __restrict__ scratch,
                  u8* __restrict__ slots, u64 slot_bytes, ZeBlockOut* __restrict__ outs, u32* __restrict__ work_counter, ZeUpload up)
 {
-    extern __shared__ __align__(16) u8 z2_smem_raw[];
+    u8* const z2_smem_raw = simt_dyn_smem;
     Z2Shared& S = *(Z2Shared*)z2_smem_raw;
     Z2Scratch& G = scratch[blockIdx.x];
     u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,7 +529,7 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
                 // ---- V + P: warp w owns the w-th region of Z2_REG positions of the pass and walks it in steps of 32: every lane
                 // verifies its position's candidate (common prefix 4..15, 15 = "15 or more"), then the warp takes the matches
                 // of the step greedily from the left (one-step lazy), extending long ones 256 bytes per vote
-                if (tid == 32) Z2_T0();
+
                 const u16* const hd = S.mf.hd[ps & 1];
                 u32 const carry = S.carry;                                    // end of the longest match of the earlier passes (buffer offset)
                 u32 const reg = warp - 1;
@@ -412,39 +559,59 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
                         Z2_VERIFY(pos + 32, m_nx, d_nx)
                         u32 mn = __shfl_down_sync(0xFFFFFFFFu, m, 1); if (lane == 31) mn = 0;
                         bool const take = m >= 4 && !(m < 15 && mn > m + 1);                 // one-step lazy
-                        for (;;) {
-                            u32 const mask = __ballot_sync(0xFFFFFFFFu, take && pos >= cover);
-                            if (!mask) break;
-                            u32 const L = (u32)__ffs((int)mask) - 1;
-                            u32 const p = b + L, mL = __shfl_sync(0xFFFFFFFFu, m, (int)L), dL = __shfl_sync(0xFFFFFFFFu, d, (int)L);
-                            // backwards, down to the end of the previous match (all lanes compute the same); loads first
-                            bool const bk = p > cover && p >= dL + 4 + skew;
-                            u32 const xb = bk ? z2_ld32(in, p - 4) ^ z2_ld32(in, p - 4 - dL) : 1u << 31;
-                            u32 end = p + mL;
-                            if (mL == 15) {                     // bytes [p, p + 15) match: compare on from p + 8, eight bytes per lane
-                                u32 a = p + 8;
+                        // selection: every match knows the first one that starts at or after its end (one ballot, no loop); the
+                        // warp then hops from match to match.  Only "15 or more" matches are extended on the way.
+                        u32 const takemask = __ballot_sync(0xFFFFFFFFu, take);
+                        u32 my_end = pos + m;
+                        #define Z2_NEXT_FROM(e_) ((e_) >= b + 32 ? 32u : min(32u, (u32)__ffs((int)(takemask & (0xFFFFFFFFu << ((e_) > b ? (e_) - b : 0u)))) - 1u))   /* 32 = none */
+                        u32 my_hop = take ? (Z2_NEXT_FROM(my_end) | (m == 15 ? 0x100u : 0u)) : 0u;      // bit 8: to be extended
+                        u32 selmask = 0, lastL = 0;
+                        u32 L = Z2_NEXT_FROM(cover);
+                        while (L < 32) {
+                            selmask |= 1u << L; lastL = L;
+                            u32 const hop = __shfl_sync(0xFFFFFFFFu, my_hop, (int)L);
+                            if (hop & 0x100u) {                 // bytes [p, p + 15) match: compare on from p + 8, eight bytes per lane
+                                u32 const dL = __shfl_sync(0xFFFFFFFFu, d, (int)L);
+                                u32 a = b + L + 8, endL;
                                 for (;;) {
                                     u32 const my = a + 8 * lane;
                                     u32 cm = 8;                 // bytes of my window that match
                                     if (my + 8 <= e_end) { u64 const x = z2_ld64(in, my) ^ z2_ld64(in, my - dL); if (x) cm = ze_common8(0, x); }
                                     else { cm = 0; while (my + cm < e_end && in[my + cm] == in[my + cm - dL]) cm++; }
                                     u32 const stop = __ballot_sync(0xFFFFFFFFu, cm < 8);
-                                    if (stop) { u32 const fl = (u32)__ffs((int)stop) - 1; end = a + 8 * fl + __shfl_sync(0xFFFFFFFFu, cm, (int)fl); break; }
+                                    if (stop) { u32 const fl = (u32)__ffs((int)stop) - 1; endL = a + 8 * fl + __shfl_sync(0xFFFFFFFFu, cm, (int)fl); break; }
                                     a += 256;
                                 }
-                            }
-                            u32 start = p;
-                            if (bk) { u32 const same = xb ? ((u32)__clz((int)xb) >> 3) : 4u; start -= min(same, start - cover); }
-                            else while (start > cover && start > dL + skew && in[start - 1] == in[start - 1 - dL]) start--;
-                            if (cnt >= Z2_RMAX - 1) { cover = r1; break; }
-                            if (lane == 0) rec[cnt] = (u64)(start - skew) | ((u64)(end - start) << 17) | ((u64)dL << 35);
-                            cnt++; cover = end; endm = end - skew;
+                                if (lane == L) my_end = endL;
+                                L = Z2_NEXT_FROM(endL);
+                            } else L = hop & 0xFFu;
                         }
+                        u32 my_prev = cover;                    // the end of the match selected before mine
+                        if (selmask) {
+                            u32 const below = selmask & ((1u << lane) - 1u);
+                            u32 const pe = __shfl_sync(0xFFFFFFFFu, my_end, below ? 31 - __clz((int)below) : 0);
+                            if (below) my_prev = pe;
+                            cover = __shfl_sync(0xFFFFFFFFu, my_end, (int)lastL);
+                        }
+                        // ... then every selected lane finishes its own match: up to four bytes backwards (down to the end of
+                        // the match before it), record
+                        if ((selmask >> lane) & 1u) {
+                            u32 start = pos;
+                            if (start > my_prev) {
+                                if (start >= d + 4 + skew) {
+                                    u32 const x = z2_ld32(in, start - 4) ^ z2_ld32(in, start - 4 - d);
+                                    u32 const same = x ? ((u32)__clz((int)x) >> 3) : 4u;
+                                    start -= min(same, start - my_prev);
+                                } else while (start > my_prev && start > d + skew && in[start - 1] == in[start - 1 - d]) start--;
+                            }
+                            rec[cnt + (u32)__popc(selmask & ((1u << lane) - 1u))] = (u64)(start - skew) | ((u64)(my_end - start) << 17) | ((u64)d << 35);
+                        }
+                        if (selmask) { cnt += (u32)__popc(selmask); endm = cover - skew; }
                         m = pos + 32 >= cover ? m_nx : 0u; d = d_nx;
                     }
                     if (lane == 0) { S.x0[unit] = endm; S.x1[unit] = cnt; if (endm) atomicMax(&S.carry, endm + skew); }
                 }
-                if (tid == 32) Z2_T1(13);
+
             }
             __syncthreads();
             Z2_MARK(8);
@@ -535,31 +702,6 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
         __syncthreads();
         Z2_MARK(2);
 
-        // ================================================================= entropy tables: four warps
-        Z2_T0();
-        if (nseq) {
-            if (tid == 0)  ze_make_table(S.en.ct[0], S.en.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.en.tmp_sym[0]);
-            if (tid == 32) ze_make_table(S.en.ct[1], S.en.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.en.tmp_sym[1]);
-            if (tid == 64) ze_make_table(S.en.ct[2], S.en.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.en.tmp_sym[2]);
-        }
-        if (warp == 3) {
-            Z2_T0();
-            u32 mode = 0, tb = 0;
-            u32 most = 0; for (u32 s = lane; s < 256; s += 32) most = max(most, S.en.hist[0][s]);
-            #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) most = max(most, __shfl_xor_sync(0xFFFFFFFFu, most, d));
-            if (nlit >= 8 && most == nlit) mode = 1;                                   // RLE literals
-            else if (nlit >= 64) {                                                     // ZSTD_minLiteralsToCompress, zstd/zstd.c:20918
-                bool const ok = z2_huf_build(S.en.huf, S.en.hist[0], S.en.wk, lane);
-                if (lane == 0 && ok) { tb = ze_huf_write_table(S.en.huf_tbl, S.en.huf, S.en.ct[3], S.en.tmp_sym[3]); if (tb) mode = 2; }
-            }
-            if (lane == 0) { S.lit_mode = mode; S.huf_tbl_bytes = tb; }
-            if (lane == 0) Z2_T1(15);
-        }
-        if (tid == 0) Z2_T1(7);
-        __syncthreads();
-        Z2_MARK(3);
-
         // ================================================================= sub-blocks
         // The chunk's sequences are cut into up to Z2_MAXSUB runs of equal length and every run becomes a zstd block of its
         // own (its literals are a contiguous range of the gathered literals).  The FSE state chains -- three strictly serial
@@ -586,6 +728,73 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
             if (tid == 0) { S.sub_lit[nsub] = nlit; S.sub_seq[nsub] = nseq; if (!nseq) { S.sub_lit[0] = 0; S.sub_seq[0] = 0; } }
         }
         __syncthreads();
+        // ================================================================= entropy tables and FSE state chains, side by side
+        //   warps 0-2: the LL / OF / ML tables (one lane each), then warp 0 runs the state chains
+        //   warp 3   : the Huffman code of the literals and its description
+        Z2_T0();
+        if (warp < 3) {
+            if (nseq) {
+                if (warp == 0) z2_make_table_warp(S.en.ct[0], S.en.hLL, 35, nseq, 9, 6, e_LL_defnorm, 35, S.en.tmp_sym[0], S.en.nrm[0], S.en.cum[0], lane);
+                if (warp == 1) z2_make_table_warp(S.en.ct[1], S.en.hOF, 31, nseq, 8, 5, e_OF_defnorm, 28, S.en.tmp_sym[1], S.en.nrm[1], S.en.cum[1], lane);
+                if (warp == 2) z2_make_table_warp(S.en.ct[2], S.en.hML, 52, nseq, 9, 6, e_ML_defnorm, 52, S.en.tmp_sym[2], S.en.nrm[2], S.en.cum[2], lane);
+            }
+            if (tid == 0) Z2_T1(7);
+            Z2_BAR_SYNC(2, 96);
+            if (tid == 0) Z2_T0();
+            // ---- FSE state chains: warp 0, lane 3 * sub-block + table (0 LL, 1 OF, 2 ML) walks its sub-block from the last
+            // sequence to the first and leaves the state on entry of every thread's range in x0 / x1 / x2 (the ranges are then
+            // re-run by their threads, all at once, to count and to write the bits)
+            if (warp == 0 && nseq) {
+                u32 const sb = lane / 3, t = lane - 3 * sb;
+                if (sb < nsub) {
+                    ZeCTable const& ct = S.en.ct[t];
+                    if (ct.mode == 1) S.fin[sb][t] = 0;            // RLE: no state bits
+                    else {
+                        u32* const xb = t == 0 ? S.x0 : t == 1 ? S.x1 : S.x2;
+                        u32 const s_lo = S.sub_seq[sb], s_hi = S.sub_seq[sb + 1];
+                        u32 const sh = t == 0 ? 52u : 58u;
+                        u32 const m_of = t == 1 ? 0xFFFFFFFFu : 0u;           // branch-free selection: the three lanes of a sub-block stay converged
+                        #define Z2_CODE_OF(r_) ((ze_hibit(((u32)((r_) >> 34) & 0x3FFFFu) | 1u) & m_of) | ((u32)((r_) >> sh) & 63u & ~m_of))
+                        u32 i = s_hi - 1;
+                        u32 q = i / K, r = i - q * K;
+                        u32 state = z2_fse_init(ct, Z2_CODE_OF(Z2_SEQ(i)));
+                        int dnb = 0, dfs = 0;
+                        if (i > s_lo) { u32 const sym = Z2_CODE_OF(Z2_SEQ(i - 1)); dnb = ct.dnb[sym]; dfs = ct.dfs[sym]; }
+                        // two sequences ahead: the record; one ahead: its symbol's deltas; now: the state transition
+                        #define Z2_CHAIN_LOOP(SEQ_) { \
+                            u64 rr1_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
+                            while (i > s_lo) { \
+                                i--; if (r == 0) { r = K - 1; q--; } else r--; \
+                                u64 const rr2_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
+                                u32 const nsym_ = Z2_CODE_OF(rr1_); \
+                                int const ndnb_ = ct.dnb[nsym_], ndfs_ = ct.dfs[nsym_]; \
+                                if (r == K - 1) xb[q] = state; \
+                                u32 const nb_ = (state + (u32)dnb) >> 16; \
+                                state = ct.state[(state >> nb_) + dfs]; \
+                                dnb = ndnb_; dfs = ndfs_; rr1_ = rr2_; \
+                            } }
+                        #define Z2_SEQ_S(i_) sq[i_]
+                        if (s_hi <= Z2_SEQ_SMEM) Z2_CHAIN_LOOP(Z2_SEQ_S) else Z2_CHAIN_LOOP(Z2_SEQ)
+                        S.fin[sb][t] = state;
+                    }
+                }
+            }
+            if (tid == 0) Z2_T1(13);
+        } else if (warp == 3) {
+            u32 mode = 0, tb = 0;
+            u32 most = 0; for (u32 s = lane; s < 256; s += 32) most = max(most, S.en.hist[0][s]);
+            #pragma unroll
+            for (int d = 16; d > 0; d >>= 1) most = max(most, __shfl_xor_sync(0xFFFFFFFFu, most, d));
+            if (nlit >= 8 && most == nlit) mode = 1;                                   // RLE literals
+            else if (nlit >= 64) {                                                     // ZSTD_minLiteralsToCompress, zstd/zstd.c:20918
+                bool const ok = z2_huf_build(S.en.huf, S.en.hist[0], S.en.wk, lane);
+                if (lane == 0 && ok) { tb = ze_huf_write_table(S.en.huf_tbl, S.en.huf, S.en.ct[3], S.en.tmp_sym[3]); if (tb) mode = 2; }
+            }
+            if (lane == 0) { S.lit_mode = mode; S.huf_tbl_bytes = tb; }
+            if (lane == 0) Z2_T1(15);
+        }
+        __syncthreads();
+        Z2_MARK(3);
         u32 const chunk_lit_mode = S.lit_mode, tb = S.huf_tbl_bytes;
         // ---- Huffman streams: every sub-block with >= 64 literals gets one (< 256 literals) or four streams
         if (tid == 0) {
@@ -635,45 +844,6 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
         }
         __syncthreads();
         Z2_MARK(11);
-        // ---- FSE state chains: warp 0, lane 3 * sub-block + table (0 LL, 1 OF, 2 ML) walks its sub-block from the last
-        // sequence to the first and leaves the state on entry of every thread's range in x0 / x1 / x2 (the ranges are then
-        // re-run by their threads, all at once, to count and to write the bits)
-        if (warp == 0 && nseq) {
-            u32 const sb = lane / 3, t = lane - 3 * sb;
-            if (sb < nsub) {
-                ZeCTable const& ct = S.en.ct[t];
-                if (ct.mode == 1) S.fin[sb][t] = 0;            // RLE: no state bits
-                else {
-                    u32* const xb = t == 0 ? S.x0 : t == 1 ? S.x1 : S.x2;
-                    u32 const s_lo = S.sub_seq[sb], s_hi = S.sub_seq[sb + 1];
-                    u32 const sh = t == 0 ? 52u : 58u;
-                    u32 const m_of = t == 1 ? 0xFFFFFFFFu : 0u;           // branch-free selection: the three lanes of a sub-block stay converged
-                    #define Z2_CODE_OF(r_) ((ze_hibit(((u32)((r_) >> 34) & 0x3FFFFu) | 1u) & m_of) | ((u32)((r_) >> sh) & 63u & ~m_of))
-                    u32 i = s_hi - 1;
-                    u32 q = i / K, r = i - q * K;
-                    u32 state = z2_fse_init(ct, Z2_CODE_OF(Z2_SEQ(i)));
-                    int dnb = 0, dfs = 0;
-                    if (i > s_lo) { u32 const sym = Z2_CODE_OF(Z2_SEQ(i - 1)); dnb = ct.dnb[sym]; dfs = ct.dfs[sym]; }
-                    // two sequences ahead: the record; one ahead: its symbol's deltas; now: the state transition
-                    #define Z2_CHAIN_LOOP(SEQ_) { \
-                        u64 rr1_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
-                        while (i > s_lo) { \
-                            i--; if (r == 0) { r = K - 1; q--; } else r--; \
-                            u64 const rr2_ = i > s_lo + 1 ? SEQ_(i - 2) : 0ull; \
-                            u32 const nsym_ = Z2_CODE_OF(rr1_); \
-                            int const ndnb_ = ct.dnb[nsym_], ndfs_ = ct.dfs[nsym_]; \
-                            if (r == K - 1) xb[q] = state; \
-                            u32 const nb_ = (state + (u32)dnb) >> 16; \
-                            state = ct.state[(state >> nb_) + dfs]; \
-                            dnb = ndnb_; dfs = ndfs_; rr1_ = rr2_; \
-                        } }
-                    #define Z2_SEQ_S(i_) sq[i_]
-                    if (s_hi <= Z2_SEQ_SMEM) Z2_CHAIN_LOOP(Z2_SEQ_S) else Z2_CHAIN_LOOP(Z2_SEQ)
-                    S.fin[sb][t] = state;
-                }
-            }
-        }
-        __syncthreads();
         Z2_MARK(10);
         // ---- every thread re-runs its range from the recorded states: bit count, then (below) the bits themselves
         ZeCTable const& cL = S.en.ct[0]; ZeCTable const& cO = S.en.ct[1]; ZeCTable const& cM = S.en.ct[2];
@@ -846,3 +1016,4 @@ zb_compress_smem(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jobs
     }
 }
 static_assert(sizeof(Z2Shared) <= 227 * 1024, "Z2Shared exceeds the 227 KB a CTA may own");
+
