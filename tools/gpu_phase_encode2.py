@@ -25,9 +25,9 @@ step(); L.zb_encode2_phase_read(buf, 1)
 ctx.profile(True); csz = step(); pr = ctx.profile_read(); ctx.profile(False)
 print({k: round(v[0], 3) for k, v in pr.items()}, "ratio %.3f" % (len(blob) / csz))
 L.zb_encode2_phase_read(buf, 1)
-names = {0: "load/trivial", 1: "mf prologue H0+L0", 7: "  (LL table)", 13: "  (mf V+P, warp 1)", 14: "  (unused)", 15: "  (Huffman)", 8: "mf passes", 9: "stitch", 2: "gather+hist", 3: "tables", 11: "sub-blocks+lit count",
-         10: "seq chains", 12: "seq bits+layout", 4: "headers+lit pack", 5: "seq pack", 6: "end"}
-tot = sum(buf[i] for i in range(13) if i != 7)
-for i in (0, 1, 8, 9, 2, 3, 7, 13, 14, 15, 11, 10, 12, 4, 5, 6):
+names = {0: "load/trivial", 1: "mf prologue H0+L0", 8: "mf passes", 9: "stitch", 2: "gather+hist", 3: "tables+chains+Huffman", 7: "  (FSE tables, w0)", 13: "  (chains, w0)", 15: "  (Huffman, w3)",
+         11: "sub-blocks+lit count", 10: "-", 12: "seq bits+layout", 4: "headers+lit pack", 5: "seq pack", 6: "end"}
+tot = sum(buf[i] for i in (0, 1, 8, 9, 2, 3, 11, 10, 12, 4, 5, 6))
+for i in (0, 1, 8, 9, 2, 3, 7, 13, 15, 11, 12, 4, 5, 6):
     print("%-22s %10.0f cycles/block  %5.1f%%" % (names[i], buf[i] / n, 100.0 * buf[i] / max(tot, 1)))
 print("total cycles/block %.0f (%s, %d x %d)" % (tot / n, "mix" if mix else "text", n, size))
