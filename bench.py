@@ -37,6 +37,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def host_threads():
+    """Threads the CPU arms may really use: the scheduler affinity of this process, cut by the cgroup CPU quota.
+    os.cpu_count() is the machine's count and says nothing about the lease."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    use = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return use, {"os_cpu_count": os.cpu_count(), "sched_getaffinity": aff, "cgroup_cpu_quota": quota, "threads_used": use}
+
+
 # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to fd 1 from C, so
 # fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original stdout.
 _REAL_STDOUT = os.dup(1)
@@ -114,7 +134,7 @@ class ClockSampler:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads, host_info = host_threads()
     ref, blob, cblob, coff, clens = make_batch(N_FRAMES, threads)
     sizes = np.full(N_FRAMES, FRAME, dtype=np.uint64)
     for _ in range(args.warmup):
@@ -129,11 +149,77 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "multi_decompress_to_buffer: %d x 4 KiB independent level-3 frames (S-text), host CPU" % N_FRAMES,
-                   "threads": threads},
+                   "threads": threads, "host": host_info},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "reference",
                          "sample": "the full %d-frame batch per step (oracle/_ref libzstd 1.5.7 -O3, reference batch orchestration)" % N_FRAMES},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def run_dictionary_arm(zstd, ref, cores, device):
+    """BASELINE.json configs[3]: 1,048,576 x ~1 KiB JSON-like records with a trained dictionary, compress + decompress
+    through the public API (host buffers), the unmodified reference on the host cores beside it.  The records are
+    16384 distinct ones repeated (every record is an independent frame, so repeats do not help either codec)."""
+    n_unique, n = 16384, int(os.environ.get("ZB_BENCH_DICT_RECORDS", "1048576"))
+    recs = corpus.json_records(n_unique + 2000)
+    dct = ref.train_dictionary(112640, recs[:2000])
+    recs = recs[2000:]
+    one = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    ln1 = np.array([len(r) for r in recs], dtype=np.uint64)
+    reps = max(1, n // n_unique)
+    n = reps * n_unique
+    blob = np.tile(one, reps)
+    ln = np.tile(ln1, reps)
+    off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.uint64)
+    U = int(ln.sum())
+    rc, rl = ref.batch(True, blob, off, ln, level=3, threads=cores, dict_data=dct)
+    rl = rl.astype(np.uint64)
+    ro = np.concatenate([[0], np.cumsum(rl)[:-1]]).astype(np.uint64)
+    tc = td = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter(); ref.batch(True, blob, off, ln, level=3, threads=cores, dict_data=dct, gather=False); tc = min(tc, time.perf_counter() - t0)
+        t0 = time.perf_counter(); ref.batch(False, rc, ro, rl, dst_len=ln, threads=cores, dict_data=dct, gather=False); td = min(td, time.perf_counter() - t0)
+    d = zstd.ZstdCompressionDict(dct)
+    pin = zstd.PinnedBuffer(len(blob), device=device); np.frombuffer(pin, dtype=np.uint8)[:] = blob
+    bws = zstd.BufferWithSegments(pin, np.stack([off, ln], axis=1).astype(np.uint64).tobytes())
+    cctx = zstd.ZstdCompressor(level=3, dict_data=d)
+    dctx = zstd.ZstdDecompressor(dict_data=d)
+    res = cctx.multi_compress_to_buffer(bws)
+    csz = res.size()
+    back = dctx.multi_decompress_to_buffer(res)          # our frames regenerate (sampled) ...
+    step = max(1, n // 4099)
+    ok = all(back[i].tobytes() == recs[i % n_unique] for i in range(0, n, step))
+    del back
+    # ... and the reference decoder regenerates them all
+    datas, segs, base = [], [], 0
+    for b_ in (res._buffers if hasattr(res, "_buffers") else [res]):
+        d_ = np.frombuffer(b_.tobytes(), dtype=np.uint8)
+        g_ = np.frombuffer(b_._segments, dtype=np.uint64).reshape(-1, 2).copy()
+        g_[:, 0] += np.uint64(base)
+        datas.append(d_); segs.append(g_); base += len(d_)
+    seg = np.concatenate(segs)
+    rb, _ = ref.batch(False, np.concatenate(datas), np.ascontiguousarray(seg[:, 0]), np.ascontiguousarray(seg[:, 1]),
+                      dst_len=ln, threads=cores, dict_data=dct)
+    ok_ref = bool(np.array_equal(rb, blob))
+    del rb
+    tg = tgd = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter(); r2 = cctx.multi_compress_to_buffer(bws); _ = r2[n - 1].tobytes(); tg = min(tg, time.perf_counter() - t0); del r2
+    pin2 = zstd.PinnedBuffer(len(rc), device=device); np.frombuffer(pin2, dtype=np.uint8)[:] = rc
+    fbws = zstd.BufferWithSegments(pin2, np.stack([ro, rl], axis=1).astype(np.uint64).tobytes())
+    o2 = dctx.multi_decompress_to_buffer(fbws); ok_dec = o2[n - 1].tobytes() == recs[(n - 1) % n_unique]; del o2
+    for _ in range(3):
+        t0 = time.perf_counter(); o2 = dctx.multi_decompress_to_buffer(fbws); _ = o2[n - 1].tobytes(); tgd = min(tgd, time.perf_counter() - t0); del o2
+    return {
+        "workload": "%d x ~%d B JSON-like records (%d distinct), trained %d-byte dictionary, level 3; public API with host buffers"
+                    % (n, U // n, n_unique, len(dct)),
+        "compress_e2e": {"value": U / tg / 1e9, "unit": "GB/s", "ms": tg * 1e3},
+        "decompress_e2e": {"value": U / tgd / 1e9, "unit": "GB/s", "ms": tgd * 1e3},
+        "ratio": U / csz, "reference_ratio": U / float(rl.sum()), "size_vs_reference_pct": 100.0 * (csz / float(rl.sum()) - 1.0),
+        "roundtrip": {"own_decoder_sampled": bool(ok), "reference_decoder_all": ok_ref, "reference_frames_on_gpu": bool(ok_dec)},
+        "cpu_baseline": {"compress": U / tc / 1e9, "decompress": U / td / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference",
+                         "sample": "the same batch, best of 2"},
+    }
 
 
 def main():
@@ -163,7 +249,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_frames = args.frames
-    threads = max(1, (os.cpu_count() or 1) // world)
+    cores, host_info = host_threads()
+    threads = max(1, cores // world)
     ref, blob, cblob, coff, clens = make_batch(n_frames, threads)
     U, Cb = int(len(blob)), int(len(cblob))
     log("[rank %d] batch: %d frames, U=%d B, C=%d B, ratio %.3f" % (rank, n_frames, U, Cb, U / Cb))
@@ -238,8 +325,11 @@ def main():
     assert last == blob[-FRAME:].tobytes()
 
     # ---------------- secondary arm: multi_compress_to_buffer on 128 KiB Silesia-mix segments (configs[2], scaled)
-    cn = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "8192"))      # set to a small number for quick kernel experiments
-    cblob_in, coff_in, cln_in = corpus.silesia_mix(cn, 131072)
+    # BASELINE.json configs[2] in full: 65536 x 128 KiB, ONE batch cut by segment index over the ranks (strong scaling:
+    # every GPU gets 65536 / N segments, no data-path collective).  ZB_BENCH_COMPRESS_SEGMENTS shrinks it for experiments.
+    cn_total = int(os.environ.get("ZB_BENCH_COMPRESS_SEGMENTS", "65536"))
+    cn = cn_total // world
+    cblob_in, coff_in, cln_in = corpus.silesia_mix(cn, 131072, seed=3 + rank)
     csegs = np.stack([coff_in, cln_in], axis=1).astype(np.uint64)
     d_cin = torch.empty(len(cblob_in) + 256, dtype=torch.uint8, device="cuda")
     d_cin[:len(cblob_in)].copy_(torch.from_numpy(cblob_in))
@@ -288,17 +378,46 @@ def main():
         del rr
     barrier()
     comp_e2e_ms = (time.perf_counter() - t0) * 1e3 / csteps
-    del d_cin
+    ctx.profile(True)
+    L.zb200_result_free(step_compress())
+    comp_prof = ctx.profile_read()
+    ctx.profile(False)
+    del d_cin, cpin, cbws, cctx
 
     times = torch.tensor([dev_ms, e2e_ms, comp_ms, comp_e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, comp_ms, comp_e2e_ms = (float(times[i]) for i in range(4))
 
+    # ---------------- one call, one batch, N devices: the in-process partition (threads -> devices) of the public API
+    sharded = None
+    if world > 1:
+        barrier()
+        if rank == 0 and torch.cuda.device_count() >= world:
+            dsh = zstd.ZstdDecompressor()
+            r = dsh.multi_decompress_to_buffer(bws, threads=world); del r
+            ts = []
+            for _ in range(max(3, args.steps // 2)):
+                t0 = time.perf_counter()
+                r = dsh.multi_decompress_to_buffer(bws, threads=world)
+                lastb = r[n_frames - 1].tobytes(); del r
+                ts.append(time.perf_counter() - t0)
+            assert lastb == blob[-FRAME:].tobytes()
+            sharded = {"api": "ZstdDecompressor.multi_decompress_to_buffer(threads=%d): one process, the batch cut by segment "
+                              "index over %d devices, host buffers" % (world, world),
+                       "value": U / min(ts) / 1e9, "unit": "GB/s", "ms_per_step": min(ts) * 1e3, "devices": world}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    dict_info = None
+    try:
+        dict_info = run_dictionary_arm(zstd, ref, cores, local)
+    except Exception as e:          # the arm is secondary: report, do not lose the headline line
+        dict_info = {"error": repr(e)}
 
     # ---------------- roofline of the dominant kernel
     peaks = {}
@@ -312,9 +431,10 @@ def main():
     kernels = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items()}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
     achieved = alg_bytes / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
-    traffic = None
+    traffic = None          # DRAM bytes per step: the SUM over the step's kernels (one ncu --set full capture, profiles/traffic.json)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = sum(int(tj[k]) for k in tj if k.startswith("zb_") and not k.startswith("zb_compress"))
     except Exception:
         pass
     # the library times spans, some of which hold two kernels: placement = zb_place_reduce + zb_place_scan, execute =
@@ -323,7 +443,6 @@ def main():
     launches = sum(v["launches"] * per_span.get(k, 1) for k, v in kernels.items())
 
     # ---------------- CPU baseline: the unmodified reference on this box's cores, same batch
-    cores = os.cpu_count() or 1
     sizes = np.full(n_frames, FRAME, dtype=np.uint64)
     ref.batch(False, cblob, coff, clens, dst_len=sizes, threads=cores, gather=False)
     best = 1e9
@@ -341,14 +460,26 @@ def main():
         t0 = time.perf_counter()
         refc_total = ref.batch(True, cblob_in, coff_in, cln_in, level=3, threads=cores, gather=False)
         tcb = min(tcb, time.perf_counter() - t0)
+    ck = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in (comp_prof or {}).items()}
+    cdom = max(ck, key=lambda k: ck[k]["ms_per_launch"]) if ck else None
+    c_alg = len(cblob_in) + csz + 32 * cn
     compress_info = {
-        "workload": "multi_compress_to_buffer: %d x 128 KiB Silesia-mix segments per GPU, level-3 class" % cn,
+        "workload": "multi_compress_to_buffer: %d x 128 KiB Silesia-mix segments in all (BASELINE configs[2]), cut by segment "
+                    "index over %d GPU(s): %d per GPU, level-3 class" % (cn * world, world, cn),
+        "scaling": "strong", "segments_total": cn * world, "segments_per_gpu": cn,
         "value": world * len(cblob_in) / (comp_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": comp_ms,
-        "e2e": {"value": world * len(cblob_in) / (comp_e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": comp_e2e_ms},
+        "e2e": {"value": world * len(cblob_in) / (comp_e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": comp_e2e_ms,
+                "h2d_bytes_per_step": len(cblob_in) + 16 * cn, "d2h_bytes_per_step": csz + 16 * cn},
+        "kernels": ck,
+        "roofline": None if not cdom else {"bound": "hbm", "kernel": cdom, "achieved": c_alg / (ck[cdom]["ms_per_launch"] * 1e-3) / 1e9,
+                                           "peak": peak, "unit": "GB/s", "frac": c_alg / (ck[cdom]["ms_per_launch"] * 1e-3) / 1e9 / peak,
+                                           "algorithmic_bytes_per_launch": c_alg,
+                                           "note": "rank 0's shard; shared-memory and issue bound (one CTA per SM, block resident in shared memory)"},
         "ratio": len(cblob_in) / csz, "reference_level3_ratio": len(cblob_in) / refc_total,
         "size_vs_reference_pct": 100.0 * (csz / refc_total - 1.0),
         "roundtrip": "reference decoder regenerates the input bit-exact",
-        "cpu_baseline": {"value": len(cblob_in) / tcb / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference"},
+        "cpu_baseline": {"value": len(cblob_in) / tcb / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference",
+                         "sample": "rank 0's shard (%d segments), best of 3, ZSTD_compressStream2(e_end) per segment on %d threads" % (cn, cores)},
     }
     emit({
         "metric": METRIC, "value": world * U / (dev_ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
@@ -358,7 +489,8 @@ def main():
                                "(S-text, reference-compressed, ratio %.2f)" % (n_frames, U / Cb),
                    "l2": "inputs (%d MB compressed + %d MB output per step) exceed the 126 MB L2; no flush needed"
                          % (Cb >> 20, U >> 20),
-                   "sharding": "independent frames, one process per GPU, no data-path collective"},
+                   "sharding": "independent frames, one process per GPU, every GPU decodes its own batch of this size (weak scaling, "
+                               "no data-path collective); `compress` below is ONE batch cut over the GPUs, `sharded` one call over N devices"},
         "e2e": {"value": world * U / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": Cb + 16 * n_frames, "d2h_bytes_per_step": U + 16 * n_frames,
                 "api": "ZstdDecompressor.multi_decompress_to_buffer(BufferWithSegments in pinned host memory)"},
@@ -369,6 +501,9 @@ def main():
                      "note": "latency/issue-bound bitstream work; fraction of HBM copy bandwidth"},
         "kernels": kernels,
         "compress": compress_info,
+        "dictionary": dict_info,
+        "sharded": sharded,
+        "host": host_info,
         "scratch_bytes_per_step": scratch,
         "cpu_baseline": {"value": U / best / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference",
                          "one_core_GBps": one_core,
