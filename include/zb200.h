@@ -93,6 +93,21 @@ int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const s
                                 const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags,
                                 zb200_result** out);
 
+/* ---- decompression parameters: what ZstdDecompressor(max_window_size=...) configures (c-ext/decompressor.c:17-60,
+ * ZSTD_DCtx_setMaxWindowSize zstd/zstd.c:45025).  As in the reference's streaming decoder (zstd/zstd.c:45406-45453) the
+ * limit binds for frames whose header carries no content size -- the others take the single-pass path that needs no
+ * window buffer.  A frame over the limit fails with code 16, "Frame requires too much memory for decoding". */
+typedef struct {
+    uint64_t max_window_size;     /* 0 = the reference's default, (1 << 27) + 1 (ZSTD_MAXWINDOWSIZE_DEFAULT, zstd/zstd.c:43465) */
+    uint32_t reserved[2];
+} zb200_dparams;
+int zb200_decompress_batch_ex(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                              const uint64_t* dst_sizes, const zb200_ddict* dict, const zb200_dparams* params,
+                              uint32_t flags, zb200_result** out);
+int zb200_decompress_batch_ptrs_ex(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
+                                   const uint64_t* dst_sizes, const zb200_ddict* dict, const zb200_dparams* params,
+                                   uint32_t flags, zb200_result** out);
+
 /* ---- batch compression.
  * src_base + segs[i].offset .. +length is the i-th input (DataSource, c-ext/compressor.c:805-808).
  * Every input becomes one zstd frame (RFC 8878) of independent <=128 KiB blocks. */

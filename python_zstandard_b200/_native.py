@@ -24,6 +24,11 @@ class FrameInfo(C.Structure):
                 ("header_size", C.c_uint32), ("has_checksum", C.c_uint32), ("status", C.c_uint32)]
 
 
+class DParams(C.Structure):
+    """zb200_dparams (include/zb200.h): what ZstdDecompressor(max_window_size=...) configures."""
+    _fields_ = [("max_window_size", C.c_uint64), ("reserved", C.c_uint32 * 2)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -65,6 +70,8 @@ def lib():
             "zb200_ddict_id": (u32, [vp]),
             "zb200_decompress_batch": (i, [vp, vp, vp, sz, vp, vp, u32, C.POINTER(vp)]),
             "zb200_decompress_batch_ptrs": (i, [vp, vp, vp, sz, vp, vp, u32, C.POINTER(vp)]),
+            "zb200_decompress_batch_ex": (i, [vp, vp, vp, sz, vp, vp, vp, u32, C.POINTER(vp)]),
+            "zb200_decompress_batch_ptrs_ex": (i, [vp, vp, vp, sz, vp, vp, vp, u32, C.POINTER(vp)]),
             "zb200_compress_batch": (i, [vp, vp, vp, sz, vp, vp, u32, C.POINTER(vp)]),
             "zb200_compress_batch_ptrs": (i, [vp, vp, vp, sz, vp, vp, u32, C.POINTER(vp)]),
             "zb200_compress_bound": (u64, [u64]),

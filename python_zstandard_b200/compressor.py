@@ -110,9 +110,10 @@ class ZstdCompressor:
         seg = np.array([[0, len(buf)]], dtype=np.uint64)
         res = C.c_void_p()
         p = self._params()
+        dd = self._dict(ctx)            # (takes ctx.lock itself when it has to build the digest)
         with ctx.lock:
             rc = L.zb200_compress_batch(ctx.h, buf.ctypes.data if len(buf) else None, seg.ctypes.data, 1, C.byref(p),
-                                        self._dict(ctx), 0, C.byref(res))
+                                        dd, 0, C.byref(res))
         ctx.check(rc, "zb200_compress_batch")
         try:
             n = L.zb200_result_size(res)
@@ -174,8 +175,9 @@ class ZstdCompressor:
             ptrs = (C.c_void_p * k)(*[a.ctypes.data if len(a) else None for a in arrs])
             lens = (C.c_size_t * k)(*[len(a) for a in arrs])
             res = C.c_void_p()
+            dd = self._dict(ctx)
             with ctx.lock:
-                rc = L.zb200_compress_batch_ptrs(ctx.h, ptrs, lens, k, C.byref(p), self._dict(ctx), 0, C.byref(res))
+                rc = L.zb200_compress_batch_ptrs(ctx.h, ptrs, lens, k, C.byref(p), dd, 0, C.byref(res))
             ctx.check(rc, "zb200_compress_batch_ptrs")
             results.append(BufferWithSegments._from_result(ctx, res))
         return BufferWithSegmentsCollection(*results)
@@ -216,8 +218,9 @@ class ZstdCompressor:
 
     def _launch(self, ctx, base_ptr, sub, n, p):
         res = C.c_void_p()
+        dd = self._dict(ctx)
         with ctx.lock:
-            rc = ctx.L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, n, C.byref(p), self._dict(ctx), 0, C.byref(res))
+            rc = ctx.L.zb200_compress_batch(ctx.h, base_ptr, sub.ctypes.data, n, C.byref(p), dd, 0, C.byref(res))
         ctx.check(rc, "zb200_compress_batch")
         return res
 

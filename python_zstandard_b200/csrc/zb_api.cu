@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <chrono>
 #include <cstdlib>
@@ -18,7 +19,7 @@
 
 extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
-void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, cudaStream_t st);
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, cudaStream_t st);
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
                      u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
@@ -102,6 +103,7 @@ struct zb200_ddict {
 
 struct zb200_result {
     zb200_ctx* ctx; void* data = nullptr; bool data_on_device = false; bool data_pinned_pool = false;
+    bool data_owned_device = false;        // ZB200_DST_DEVICE: the result owns its device allocation (stream-ordered pool)
     u64 size = 0; size_t n = 0;
     std::vector<zb200_segment> segs;
     bool has_error = false; size_t err_item = 0; int err_code = 0; u64 err_got = 0, err_expected = 0;
@@ -187,6 +189,10 @@ int zb200_ctx_create(int device, zb200_ctx** out)
         delete ctx; return -1;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // device-resident results come from the stream-ordered pool: keep what it has freed (no cudaMalloc per call)
+        cudaMemPool_t pool; unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaHostAlloc((void**)&ctx->h_progress, 64 * sizeof(unsigned long long), cudaHostAllocPortable);
@@ -238,7 +244,7 @@ const char* zb200_error_string(int code)
     case 44: return "tableLog requires too much memory : unsupported";
     case 46: return "Unsupported max Symbol Value : too large";
     case 48: return "Specified maxSymbolValue is too small";
-    case 64: return "Allocation error : not enough memory";
+    case 64: return "Allocation error : not enough memory";      /* also: a frame whose literal / sequence counts do not fit 32 bits */
     case 70: return "Destination buffer is too small";
     case 72: return "Src size is incorrect";
     case 74: return "Operation on NULL destination buffer";
@@ -323,7 +329,7 @@ uint32_t zb200_ddict_id(const zb200_ddict* d) { return d ? d->dev.dict_id : 0; }
 // Device-side pipeline shared by the host and device entry points.  d_src/d_segs/d_dst_sizes are device
 // pointers.  On return the output is in ctx->dst (or caller_dst), segment table + status on the host.
 static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_segs, size_t n, const u64* d_dst_sizes,
-                          const zb200_ddict* dict, zb200_result* res, bool copy_back, bool exact_sizes)
+                          const zb200_ddict* dict, zb200_result* res, bool copy_back, bool exact_sizes, u64 window_limit)
 {
     u32 const nf = (u32)n;
     ZbDictDev dd = dict ? dict->dev : no_dict();
@@ -342,7 +348,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(cudaMemsetAsync(d_totals, 0, 8 * sizeof(u64), ctx->stream));
     CK(ctx->ck.ensure(n * sizeof(u32)));
 
-    { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), ctx->stream); }
+    { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), window_limit, ctx->stream); }
     { KSpan s(ctx, ZB200_K_PLACE);
       zb_launch_place(ctx->info.as<ZbFrameInfo>(), d_dst_sizes, nf, ctx->place.as<ZbFramePlace>(), d_totals,
                       ctx->status.as<u32>(), ctx->partial.as<u64>(), ctx->stream); }
@@ -355,7 +361,11 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(ctx->blocks.ensure((totals[1] + 1) * sizeof(ZbBlock)));
     CK(ctx->seqs.ensure((totals[2] + 1) * sizeof(ZbSeq)));
     CK(ctx->lits.ensure(totals[3] + 64));
-    CK(ctx->dst.ensure(totals[0] + 64));
+    // the output: the context's arena when it is copied back to the host, an allocation of its own (stream-ordered pool)
+    // when the caller keeps it on the device -- the next call on this context must not touch a live result
+    u8* d_out;
+    if (copy_back) { CK(ctx->dst.ensure(totals[0] + 64)); d_out = ctx->dst.as<u8>(); }
+    else { void* p = nullptr; CK(cudaMallocAsync(&p, totals[0] + 64, ctx->stream)); d_out = (u8*)p; res->data = p; res->data_on_device = true; res->data_owned_device = true; }
     ctx->last_scratch = (totals[1] + 1) * sizeof(ZbBlock) + (totals[2] + 1) * sizeof(ZbSeq) + totals[3];
 
     // ---- chunks of frames: the device->host copy of chunk k overlaps the kernels of chunk k+1
@@ -376,7 +386,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         res->data = pinned_get(ctx, totals[0] ? totals[0] : 1);
         if (!res->data) return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation);
         res->data_pinned_pool = true;
-    } else { res->data = ctx->dst.p; res->data_on_device = true; }
+    }
     for (u32 k = 0; k < n_chunks; k++) {
         u32 const f0 = cut[k], f1 = cut[k + 1];
         u32* const counter = n_chunks > 1 ? d_counter + 8 + k : d_counter;
@@ -393,15 +403,15 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
                             ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, EW, ctx->stream); }
         { KSpan s(ctx, ZB200_K_EXECUTE);
           zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
-                            ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), ctx->dst.as<u8>(), f0, f1, dd, ctx->stream); }
+                            ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out, f0, f1, dd, ctx->stream); }
         if (totals[4]) { KSpan s(ctx, ZB200_K_VERIFY);
-          zb_launch_verify(ctx->dst.as<u8>(), ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->info.as<ZbFrameInfo>(),
+          zb_launch_verify(d_out, ctx->place.as<ZbFramePlace>(), ctx->out_sizes.as<u64>(), ctx->info.as<ZbFrameInfo>(),
                            ctx->ck.as<u32>(), f0, f1, ctx->status.as<u32>(), ctx->stream); }
         if (copy_back && n_chunks > 1) {
             CK(cudaEventRecord(ctx->chunk_ev[k], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[k], 0));
             u64 const o0 = cpl[k].dst_off, o1 = cpl[k + 1].dst_off;
-            if (o1 > o0) CK(cudaMemcpyAsync((u8*)res->data + o0, ctx->dst.as<u8>() + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (o1 > o0) CK(cudaMemcpyAsync((u8*)res->data + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
     }
     { KSpan s(ctx, ZB200_K_FINISH);
@@ -410,7 +420,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     u32 first_err = 0xFFFFFFFFu;
     CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&first_err, d_first_err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    if (copy_back && n_chunks == 1) CK(cudaMemcpyAsync(res->data, ctx->dst.p, totals[0], cudaMemcpyDeviceToHost, ctx->stream));
+    if (copy_back && n_chunks == 1) CK(cudaMemcpyAsync(res->data, d_out, totals[0], cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (copy_back && n_chunks > 1) CK(cudaStreamSynchronize(ctx->copy_stream));
     if (ctx->prof) fold_spans(ctx);
@@ -418,13 +428,21 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         u32 code = 0; u64 got = 0; ZbFramePlace pl;
         cudaMemcpy(&code, ctx->status.as<u32>() + first_err, sizeof code, cudaMemcpyDeviceToHost);
         cudaMemcpy(&pl, ctx->place.as<ZbFramePlace>() + first_err, sizeof pl, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&got, ctx->out_sizes.as<u64>() + first_err, sizeof got, cudaMemcpyDeviceToHost);     // what the frame regenerated (size mismatch)
         res->has_error = true; res->err_item = first_err; res->err_code = (int)code; res->err_got = got; res->err_expected = pl.dst_cap;
     }
     return 0;
 }
 
+static u64 window_limit_of(const zb200_dparams* p)
+{
+    // ZSTD_MAXWINDOWSIZE_DEFAULT = (1 << ZSTD_WINDOWLOG_LIMIT_DEFAULT) + 1 (zstd/zstd.c:43465, :5585)
+    return p && p->max_window_size ? p->max_window_size : ((1ull << 27) + 1);
+}
+
 static int decompress_common(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
-                             const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
+                             const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out,
+                             const zb200_dparams* dparams = nullptr)
 {
     *out = nullptr;
     if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_decompress_batch: bad arguments", cudaSuccess);
@@ -458,7 +476,7 @@ static int decompress_common(zb200_ctx* ctx, const void* src_base, const zb200_s
     }
     zb200_result* res = new zb200_result(); res->ctx = ctx;
     int rc = run_decompress(ctx, d_src, d_segs, n, d_dst_sizes, dict, res, !(flags & ZB200_DST_DEVICE),
-                            !(flags & ZB200_SIZES_ARE_CAPACITY));
+                            !(flags & ZB200_SIZES_ARE_CAPACITY), window_limit_of(dparams));
     if (rc) { zb200_result_free(res); return rc; }
     *out = res;
     return 0;
@@ -470,8 +488,20 @@ int zb200_decompress_batch(zb200_ctx* ctx, const void* src_base, const zb200_seg
     return decompress_common(ctx, src_base, segs, n, dst_sizes, dict, flags, out);
 }
 
+int zb200_decompress_batch_ex(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
+                              const uint64_t* dst_sizes, const zb200_ddict* dict, const zb200_dparams* params, uint32_t flags, zb200_result** out)
+{
+    return decompress_common(ctx, src_base, segs, n, dst_sizes, dict, flags, out, params);
+}
+
 int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
                                 const uint64_t* dst_sizes, const zb200_ddict* dict, uint32_t flags, zb200_result** out)
+{
+    return zb200_decompress_batch_ptrs_ex(ctx, srcs, sizes, n, dst_sizes, dict, nullptr, flags, out);
+}
+
+int zb200_decompress_batch_ptrs_ex(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
+                                   const uint64_t* dst_sizes, const zb200_ddict* dict, const zb200_dparams* params, uint32_t flags, zb200_result** out)
 {
     *out = nullptr;
     if (!ctx || !srcs || !sizes || n == 0) return fail(ctx, "zb200_decompress_batch_ptrs: bad arguments", cudaSuccess);
@@ -482,7 +512,7 @@ int zb200_decompress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const s
     if (!stage) return fail(ctx, "pinned staging allocation", cudaErrorMemoryAllocation);
     std::vector<zb200_segment> segs(n); u64 pos = 0;
     for (size_t i = 0; i < n; i++) { memcpy(stage + pos, srcs[i], sizes[i]); segs[i].offset = pos; segs[i].length = sizes[i]; pos += sizes[i]; }
-    int rc = decompress_common(ctx, stage, segs.data(), n, dst_sizes, dict, flags & ~ZB200_SRC_DEVICE, out);
+    int rc = decompress_common(ctx, stage, segs.data(), n, dst_sizes, dict, flags & ~ZB200_SRC_DEVICE, out, params);
     pinned_put(ctx, stage);
     return rc;
 }
@@ -597,25 +627,32 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     if (overlap_upload) CK(cudaStreamSynchronize(ctx->copy_stream));
     if (upstatus) return fail(ctx, "zb200_compress_batch: the input upload did not complete", cudaErrorUnknown);
     if (zb_trace_on()) tr2 = zb_now_ms();
-    CK(ctx->dst.ensure(total + 64));
+    // the result is held by a unique_ptr until it is handed out: every early return below frees it (and its buffers)
+    std::unique_ptr<zb200_result, void (*)(zb200_result*)> res(new zb200_result(), zb200_result_free);
+    res->ctx = ctx; res->n = n; res->size = total; res->segs.resize(n);
+    u8* d_out;
+    if (!(flags & ZB200_DST_DEVICE)) { CK(ctx->dst.ensure(total + 64)); d_out = ctx->dst.as<u8>(); }
+    else {      // a device-resident result owns its allocation: later calls on this context leave it alone
+        void* p = nullptr; CK(cudaMallocAsync(&p, total + 64, ctx->stream));
+        d_out = (u8*)p; res->data = p; res->data_on_device = true; res->data_owned_device = true;
+    }
     { KSpan s(ctx, ZB200_K_FRAMES);
       zb_launch_write_frames(d_src, d_segs, ctx->seginfo.p, ctx->bouts.p, ctx->slots.as<u8>(), slot_bytes, (u32)n, P.write_checksum ? 1 : 0,
-                             P.write_content_size ? 1 : 0, P.dict_id, ctx->out_segs.as<ZbSegment>(), ctx->dst.as<u8>(), ctx->stream); }
-    zb200_result* res = new zb200_result(); res->ctx = ctx; res->n = n; res->size = total; res->segs.resize(n);
+                             P.write_content_size ? 1 : 0, P.dict_id, ctx->out_segs.as<ZbSegment>(), d_out, ctx->stream); }
     CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
     if (!(flags & ZB200_DST_DEVICE)) {
         res->data = pinned_get(ctx, total ? total : 1);
-        if (!res->data) { delete res; return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation); }
+        if (!res->data) return fail(ctx, "pinned output allocation", cudaErrorMemoryAllocation);
         res->data_pinned_pool = true;
-        CK(cudaMemcpyAsync(res->data, ctx->dst.p, total, cudaMemcpyDeviceToHost, ctx->stream));
-    } else { res->data = ctx->dst.p; res->data_on_device = true; }
+        CK(cudaMemcpyAsync(res->data, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->prof) fold_spans(ctx);
     ctx->last_scratch = (u64)ctas * (smem_kernel ? zb_encode2_scratch_bytes() : zb_encode_scratch_bytes()) + nj * slot_bytes;
     if (zb_trace_on()) { double const tr3 = zb_now_ms();
         fprintf(stderr, "[zb200] compress ctx %p n=%zu blocks=%zu: start %.3f upload %.2f kernels %.2f frames+download %.2f ms\n",
                 (void*)ctx, n, nj, tr0, tr1 - tr0, tr2 - tr1, tr3 - tr2); }
-    *out = res;
+    *out = res.release();
     return 0;
 }
 
@@ -657,6 +694,7 @@ void zb200_result_free(zb200_result* r)
 {
     if (!r) return;
     if (r->data && r->data_pinned_pool) pinned_put(r->ctx, r->data);
+    if (r->data && r->data_owned_device) { cudaSetDevice(r->ctx->device); cudaFreeAsync(r->data, r->ctx->stream); }
     delete r;
 }
 

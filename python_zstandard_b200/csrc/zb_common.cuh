@@ -26,6 +26,7 @@ enum : u32 {
     ZB_E_DICT_WRONG = 32,
     ZB_E_TABLELOG_TOO_LARGE = 44,
     ZB_E_MAXSYMBOL_TOO_SMALL = 48,
+    ZB_E_MEMORY = 64,
     ZB_E_DSTSIZE_TOO_SMALL = 70,
     ZB_E_SRCSIZE_WRONG = 72,
     // ours (python-zstandard worker errors, c-ext/decompressor.c:911-917)

@@ -115,16 +115,20 @@ __device__ static u32 zb_parse_lit_header(const u8* s, u32 n, ZbLitHdr& L)
 // K1: frame scan -- one lane per frame
 // ===========================================================================
 __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
-                               ZbFrameInfo* __restrict__ info)
+                               ZbFrameInfo* __restrict__ info, u64 window_limit)
 {
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+    u64 n_lit = 0, n_seq_rec = 0, n_blocks = 0;         // 64-bit while counting: a frame of >= 4 GiB of literals must fail, not wrap
     ZbFrameInfo fi; fi.content_size = ZB_CONTENT_UNKNOWN; fi.n_blocks = 0; fi.n_seq_rec = 0; fi.n_lit = 0;
     fi.status = ZB_OK; fi.dict_id = 0; fi.flags = 0;
     if (!zb_skip_skippable(s, n)) { fi.status = ZB_E_SRCSIZE_WRONG; info[f] = fi; return; }
     ZbHdr h; zb_parse_header(s, n, h);
     if (h.status == ZB_OK && n < 9) h.status = ZB_E_SRCSIZE_WRONG;       // zstd/zstd.c:44188
+    // the window limit binds where the reference's streaming decoder cannot take its single-pass shortcut, i.e. for frames
+    // whose header has no content size (zstd/zstd.c:45406-45453, ZSTD_d_windowLogMax / ZSTD_DCtx_setMaxWindowSize :45025)
+    if (h.status == ZB_OK && h.content_size == ZB_CONTENT_UNKNOWN && h.window > window_limit) h.status = ZB_E_WINDOW_TOO_LARGE;
     if (h.status != ZB_OK) { fi.status = h.status; info[f] = fi; return; }
     fi.content_size = h.content_size; fi.dict_id = h.dict_id; fi.flags = h.checksum;
     u64 pos = h.hdr_size;
@@ -132,7 +136,7 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
         if (pos + 3 > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
         u32 bh = zb_rd24(s + pos); pos += 3;
         u32 type = (bh >> 1) & 3, bsize = bh >> 3;
-        fi.n_blocks++;
+        n_blocks++;
         if (type == 3) { fi.status = ZB_E_CORRUPTION; break; }
         if (type == 1) bsize = 1;
         if (pos + bsize > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
@@ -141,7 +145,7 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
             if (e) { fi.status = e; break; }
             u32 lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
             if (L.regen > ZB_BLOCK_MAX || lsec > bsize) { fi.status = ZB_E_CORRUPTION; break; }
-            if (L.type >= 2) fi.n_lit += (L.regen + 15) & ~15u;          // 16-byte aligned scratch slices
+            if (L.type >= 2) n_lit += (L.regen + 15) & ~15u;             // 16-byte aligned scratch slices
             if (lsec >= bsize) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
             const u8* q = s + pos + lsec; u32 left = bsize - lsec;
             u32 nseq = q[0];
@@ -149,11 +153,13 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
                 if (nseq == 0xFF) { if (left < 3) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(q + 1) + 0x7F00; }
                 else { if (left < 2) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + q[1]; }
             }
-            fi.n_seq_rec += nseq + 1;
+            n_seq_rec += nseq + 1;
         }
         pos += bsize;
         if (bh & 1) break;
     }
+    if (fi.status == ZB_OK && (n_lit > 0xFFFFFFFFull || n_seq_rec > 0xFFFFFFFFull || n_blocks > 0xFFFFFFFFull)) fi.status = ZB_E_MEMORY;
+    fi.n_lit = (u32)n_lit; fi.n_seq_rec = (u32)n_seq_rec; fi.n_blocks = (u32)n_blocks;
     info[f] = fi;
 }
 
@@ -744,9 +750,9 @@ extern "C" {
 
 void zb_launch_default_tables(cudaStream_t st) { zb_build_default_tables<<<1, 32, 0, st>>>(); }
 
-void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, cudaStream_t st)
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, cudaStream_t st)
 {
-    zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info);
+    zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info, window_limit);
 }
 
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,

@@ -506,8 +506,10 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
                     if (last) {
                         if (h.content_size != ZB_CONTENT_UNKNOWN && out_pos != h.content_size) err = ZB_E_CORRUPTION;
                         else if (h.checksum && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
-                        else if (h.checksum) ck_expect[f] = zb_rd32(s + pos);     // compared with XXH64 of the output by zb_verify_checksums
-                        else if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;   // c-ext/decompressor.c:1151-1162
+                        else {
+                            if (h.checksum) ck_expect[f] = zb_rd32(s + pos);      // compared with XXH64 of the output by zb_verify_checksums
+                            if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;    // every frame, checksummed or not: c-ext/decompressor.c:1151-1162
+                        }
                         done = true;
                     }
                 }
@@ -515,7 +517,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
             }
         }
         if (lane < take && f < n_frames && status[f] == ZB_OK) {
-            if (err) { status[f] = err; out_sizes[f] = 0; } else out_sizes[f] = out_pos;
+            if (err) { status[f] = err; out_sizes[f] = err == ZB_E_SIZE_MISMATCH ? out_pos : 0; } else out_sizes[f] = out_pos;     // (the mismatch message names the size)
         } else if (lane < take && f < n_frames) out_sizes[f] = 0;
     }
 }

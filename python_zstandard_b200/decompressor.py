@@ -55,6 +55,8 @@ class ZstdDecompressor:
             raise ZstdError("unable to set max window size: Parameter is out of bound")
         self._dict_data = dict_data
         self._max_window_size = max_window_size
+        # enforced by the scan kernel like ZSTD_DCtx_setMaxWindowSize (c-ext/decompressor.c:22-24, zstd/zstd.c:45452)
+        self._dparams = _native.DParams(max_window_size, (C.c_uint32 * 2)(0, 0))
         self._format = format
         self._ctx = None
 
@@ -90,8 +92,8 @@ class ZstdDecompressor:
         res = C.c_void_p()
         dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
         with ctx.lock:
-            rc = L.zb200_decompress_batch(ctx.h, buf.ctypes.data, seg.ctypes.data, 1, sizes.ctypes.data, dd, flags,
-                                          C.byref(res))
+            rc = L.zb200_decompress_batch_ex(ctx.h, buf.ctypes.data, seg.ctypes.data, 1, sizes.ctypes.data, dd,
+                                             C.byref(self._dparams), flags, C.byref(res))
         ctx.check(rc, "zb200_decompress_batch")
         try:
             item, code = C.c_size_t(), C.c_int()
@@ -208,9 +210,9 @@ class ZstdDecompressor:
         res = C.c_void_p()
         dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
         with ctx.lock:
-            rc = L.zb200_decompress_batch(ctx.h, base_ptr, segs.ctypes.data, n,
-                                          sizes_arr.ctypes.data if sizes_arr is not None else None, dd, flags,
-                                          C.byref(res))
+            rc = L.zb200_decompress_batch_ex(ctx.h, base_ptr, segs.ctypes.data, n,
+                                             sizes_arr.ctypes.data if sizes_arr is not None else None, dd,
+                                             C.byref(self._dparams), flags, C.byref(res))
         ctx.check(rc, "zb200_decompress_batch")
         return res
 
@@ -282,8 +284,8 @@ class ZstdDecompressor:
             res = C.c_void_p()
             dd = self._dict_data._ddict(ctx) if self._dict_data is not None else None
             with ctx.lock:
-                rc = L.zb200_decompress_batch_ptrs(ctx.h, ptrs, lens, k, ssz.ctypes.data if ssz is not None else None,
-                                                   dd, 0, C.byref(res))
+                rc = L.zb200_decompress_batch_ptrs_ex(ctx.h, ptrs, lens, k, ssz.ctypes.data if ssz is not None else None,
+                                                      dd, C.byref(self._dparams), 0, C.byref(res))
             ctx.check(rc, "zb200_decompress_batch_ptrs")
             self._raise_item_error(L, res, lo)
             out.append(BufferWithSegments._from_result(ctx, res))

@@ -5,6 +5,7 @@ dict_id(), as_bytes(), len()).  Training (ZDICT_*, c-ext/compressiondict.c:13-14
 is out of scope: train with the reference and pass the bytes in.
 """
 import struct
+import threading
 
 from . import _native
 from .errors import ZstdError
@@ -24,6 +25,7 @@ class ZstdCompressionDict:
         self.k = k
         self.d = d
         self._ddicts = {}       # device index -> native handle
+        self._lock = threading.Lock()
         is_full = len(self._data) >= 8 and struct.unpack_from("<I", self._data)[0] == _DICT_MAGIC
         if dict_type == DICT_TYPE_FULLDICT and not is_full:
             raise ZstdError("dictionary is not a full zstd dictionary")
@@ -49,15 +51,24 @@ class ZstdCompressionDict:
 
     # -- device digest (ensure_ddict, c-ext/compressiondict.c:148-162)
     def _ddict(self, ctx):
+        """The device digest of this dictionary on ctx's device: one per device, created under the dictionary's lock and
+        the context's lock (several pipeline workers may ask at once), freed when the dictionary object goes away."""
         h = self._ddicts.get(ctx.device)
-        if h is None:
-            import ctypes as C
-            h = C.c_void_p()
-            data = self._data
-            if self._raw and len(data) >= 8 and struct.unpack_from("<I", data)[0] == _DICT_MAGIC:
-                raise ZstdError("raw-content dictionaries starting with the dictionary magic are not supported")
-            rc = ctx.L.zb200_ddict_create(ctx.h, data, len(data), C.byref(h))
-            if rc != 0:
-                raise ZstdError("unable to load dictionary: %s" % ctx.last_error())
-            self._ddicts[ctx.device] = h
+        if h is not None:
+            return h
+        with self._lock:
+            h = self._ddicts.get(ctx.device)
+            if h is None:
+                import ctypes as C
+                import weakref
+                h = C.c_void_p()
+                data = self._data
+                if self._raw and len(data) >= 8 and struct.unpack_from("<I", data)[0] == _DICT_MAGIC:
+                    raise ZstdError("raw-content dictionaries starting with the dictionary magic are not supported")
+                with ctx.lock:
+                    rc = ctx.L.zb200_ddict_create(ctx.h, data, len(data), C.byref(h))
+                if rc != 0:
+                    raise ZstdError("unable to load dictionary: %s" % ctx.last_error())
+                self._ddicts[ctx.device] = h
+                weakref.finalize(self, ctx.L.zb200_ddict_free, h)
         return h

@@ -309,7 +309,7 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     std::vector<ZbSegment> segs(n); for (u32 i = 0; i < n; i++) { segs[i].offset = seg_off[i]; segs[i].length = seg_len[i]; }
     std::vector<ZbFrameInfo> info(n); std::vector<ZbFramePlace> place(n + 1); std::vector<u32> status(n, 0);
     u64 totals[8] = {0}; u32 const pctas = (n + ZB_PLACE_CTA - 1) / ZB_PLACE_CTA; std::vector<u64> partial(pctas * 4 + 4);
-    simt::launch((n + 127) / 128, 128, [&] { zb_scan_frames(src, segs.data(), n, info.data()); });
+    simt::launch((n + 127) / 128, 128, [&] { zb_scan_frames(src, segs.data(), n, info.data(), (1ull << 27) + 1); });
     simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_reduce(info.data(), dst_sizes, n, partial.data()); });
     simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_scan(info.data(), dst_sizes, n, partial.data(), place.data(), totals, status.data()); });
     if (totals[0] > out_cap) return -1000;
@@ -397,7 +397,7 @@ extern "C" int t_decode_frame(const u8* src, u64 n, const u8* dict_raw, u32 dict
         } else { dict.content = dict_raw; dict.content_size = dict_n; }
     }
     ZbSegment seg; seg.offset = 0; seg.length = n;
-    ZbFrameInfo fi; zb_scan_frames(src, &seg, 1, &fi);
+    ZbFrameInfo fi; zb_scan_frames(src, &seg, 1, &fi, (1ull << 27) + 1);
     if (fi.status != ZB_OK) return (int)fi.status;
     u64 const want = fi.content_size != ZB_CONTENT_UNKNOWN ? fi.content_size : cap;
     if (want > cap) return (int)ZB_E_DSTSIZE_TOO_SMALL;

@@ -94,7 +94,7 @@ def test_input_kinds_and_sizes(ref):
     assert [result[i].tobytes() for i in range(3)] == original
     with pytest.raises(ValueError, match="decompressed_sizes size mismatch; expected 24, got 16"):
         dctx.multi_decompress_to_buffer(frames, decompressed_sizes=sizes[:16])
-    with pytest.raises(zstd.ZstdError, match="error decompressing item 1: decompressed 18 bytes; expected 19|error decompressing item 1"):
+    with pytest.raises(zstd.ZstdError, match="error decompressing item 1: decompressed 18 bytes; expected 19"):
         dctx.multi_decompress_to_buffer(frames, decompressed_sizes=struct.pack("=QQQ", 12, 19, 24))
 
 
@@ -209,3 +209,55 @@ def test_content_checksum_is_verified(oracle):
     # a multi-block checksummed frame still verifies
     big = [v for v in helpers.golden_vectors() if v[0] == "text150k_l3_multiblock"][0]
     assert d.decompress(big[1]) == big[2]
+
+
+def test_size_mismatch_is_reported_for_checksummed_frames_too(ref):
+    """c-ext/decompressor.c:1151-1162: every item whose regenerated size differs from decompressed_sizes[i] fails, with the
+    size it did regenerate in the message -- frames with a content checksum included."""
+    data = [b"a" * 1000, corpus.text_corpus(1 << 16).tobytes()[:5000]]
+    for checksum in (False, True):
+        frames = [ref.compress(d, checksum=checksum) for d in data]
+        with pytest.raises(zstd.ZstdError, match="error decompressing item 1: decompressed 5000 bytes; expected 5001"):
+            zstd.ZstdDecompressor().multi_decompress_to_buffer(frames, decompressed_sizes=struct.pack("=QQ", 1000, 5001))
+        nofcs = [ref.compress(d, checksum=checksum, content_size=False) for d in data]
+        with pytest.raises(zstd.ZstdError, match="error decompressing item 0: decompressed 1000 bytes; expected 1024"):
+            zstd.ZstdDecompressor().multi_decompress_to_buffer(nofcs, decompressed_sizes=struct.pack("=QQ", 1024, 5000))
+        out = zstd.ZstdDecompressor().multi_decompress_to_buffer(nofcs, decompressed_sizes=struct.pack("=QQ", 1000, 5000))
+        assert [out[i].tobytes() for i in range(2)] == data
+
+
+def test_max_window_size_is_enforced(ref):
+    """ZstdDecompressor(max_window_size=...) -> ZSTD_DCtx_setMaxWindowSize (c-ext/decompressor.c:22-24).  As in the reference's
+    streaming decoder (zstd/zstd.c:45406-45453) the limit binds for frames without a content size in their header; the
+    message is the reference's (zstd/zstd.c:3585)."""
+    data = corpus.text_corpus(1 << 20).tobytes()[:300000]
+    with_fcs, without = ref.compress(data), ref.compress(data, content_size=False)
+    small = zstd.ZstdDecompressor(max_window_size=1 << 12)
+    assert small.multi_decompress_to_buffer([with_fcs])[0].tobytes() == data            # single-pass path: no window buffer needed
+    with pytest.raises(zstd.ZstdError, match="error decompressing item 0: Frame requires too much memory for decoding"):
+        small.multi_decompress_to_buffer([without], decompressed_sizes=struct.pack("=Q", len(data)))
+    with pytest.raises(zstd.ZstdError, match="decompression error: Frame requires too much memory for decoding"):
+        small.decompress(without, max_output_size=len(data))
+    roomy = zstd.ZstdDecompressor(max_window_size=1 << 22)
+    assert roomy.multi_decompress_to_buffer([without], decompressed_sizes=struct.pack("=Q", len(data)))[0].tobytes() == data
+    assert zstd.ZstdDecompressor().decompress(without, max_output_size=len(data)) == data
+
+
+def test_device_resident_results_survive_the_next_call(ref):
+    """ZB200_DST_DEVICE results own their device allocation: a later call on the same context leaves them alone."""
+    import ctypes as C
+    from python_zstandard_b200 import _native
+    L = _native.lib(); ctx = _native.Context.get(0)
+    a, b = [corpus.text_corpus(1 << 20).tobytes()[i * 50000:(i + 1) * 50000] for i in range(2)]
+    def run(data):
+        f = np.frombuffer(ref.compress(data), dtype=np.uint8).copy()
+        seg = np.array([[0, len(f)]], dtype=np.uint64)
+        r = C.c_void_p()
+        ctx.check(L.zb200_decompress_batch(ctx.h, f.ctypes.data, seg.ctypes.data, 1, None, None, _native.DST_DEVICE, C.byref(r)), "decompress")
+        return r
+    ra = run(a); rb = run(b)
+    for r, want in ((ra, a), (rb, b)):
+        out = np.empty(len(want), dtype=np.uint8)
+        ctx.check(L.zb200_memcpy_d2h(ctx.h, out.ctypes.data, L.zb200_result_data(r), len(want)), "d2h")
+        assert out.tobytes() == want
+        L.zb200_result_free(r)
