@@ -18,6 +18,9 @@ from .dictionary import (ZstdCompressionDict, DICT_TYPE_AUTO, DICT_TYPE_RAWCONTE
 from .decompressor import ZstdDecompressor, FORMAT_ZSTD1, FORMAT_ZSTD1_MAGICLESS  # noqa: F401
 from .compressor import ZstdCompressor, ZstdCompressionParameters  # noqa: F401
 from ._native import set_device, default_device  # noqa: F401
+from .streams import (COMPRESSOBJ_FLUSH_FINISH, COMPRESSOBJ_FLUSH_BLOCK, DECOMPRESSION_RECOMMENDED_INPUT_SIZE,  # noqa: F401
+                      DECOMPRESSION_RECOMMENDED_OUTPUT_SIZE, COMPRESSION_RECOMMENDED_INPUT_SIZE,
+                      COMPRESSION_RECOMMENDED_OUTPUT_SIZE)
 
 __version__ = "0.25.0+b200"
 backend = "b200"

@@ -228,4 +228,9 @@ class ZstdCompressor:
     def _unsupported(self, *a, **k):
         raise NotImplementedError("streaming compression objects are outside the B200 batch path")
 
-    stream_reader = stream_writer = compressobj = read_to_iter = copy_stream = chunker = _unsupported
+    stream_reader = stream_writer = read_to_iter = copy_stream = chunker = _unsupported
+
+    def compressobj(self, size=-1):
+        """c-ext/compressor.c:576-640; the frame is written in one piece at flush() (streams.py)."""
+        from .streams import ZstdCompressionObj
+        return ZstdCompressionObj(self, size)

@@ -295,5 +295,16 @@ class ZstdDecompressor:
     def _unsupported(self, *a, **k):
         raise NotImplementedError("streaming decompression objects are outside the B200 batch path")
 
-    stream_reader = stream_writer = decompressobj = read_to_iter = copy_stream = _unsupported
+    stream_writer = read_to_iter = copy_stream = _unsupported
     decompress_content_dict_chain = _unsupported
+
+    # ------------------------------------------------------------------ SURVEY.md section 8f rows 1 and 3
+    def decompressobj(self, write_size=131072, read_across_frames=False):
+        """c-ext/decompressor.c:397-455; a whole frame is the unit of device work (streams.py)."""
+        from .streams import ZstdDecompressionObj
+        return ZstdDecompressionObj(self, write_size, read_across_frames)
+
+    def stream_reader(self, source, read_size=131075, read_across_frames=False, closefd=True):
+        """c-ext/decompressor.c:509-566, c-ext/decompressionreader.c:177-318."""
+        from .streams import ZstdDecompressionReader
+        return ZstdDecompressionReader(self, source, read_size, read_across_frames, closefd)
