@@ -1,25 +1,28 @@
-// zb_encode2.cuh -- the round-2 block compressor: ONE CTA of 1024 threads per SM, the <=128 KiB block resident in
-// shared memory (TMA bulk copy), every dependent access (hash tables, candidate verification, parse, FSE states) served
-// from shared memory; only streaming intermediates (unit records, compacted sequences) go through the L2-resident
-// per-CTA scratch.  Included by zb_encode.cu (it reuses the table builders above).
+// zb_encode2.cuh -- the round-2 block compressor: ONE CTA of 1024 threads per SM, the <= 128 KiB block resident in
+// shared memory (TMA bulk copy); every dependent access (hash table, candidate verification, parse, FSE states, Huffman
+// codes) is served from shared memory; only streaming intermediates (match records, final sequences) pass through the
+// L2-resident per-CTA scratch.  Included by zb_encode.cu (it reuses the serial table builders above).
 //
 // Stands in for ZSTD_compressBlock_doubleFast (zstd/zstd.c:31039) + ZSTD_entropyCompressSeqStore (:25842) per block:
 //   load     cp.async.bulk global -> shared, mbarrier completion
-//   links    passes of 16 KiB.  near: a warp per 1 KiB sub-chunk, private 512-slot table (position | 6-bit tag),
-//            16 positions per half-step, exact order.  far: one 2^14-slot table keyed on 5 bytes, advanced in rounds
-//            of 1024 positions (all threads): lookup -> verify both candidates + distances 1..4 against the input in
-//            shared memory (<= 15 bytes) -> one-step lazy with the neighbour's length -> dist[] (0 = no match here)
-//   parse    a lane per 132-byte unit walks dist[]: a match may START only in its unit but extends freely (forward
-//            to the block end, backward to the unit's anchor); records {start, len, dist} -> scratch
-//   stitch   fold of the units' last match ends -> what each unit must drop / front-trim; survivors are compacted;
-//            repcode history is an MTF(3) list, so unit summaries (3 most recent distinct offsets) scan exactly and
-//            every lane codes its unit's offsets with the true history (ZSTD_updateRep :19971)
-//   entropy  tables by four warps (LL, OF, ML, Huffman); FSE state chains run SPECULATIVELY per lane range: a lane
-//            warms its states up on the 24 sequences after its range, neighbours compare states and only lanes whose
-//            guess was wrong redo their range (states forget their past after ~log/H symbols); bit counts are
-//            prefix-scanned and every lane packs its own span; Huffman literals likewise from prefix-scanned lengths
-//   assemble literal streams are OR-ed straight into the block's slot, the sequence stream is staged in shared
-//            memory and copied; raw / RLE fallbacks
+//   match    passes of 8192 positions, software-pipelined: while warp 0 LINKS pass k+1, warps 1-29 VERIFY + PARSE pass k
+//     hash   all threads: 14-bit hash of the 5 bytes at every position
+//     link   warp 0, 32 positions per step in order through ONE 2^14-entry table: distance to the previous position with
+//            the same hash (exact except inside a step); eight steps' table accesses in flight
+//     v + p  a warp per 288-position region, 32 positions per step: every lane verifies its candidate (common prefix
+//            4..15, 15 = "or more"), one ballot tells every match where the next one may start, the warp hops along that
+//            chain (true greedy + one-step lazy inside the region), "15 or more" matches are extended 256 bytes per vote,
+//            every selected lane extends its own match backwards and writes its record
+//   stitch   fold of the regions' last match ends -> what each region must drop / front-trim; survivors are compacted;
+//            repcode history is an MTF(3) list, so region summaries (3 most recent distinct offsets) scan exactly and
+//            every lane codes its region's offsets with the true history (ZSTD_updateRep :19971)
+//   entropy  FSE tables: a warp per table (LL, OF, ML), lanes = symbols (normalise, cost, spread by closed form, cells by
+//            match.any ranks); Huffman code by warp 3 beside them.  The sequences are cut into <= 10 runs, each run becomes
+//            a zstd block of its own ("repeat" tables / "treeless" literals after the first): the three FSE state chains
+//            of every run are strictly serial, so 30 lanes walk them side by side (exact), leaving the state on entry
+//            of every thread's range; all threads then re-run their ranges to count and to write the bits
+//   write    bit counts are prefix-scanned; literal streams and sequence streams are OR-ed straight into the slot
+//            (first/last word of a span atomically, the words between plainly); raw fallback for the whole chunk
 #pragma once
 
 #define Z2_NT       1024
