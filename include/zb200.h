@@ -116,6 +116,9 @@ typedef struct {
     uint32_t write_checksum;      /* append XXH64 content checksum  (ZSTD_c_checksumFlag)    */
     uint32_t write_content_size;  /* frame content size in header   (ZSTD_c_contentSizeFlag) */
     uint32_t dict_id;             /* dictionary id to record, 0 = none (ZSTD_c_dictIDFlag)   */
+    uint32_t window_log;          /* 0 = default (21); 10..31: ZSTD_c_windowLog (c-ext/compressionparams.c:46): frames up to 2^W are
+                                     single-segment, larger ones declare a 2^W window; blocks are cut to min(2^W, 128 KiB) */
+    uint32_t reserved[3];
 } zb200_cparams;
 /* dict: optional dictionary (the same handle decompression uses; compression sees its last <= 32 KiB of
  * content as history before every frame, ZSTD_CCtx_refCDict / loadDictionary_byReference, c-ext/compressor.c:1146-1168) */

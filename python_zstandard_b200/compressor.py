@@ -4,8 +4,9 @@ Mirrors c-ext/compressor.c: constructor :88-261 (same keyword arguments, default
 texts), compress() :509-574 and multi_compress_to_buffer() :1341-1504.  The frames come from the
 CUDA block compressor in libzb200 (zb_encode.cu); they are RFC 8878 zstd and decode with any zstd
 decoder, but they are not byte-identical to CPU zstd's -- the parse is this project's own.
-With dict_data, the last 32 KiB of the dictionary content act as match history in front of every frame
-(the dictionary's entropy tables are not reused; frames stay self-describing).
+With dict_data, the last 32 KiB of the dictionary content act as match history in front of every frame, the frame
+starts from the dictionary's repcodes, and its entropy tables are reused where that is cheaper ("repeat" FSE tables,
+"treeless" literals), like the reference's ZSTD_compress_insertDictionary (zstd/zstd.c:28015-28180).
 """
 import ctypes as C
 
@@ -22,12 +23,13 @@ MAX_COMPRESSION_LEVEL = 22
 
 class CParams(C.Structure):
     _fields_ = [("level", C.c_int32), ("write_checksum", C.c_uint32), ("write_content_size", C.c_uint32),
-                ("dict_id", C.c_uint32)]
+                ("dict_id", C.c_uint32), ("window_log", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class ZstdCompressionParameters:
-    """The subset of c-ext/compressionparams.c that reaches this backend: level and the three
-    frame flags.  Strategy/window/LDM knobs are accepted only at their defaults (0)."""
+    """The subset of c-ext/compressionparams.c that reaches this backend: level, the three frame flags and window_log.
+    The match-finder knobs (hash_log, chain_log, search_log, min_match, target_length, strategy) and the LDM / job knobs
+    configure CPU zstd's strategies, which this backend does not have: anything but their defaults is rejected loudly."""
 
     _FIELDS = ("format", "compression_level", "window_log", "hash_log", "chain_log", "search_log", "min_match",
                "target_length", "strategy", "write_content_size", "write_checksum", "write_dict_id", "job_size",
@@ -44,7 +46,11 @@ class ZstdCompressionParameters:
         self.write_checksum = kw.get("write_checksum", 0)
         self.write_dict_id = kw.get("write_dict_id", 0)
         self.threads = kw.get("threads", 0)
-        for k in ("window_log", "hash_log", "chain_log", "search_log", "min_match", "target_length", "strategy",
+        wl = kw.get("window_log", 0) or 0
+        if wl and not (10 <= wl <= 31):
+            raise ValueError("window_log out of range")        # ZSTD_c_windowLog bounds, zstd/zstd.c:23003
+        self.window_log = wl
+        for k in ("hash_log", "chain_log", "search_log", "min_match", "target_length", "strategy",
                   "job_size", "overlap_log", "force_max_window", "enable_ldm", "ldm_hash_log", "ldm_min_match",
                   "ldm_bucket_size_log", "ldm_hash_rate_log"):
             v = kw.get(k, 0)
@@ -79,7 +85,9 @@ class ZstdCompressor:
             self._checksum = bool(compression_params.write_checksum)
             self._content_size = bool(compression_params.write_content_size)
             self._write_dict_id = bool(compression_params.write_dict_id)
+            self._window_log = compression_params.window_log
         else:
+            self._window_log = 0
             self._level = level
             # defaults: content size on, checksum off, dict id on (c-ext/compressor.c:213-227)
             self._checksum = bool(write_checksum) if write_checksum is not None else False
@@ -90,7 +98,7 @@ class ZstdCompressor:
 
     def _params(self):
         did = self._dict_data.dict_id() if (self._dict_data is not None and self._write_dict_id) else 0
-        return CParams(self._level, int(self._checksum), int(self._content_size), did)
+        return CParams(self._level, int(self._checksum), int(self._content_size), did, self._window_log)
 
     def _dict(self, ctx):
         return self._dict_data._ddict(ctx) if self._dict_data is not None else None

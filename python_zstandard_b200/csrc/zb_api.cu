@@ -41,9 +41,9 @@ void zb_launch_dict_table(const u8* tail, u32 D, u16* table, cudaStream_t st);
 u32 zb_encode_ctable_bytes();
 void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st);
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
-                            u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
+                            u32 dict_id, u32 window_log, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st);
 void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
-                            u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, const ZbSegment* out_segs, u8* dst, cudaStream_t st);
+                            u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, u32 window_log, const ZbSegment* out_segs, u8* dst, cudaStream_t st);
 u32 zb_encode_smem_bytes();
 size_t zb_encode2_scratch_bytes();
 void zb_launch_compress_smem(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes, void* outs, u32* work_counter,
@@ -531,7 +531,11 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_compress_batch: bad arguments", cudaSuccess);
     cudaSetDevice(ctx->device);
     double const tr0 = zb_trace_on() ? zb_now_ms() : 0; double tr1 = 0, tr2 = 0;
-    zb200_cparams P; if (params) P = *params; else { P.level = 3; P.write_checksum = 0; P.write_content_size = 1; P.dict_id = 0; }
+    zb200_cparams P; if (params) P = *params; else { memset(&P, 0, sizeof P); P.level = 3; P.write_content_size = 1; }
+    if (P.window_log && (P.window_log < 10 || P.window_log > 31)) return fail(ctx, "zb200_compress_batch: window_log out of range [10, 31]", cudaSuccess);
+    // Block_Maximum_Size = min(window, 128 KiB) (ZSTD_getBlockSize, zstd/zstd.c:27478): a small window cuts the blocks, and with
+    // them the reach of every match (matches never leave their block here)
+    u32 const block_max = P.window_log && P.window_log < 17 ? (1u << P.window_log) : ZB_BLOCK_MAX;
     std::vector<zb200_segment> hsegs;
     const u8* d_src; const ZbSegment* d_segs;
     const u8* up_src = nullptr; u64 up_bytes = 0;          // host input to upload while the kernel runs
@@ -563,7 +567,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
         u64 const len = hsegs[i].length; u64 pos = 0;
         sinfo[i].first_job = jobs.size(); sinfo[i].n_jobs = 0; sinfo[i].pad = 0;
         while (pos < len) {
-            u32 const sz = (u32)(len - pos < ZB_BLOCK_MAX ? len - pos : ZB_BLOCK_MAX);
+            u32 const sz = (u32)(len - pos < block_max ? len - pos : block_max);
             HostJob j; j.src_pos = hsegs[i].offset + pos; j.size = sz; j.seg = (u32)i; j.first = pos == 0; j.last = pos + sz == len;
             jobs.push_back(j); sinfo[i].n_jobs++; pos += sz;
             if (sz > max_block) max_block = sz;
@@ -618,7 +622,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
         CK(cudaEventRecord(ctx->chunk_ev[1], ctx->copy_stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[1], 0));
     }
     { KSpan s(ctx, ZB200_K_LAYOUT);
-      zb_launch_frame_layout(d_segs, ctx->seginfo.p, ctx->bouts.p, (u32)n, P.write_checksum ? 1 : 0, P.write_content_size ? 1 : 0, P.dict_id,
+      zb_launch_frame_layout(d_segs, ctx->seginfo.p, ctx->bouts.p, (u32)n, P.write_checksum ? 1 : 0, P.write_content_size ? 1 : 0, P.dict_id, P.window_log,
                              ctx->fsizes.as<u64>(), ctx->out_segs.as<ZbSegment>(), d_total, ctx->stream); }
     u64 total = 0; u32 upstatus = 0;
     CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -638,7 +642,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     }
     { KSpan s(ctx, ZB200_K_FRAMES);
       zb_launch_write_frames(d_src, d_segs, ctx->seginfo.p, ctx->bouts.p, ctx->slots.as<u8>(), slot_bytes, (u32)n, P.write_checksum ? 1 : 0,
-                             P.write_content_size ? 1 : 0, P.dict_id, ctx->out_segs.as<ZbSegment>(), d_out, ctx->stream); }
+                             P.write_content_size ? 1 : 0, P.dict_id, P.window_log, ctx->out_segs.as<ZbSegment>(), d_out, ctx->stream); }
     CK(cudaMemcpyAsync(res->segs.data(), ctx->out_segs.p, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
     if (!(flags & ZB200_DST_DEVICE)) {
         res->data = pinned_get(ctx, total ? total : 1);

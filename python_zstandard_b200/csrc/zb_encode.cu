@@ -68,7 +68,7 @@ struct ZeBlockJob {        // one <=128 KiB block of one segment
 };
 struct ZeBlockOut { u32 csize; u32 pad; };     // compressed block bytes (header included) in its slot
 
-struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };
+struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; u32 window_log = 0; };     // window_log: 0 = default (21)
 
 // dictionary as the block compressor sees it: the last <= 32 KiB of the dictionary content act as history
 // right before the first block of every frame (restates the "attach dictionary" mode, zstd/zstd.c:25263-25277)
@@ -1259,9 +1259,11 @@ __device__ __forceinline__ u32 ze_frame_header(u8* o, u64 size, ZeParams P)
         // like the reference at level 3 (window log 21): a frame is "single segment" (window = content) only up to 2 MiB;
         // bigger frames declare a 2 MiB window, so that streaming decoders with a window limit still take them
         // (our matches never reach further back than 64 KiB + the dictionary tail)
-        bool const single = size <= (1ull << 21);
+        // ZstdCompressionParameters(window_log=W) moves that threshold: single segment up to 2^W, a 2^W window beyond
+        u32 const wl = P.window_log ? P.window_log : 21u;
+        bool const single = size <= (1ull << wl);
         o[p++] = (u8)((fcs << 6) | ((single ? 1u : 0u) << 5) | (P.checksum << 2) | did);
-        if (!single) o[p++] = (u8)((21 - 10) << 3);
+        if (!single) o[p++] = (u8)((wl - 10) << 3);
         if (did == 1) o[p++] = (u8)P.dict_id; else if (did == 2) { o[p++] = (u8)P.dict_id; o[p++] = (u8)(P.dict_id >> 8); }
         else if (did == 3) for (int k = 0; k < 4; k++) o[p++] = (u8)(P.dict_id >> (8 * k));
         if (fcs == 0) { if (single) o[p++] = (u8)size; }
@@ -1271,6 +1273,7 @@ __device__ __forceinline__ u32 ze_frame_header(u8* o, u64 size, ZeParams P)
     } else {
         o[p++] = (u8)((P.checksum << 2) | did);
         u32 wlog = 10; while (wlog < 17 && (1ull << wlog) < size) wlog++;        // our matches never reach beyond a block
+        if (P.window_log && wlog > P.window_log) wlog = P.window_log;            // (blocks are cut to the window, zb_api.cu)
         o[p++] = (u8)((wlog - 10) << 3);
         if (did == 1) o[p++] = (u8)P.dict_id; else if (did == 2) { o[p++] = (u8)P.dict_id; o[p++] = (u8)(P.dict_id >> 8); }
         else if (did == 3) for (int k = 0; k < 4; k++) o[p++] = (u8)(P.dict_id >> (8 * k));
@@ -1395,17 +1398,17 @@ void zb_launch_compress_blocks(const u8* src, const void* jobs, u32 n_jobs, void
 }
 
 void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const void* outs, u32 n_segs, u32 checksum, u32 content_size,
-                            u32 dict_id, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st)
+                            u32 dict_id, u32 window_log, u64* sizes, ZbSegment* out_segs, u64* total, cudaStream_t st)
 {
-    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3;
+    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3; P.window_log = window_log;
     zb_frame_sizes<<<(n_segs + 255) / 256, 256, 0, st>>>(segs, (const ZeSegInfo*)seginfo, (const ZeBlockOut*)outs, n_segs, P, sizes);
     zb_scan_sizes<<<1, 1024, 0, st>>>(sizes, n_segs, out_segs, total);
 }
 
 void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
-                            u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, const ZbSegment* out_segs, u8* dst, cudaStream_t st)
+                            u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, u32 window_log, const ZbSegment* out_segs, u8* dst, cudaStream_t st)
 {
-    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3;
+    ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3; P.window_log = window_log;
     zb_write_frames<<<(n_segs + 7) / 8, 256, 0, st>>>(src, segs, (const ZeSegInfo*)seginfo, (const ZeBlockOut*)outs, slots, slot_bytes, n_segs, P,
                                                       out_segs, dst);
 }

@@ -192,3 +192,25 @@ def test_dictionary_compression(ref, oracle):
     big = dct[-3000:] + recs[0] * 3
     f = cctx.compress(big)
     assert ref.decompress(f, len(big), dct) == big
+
+
+def test_window_log_is_honoured(ref):
+    """ZstdCompressionParameters(window_log=W) (c-ext/compressionparams.c:46, ZSTD_c_windowLog): frames above 2^W declare a
+    2^W window (the reference's frame-parameter reader says so), blocks are cut to the window, and a decoder limited to
+    that window accepts the frame."""
+    data = corpus.text_corpus(1 << 20).tobytes()[:300000]
+    for wl in (10, 13, 16, 18):
+        params = zstd.ZstdCompressionParameters(compression_level=3, window_log=wl, write_content_size=1)
+        frame = zstd.ZstdCompressor(compression_params=params).compress(data)
+        assert ref.decompress(frame, len(data)) == data
+        info = zstd.get_frame_parameters(frame) if hasattr(zstd, "get_frame_parameters") else None
+        import ctypes as C
+        from python_zstandard_b200 import _native
+        fi = _native.FrameInfo()
+        _native.lib().zb200_frame_info(frame, len(frame), C.byref(fi))
+        assert fi.window_size == 1 << wl and fi.content_size == len(data)
+        nofcs = zstd.ZstdCompressor(compression_params=zstd.ZstdCompressionParameters(window_log=wl, write_content_size=0)).compress(data)
+        limited = zstd.ZstdDecompressor(max_window_size=1 << wl)
+        assert limited.decompress(nofcs, max_output_size=len(data)) == data
+    with pytest.raises(ValueError):
+        zstd.ZstdCompressionParameters(window_log=9)
