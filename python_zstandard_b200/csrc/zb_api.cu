@@ -45,6 +45,11 @@ void zb_launch_frame_layout(const ZbSegment* segs, const void* seginfo, const vo
 void zb_launch_write_frames(const u8* src, const ZbSegment* segs, const void* seginfo, const void* outs, const u8* slots, u64 slot_bytes,
                             u32 n_segs, u32 checksum, u32 content_size, u32 dict_id, u32 window_log, const ZbSegment* out_segs, u8* dst, cudaStream_t st);
 u32 zb_encode_smem_bytes();
+u32 zb_encode3_record_max();
+u32 zb_encode3_records_per_cta();
+void zb_launch_compress_recs(const u8* src, const void* jobs, u32 n_jobs, u32 n_ctas, u8* slots, u64 slot_bytes, void* outs, u32* work_counter,
+                             const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
+                             const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st);
 size_t zb_encode2_scratch_bytes();
 void zb_launch_compress_smem(const u8* src, const void* jobs, u32 n_jobs, void* scratch, u32 n_ctas, u8* slots, u64 slot_bytes, void* outs, u32* work_counter,
                              const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st);
@@ -579,14 +584,18 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     // shared memory.  Small blocks, dictionaries and the level >= 4 mode stay on the CTA-per-block kernel (6 CTAs per SM).
     static int const force_v1 = getenv("ZB200_ENCODER_V1") ? atoi(getenv("ZB200_ENCODER_V1")) : 0;
     bool const smem_kernel = !dict && P.level < 4 && max_block >= 8192 && !force_v1;
+    // Small records with a full dictionary (config 4): a warp per record, 22 records per SM (zb_encode3.cuh).
+    bool const recs_kernel = dict && dict->c_D >= 8 && dict->dev.has_entropy && dict->d_cct && P.level < 4 && nj != 0 &&
+                             max_block <= zb_encode3_record_max() && !force_v1;
     u32 ctas = smem_kernel ? (u32)ctx->sm_count : (u32)ctx->sm_count * (227u * 1024u / zb_encode_smem_bytes());
+    if (recs_kernel) { ctas = (u32)ctx->sm_count; u32 const need = ((u32)nj + zb_encode3_records_per_cta() - 1) / zb_encode3_records_per_cta(); if (ctas > need) ctas = need; }
     if (ctas > nj) ctas = (u32)nj;
     if (ctas == 0) ctas = 1;
     CK(ctx->jobs.ensure((nj + 1) * sizeof(HostJob)));
     CK(ctx->seginfo.ensure(n * sizeof(HostSegInfo)));
     CK(ctx->slots.ensure((nj + 1) * slot_bytes));
     CK(ctx->bouts.ensure((nj + 1) * 8));
-    CK(ctx->escratch.ensure((size_t)ctas * (smem_kernel ? zb_encode2_scratch_bytes() : zb_encode_scratch_bytes())));
+    if (!recs_kernel) CK(ctx->escratch.ensure((size_t)ctas * (smem_kernel ? zb_encode2_scratch_bytes() : zb_encode_scratch_bytes())));
     CK(ctx->fsizes.ensure(n * sizeof(u64)));
     CK(ctx->out_segs.ensure(n * sizeof(ZbSegment)));
     CK(ctx->small.ensure(256));
@@ -600,7 +609,11 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     bool const overlap_upload = up_bytes != 0 && nj != 0 && ctx->h_progress != nullptr;
     if (up_bytes && !overlap_upload) CK(cudaMemcpyAsync(ctx->src.p, up_src, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (overlap_upload) { CK(cudaEventRecord(ctx->chunk_ev[0], ctx->stream)); CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0)); }
-    if (nj && smem_kernel) { KSpan s(ctx, ZB200_K_COMPRESS);
+    if (recs_kernel) { KSpan s(ctx, ZB200_K_COMPRESS);
+      zb_launch_compress_recs(d_src, ctx->jobs.p, (u32)nj, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
+                              dict->c_tail, dict->c_D, dict->d_ctable, (const void*)dict->d_digest, dict->d_cct,
+                              overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, ctx->stream); }
+    else if (nj && smem_kernel) { KSpan s(ctx, ZB200_K_COMPRESS);
       zb_launch_compress_smem(d_src, ctx->jobs.p, (u32)nj, ctx->escratch.p, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
                               overlap_upload ? d_progress : nullptr, up_bytes, d_upstatus, ctx->stream); }
     else if (nj) { KSpan s(ctx, ZB200_K_COMPRESS);
@@ -652,7 +665,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     }
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->prof) fold_spans(ctx);
-    ctx->last_scratch = (u64)ctas * (smem_kernel ? zb_encode2_scratch_bytes() : zb_encode_scratch_bytes()) + nj * slot_bytes;
+    ctx->last_scratch = (recs_kernel ? 0ull : (u64)ctas * (smem_kernel ? zb_encode2_scratch_bytes() : zb_encode_scratch_bytes())) + nj * slot_bytes;
     if (zb_trace_on()) { double const tr3 = zb_now_ms();
         fprintf(stderr, "[zb200] compress ctx %p n=%zu blocks=%zu: start %.3f upload %.2f kernels %.2f frames+download %.2f ms\n",
                 (void*)ctx, n, nj, tr0, tr1 - tr0, tr2 - tr1, tr3 - tr2); }

@@ -1204,6 +1204,7 @@ zb_compress_blocks(const u8* __restrict__ src, const ZeBlockJob* __restrict__ jo
 }
 
 #include "zb_encode2.cuh"
+#include "zb_encode3.cuh"
 
 // ===========================================================================
 // dictionary hash table: the block compressor's table state after "having seen" the dictionary tail
@@ -1426,6 +1427,19 @@ void zb_launch_compress_smem(const u8* src, const void* jobs, u32 n_jobs, void* 
     zb_compress_smem<<<n_ctas, Z2_NT, sizeof(Z2Shared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, (Z2Scratch*)scratch, slots, slot_bytes, (ZeBlockOut*)outs, work_counter, up);
 }
 u32 zb_encode_small_max() { return ZE_SMALL_MAX; }
+
+// small records with a full dictionary: a warp per record (zb_encode3.cuh)
+u32 zb_encode3_record_max() { return Z3_RMAX; }
+u32 zb_encode3_records_per_cta() { return Z3_WARPS; }
+void zb_launch_compress_recs(const u8* src, const void* jobs, u32 n_jobs, u32 n_ctas, u8* slots, u64 slot_bytes, void* outs, u32* work_counter,
+                             const u8* dict_tail, u32 dict_D, const u16* dict_table, const void* dict_digest, const void* dict_cct,
+                             const unsigned long long* upload_progress, unsigned long long upload_total, u32* upload_status, cudaStream_t st)
+{
+    ZeDict dict; dict.tail = dict_tail; dict.D = dict_D; dict.pad = 0; dict.table = dict_table; dict.ent = (const ZbDictDigest*)dict_digest; dict.cct = dict_cct;
+    ZeUpload up; up.progress = upload_progress; up.total = upload_total; up.status = upload_status;
+    cudaFuncSetAttribute(zb_compress_recs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Z3Shared));
+    zb_compress_recs<<<n_ctas, Z3_NT, sizeof(Z3Shared), st>>>(src, (const ZeBlockJob*)jobs, n_jobs, slots, slot_bytes, (ZeBlockOut*)outs, work_counter, dict, up);
+}
 u32 zb_encode_ctable_bytes() { return (u32)sizeof(ZeCTable); }
 void zb_launch_dict_ctables(const void* digest, void* out3, cudaStream_t st) { zb_dict_ctables<<<1, 96, 0, st>>>((const ZbDictDigest*)digest, (ZeCTable*)out3); }
 

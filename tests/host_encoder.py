@@ -197,7 +197,8 @@ extern "C" long long t_compress_batch(const u8* src, const u64* seg_off, const u
     ZeUpload up; up.progress = nullptr; up.total = 0; up.status = nullptr;
     ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3;
     bool const small_blocks = max_block <= ZE_SMALL_MAX;             // as zb_api.cu picks the instantiation
-    if (nj && dual && small_blocks) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true, ZE_UNIT_SMALL>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    if (nj && dual == 2) simt::launch((nj + Z3_WARPS - 1) / Z3_WARPS < n_ctas ? (nj + Z3_WARPS - 1) / Z3_WARPS : n_ctas, Z3_NT, [&] { zb_compress_recs(src, jobs.data(), nj, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
+    else if (nj && dual && small_blocks) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true, ZE_UNIT_SMALL>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     else if (nj && small_blocks) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false, ZE_UNIT_SMALL>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     else if (nj && dual) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<true, ZE_UNIT>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
     else if (nj) simt::launch(n_ctas, ZE_THREADS, [&] { zb_compress_blocks<false, ZE_UNIT>(src, jobs.data(), nj, (ZeScratch*)scratch, slots.data(), slot_bytes, outs.data(), &counter, dict, up); });
@@ -260,6 +261,7 @@ def build_compress_sim():
     b = enc.index('extern "C" {')
     b = enc.rindex("// ====", 0, enc.rindex("// ====", 0, b))
     body = enc[a:b].replace('#include "zb_encode2.cuh"', open(os.path.join(csrc, "zb_encode2.cuh")).read().replace("#pragma once", ""))
+    body = body.replace('#include "zb_encode3.cuh"', open(os.path.join(csrc, "zb_encode3.cuh")).read().replace("#pragma once", ""))
     dec = open(os.path.join(csrc, "zb_decode.cu")).read()
     da = dec.index("\n", dec.index('#include "zb_common.cuh"')) + 1
     db = dec.index('extern "C" {')

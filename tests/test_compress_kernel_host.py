@@ -210,3 +210,25 @@ def test_smem_kernel_round_trips_and_sizes(sim, ref):
         if margin is not None:
             ours = sum(map(len, frames)); theirs = sum(len(ref.compress(s, level=3)) for s in segs)
             assert ours <= theirs * margin, (ours, theirs)
+
+
+def test_record_kernel_with_dictionary(sim, ref):
+    """zb_compress_recs (a warp per record, dictionary staged in shared memory: BASELINE config 4): frames regenerate through
+    the reference decoder with the dictionary, sizes stay within +1 % of the reference's level 3 with the same dictionary
+    on JSON-like records; records the dictionary does not help, empty, tiny, run and random records ride along."""
+    recs = corpus.json_records(2400)
+    dct = ref.train_dictionary(112640, recs[:2000])
+    recs = recs[2000:]
+    frames = compress(sim, recs, n_ctas=2, dual=2, dct=dct)
+    for s, f in zip(recs, frames):
+        assert ref.decompress(f, len(s), dict_data=dct) == s
+    ours = sum(map(len, frames)); theirs = sum(len(ref.compress(s, level=3, dict_data=dct)) for s in recs)
+    assert ours <= theirs * 1.01, (ours, theirs)
+    text = corpus.text_corpus(1 << 20).tobytes()
+    odd = [b"", b"a", b"abc" * 100, bytes(2048), np.random.default_rng(1).integers(0, 256, 2048).astype(np.uint8).tobytes(),
+           text[:2048], text[5000:5000 + 1399], recs[3] + recs[4][:2048 - len(recs[3])], dct[-700:], dct[-2048:]]
+    for checksum in (False, True):
+        frames = compress(sim, odd, n_ctas=1, dual=2, dct=dct, checksum=checksum)
+        for s, f in zip(odd, frames):
+            assert ref.decompress(f, len(s), dict_data=dct) == s
+            assert len(f) <= len(s) + 24
