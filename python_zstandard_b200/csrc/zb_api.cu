@@ -20,6 +20,15 @@
 extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
 void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, cudaStream_t st);
+void zb_launch_scan_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, ZbDictDev dict, u32* status,
+                           void* bdesc, u64* frame_end, cudaStream_t st);
+void zb_launch_entropy_blocks(const u8* src, const void* bdesc, u32 n_blocks, ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
+                              ZbDictDev dict, u32* status, void* bexit, u32 take, cudaStream_t st);
+void zb_launch_resolve_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const ZbFrameInfo* info, const u64* dst_sizes,
+                              ZbBlock* blocks, const void* bdesc, const void* bexit, const u64* frame_end, u64 n_blocks, ZbSeq* seqs, ZbDictDev dict,
+                              u32* status, u64* out_sizes, u32* ck_expect, u32* entry_rep, cudaStream_t st);
+size_t zb_blkdesc_bytes();
+size_t zb_blkexit_bytes();
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
                      u32* status, u64* partial, cudaStream_t st);
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
@@ -87,6 +96,7 @@ struct zb200_ctx {
     // device arenas (grow-only)
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
     DevBuf jobs, seginfo, slots, bouts, escratch, fsizes, ck;
+    DevBuf bdesc, bexit, erep, fend;          // block-parallel decode path
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -212,6 +222,7 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->bdesc.release(); ctx->bexit.release(); ctx->erep.release(); ctx->fend.release();
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
                      &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial,
                      &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes, &ctx->ck};
@@ -385,6 +396,28 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         CK(cudaMemcpyAsync(d_counter + 8, cinit.data(), n_chunks * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    // Frames of several blocks when the batch alone does not fill the machine (one huge frame at the limit): a lane per BLOCK
+    // instead of a lane per frame for the entropy stage (zb_scan_blocks -> zb_entropy_blocks -> zb_resolve_blocks / zb_patch_blocks)
+    static int const force_blocks = getenv("ZB200_BLOCK_PATH") ? atoi(getenv("ZB200_BLOCK_PATH")) : -1;
+    bool const block_path = force_blocks >= 0 ? force_blocks != 0 : (totals[1] > n && n < 3000);
+    if (block_path) {
+        u64 const nb = totals[1];
+        CK(ctx->bdesc.ensure((nb + 1) * zb_blkdesc_bytes()));
+        CK(ctx->bexit.ensure((nb + 1) * zb_blkexit_bytes()));
+        CK(ctx->erep.ensure((nb + 1) * 3 * sizeof(u32)));
+        CK(ctx->fend.ensure(n * sizeof(u64)));
+        { KSpan s(ctx, ZB200_K_SCAN);
+          zb_launch_scan_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), dd, ctx->status.as<u32>(), ctx->bdesc.p, ctx->fend.as<u64>(), ctx->stream); }
+        u32 const take = 3, EW = 7;
+        u32 cc = ctas; { u64 const need = (nb + EW * take - 1) / (EW * take); if (cc > need) cc = (u32)need; if (cc == 0) cc = 1; }
+        { KSpan s(ctx, ZB200_K_ENTROPY);
+          zb_launch_entropy_blocks(d_src, ctx->bdesc.p, (u32)nb, ctx->blocks.as<ZbBlock>(), ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, d_counter, dd,
+                                   ctx->status.as<u32>(), ctx->bexit.p, take, ctx->stream); }
+        { KSpan s(ctx, ZB200_K_PLACE);
+          zb_launch_resolve_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), ctx->info.as<ZbFrameInfo>(), exact_sizes ? d_dst_sizes : nullptr,
+                                   ctx->blocks.as<ZbBlock>(), ctx->bdesc.p, ctx->bexit.p, ctx->fend.as<u64>(), nb, ctx->seqs.as<ZbSeq>(), dd,
+                                   ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), ctx->erep.as<u32>(), ctx->stream); }
+    }
     res->n = n; res->size = totals[0];
     res->segs.resize(n);
     if (copy_back) {
@@ -402,7 +435,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         // small batches: spread the frames over all resident warps rather than filling few warps' lanes
         { u32 const spread = (f1 - f0 + ctas * EW - 1) / (ctas * EW); if (take > spread) take = spread ? spread : 1; }
         u32 cc = ctas; { u32 const need = (f1 - f0 + EW * take - 1) / (EW * take); if (cc > need) cc = need; if (cc == 0) cc = 1; }
-        { KSpan s(ctx, ZB200_K_ENTROPY);
+        if (!block_path) { KSpan s(ctx, ZB200_K_ENTROPY);
           zb_launch_entropy(d_src, d_segs, f1, ctx->place.as<ZbFramePlace>(), exact_sizes ? d_dst_sizes : nullptr, ctx->blocks.as<ZbBlock>(),
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
                             ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, EW, ctx->stream); }

@@ -383,6 +383,164 @@ struct ZbTab { const ZbFseCell* t; u32 log; };
 #include "zb_entropy.cuh"
 
 // ===========================================================================
+// Block-parallel path, K1b: zb_scan_blocks -- one thread per frame walks the block chain once more and writes, for every
+// block, what zb_entropy_blocks needs on entry: where the block sits, where its records go, and where the Huffman tree and
+// the three FSE tables valid ON ENTRY were defined (restates the bookkeeping of ZSTD_decodeLiteralsBlock's HUFptr /
+// litEntropy, zstd/zstd.c:45840-45870, and ZSTD_decodeSeqHeaders' LLTptr / OFTptr / MLTptr + fseEntropy, :46328-46400).
+// Header parsing only; a frame whose headers do not parse is failed here.
+// ===========================================================================
+__global__ void zb_scan_blocks(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
+                               const ZbFramePlace* __restrict__ place, ZbDictDev dict, u32* __restrict__ status,
+                               ZbBlkDesc* __restrict__ bdesc, u64* __restrict__ frame_end)
+{
+    u32 const f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    u64 const b0 = place[f].blk_off, b1 = place[f + 1].blk_off;
+    if (status[f] != ZB_OK) { for (u64 b = b0; b < b1; b++) { bdesc[b].flags = ZB_BD_SKIP; bdesc[b].frame = f; } return; }
+    const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+    zb_skip_skippable(s, n);
+    ZbHdr h; zb_parse_header(s, n, h);
+    u32 err = ZB_OK;
+    if (h.dict_id && dict.dict_id && h.dict_id != dict.dict_id) err = ZB_E_DICT_WRONG;
+    u32 const block_max = h.window < ZB_BLOCK_MAX ? (u32)h.window : ZB_BLOCK_MAX;
+    ZbTabSrc dHuf = {ZB_SRC_NONE, 0, nullptr, 0}, dLL = dHuf, dOF = dHuf, dML = dHuf;
+    bool fse_valid = false;
+    if (dict.has_entropy) { dHuf.kind = dLL.kind = dOF.kind = dML.kind = ZB_SRC_DICT; fse_valid = true; }
+    u64 pos = h.hdr_size, seq_i = place[f].seq_off, lit_i = place[f].lit_off, b = b0;
+    for (; b < b1 && !err; b++) {
+        ZbBlkDesc D;
+        D.hdr_off = (u64)(s + pos - src); D.seq_off = seq_i; D.lit_off = lit_i; D.frame = f; D.block_max = block_max;
+        D.flags = (b == b0 ? ZB_BD_FIRST : 0u) | (fse_valid ? ZB_BD_FSE_VALID : 0u);
+        D.dHuf = dHuf; D.dLL = dLL; D.dOF = dOF; D.dML = dML;
+        if (pos + 3 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+        u32 const bh = zb_rd24(s + pos), type = (bh >> 1) & 3; u32 bsize = bh >> 3;
+        if (type == 3) { err = ZB_E_CORRUPTION; break; }
+        if (type == 1) bsize = 1;
+        if (pos + 3 + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+        D.span = 3 + bsize;
+        bdesc[b] = D;
+        if (type == 2) {            // what this block leaves behind for the next one
+            const u8* const bs = s + pos + 3;
+            ZbLitHdr L; u32 const e = zb_parse_lit_header(bs, bsize, L);
+            if (e) { err = e; break; }
+            u32 const lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
+            if (L.regen > ZB_BLOCK_MAX || lsec >= bsize) { err = ZB_E_CORRUPTION; break; }
+            if (L.type == 2) { dHuf.kind = ZB_SRC_NCOUNT; dHuf.p = bs + L.hdr; dHuf.n = L.csize; }
+            if (L.type >= 2) lit_i += (L.regen + 15) & ~15u;
+            const u8* ip = bs + lsec; const u8* const bend = bs + bsize;
+            u32 nseq = *ip++;
+            if (nseq > 0x7F) {
+                if (nseq == 0xFF) { if (ip + 2 > bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
+                else { if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
+            }
+            seq_i += nseq + 1;
+            if (nseq) {
+                if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                u32 const modes = *ip++;
+                short nn[64]; u32 lg, ms;
+                ZbTabSrc* const dd[3] = {&dLL, &dOF, &dML};
+                u32 const kmax[3] = {35, 31, 52}, lmax[3] = {9, 8, 9};
+                for (int t = 0; t < 3 && !err; t++) {
+                    u32 const mode = (modes >> (6 - 2 * t)) & 3; ZbTabSrc& d = *dd[t];
+                    if (mode == 0) d.kind = ZB_SRC_PREDEF;
+                    else if (mode == 1) { if (ip >= bend || ip[0] > kmax[t]) { err = ZB_E_CORRUPTION; break; } d.kind = ZB_SRC_RLE; d.sym = ip[0]; ip++; }
+                    else if (mode == 2) {
+                        ms = kmax[t];
+                        u32 const u = zb_read_ncount(nn, ms, lg, ip, (u32)(bend - ip));
+                        if (u == 0 || lg > lmax[t]) { err = ZB_E_CORRUPTION; break; }
+                        d.kind = ZB_SRC_NCOUNT; d.p = ip; d.n = u; ip += u;
+                    } else if (!fse_valid || d.kind == ZB_SRC_NONE) { err = ZB_E_CORRUPTION; break; }
+                }
+                fse_valid = true;
+            }
+        }
+        pos += 3 + bsize;
+        if (bh & 1) { b++; break; }
+    }
+    for (; b < b1; b++) { bdesc[b].flags = ZB_BD_SKIP; bdesc[b].frame = f; }      // (after an error; a healthy frame has none left)
+    frame_end[f] = pos;
+    if (err) status[f] = err;
+}
+
+// K3b: zb_resolve_blocks -- one thread per frame, after zb_entropy_blocks: frame-relative output position of every block,
+// the repcode history on entry of every block (the exit histories are symbolic in it), and the checks on the frame as a
+// whole that the lane-per-frame kernel makes after its last block (zstd/zstd.c:44260-44277, c-ext/decompressor.c:1151-1162).
+__global__ void zb_resolve_blocks(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
+                                  const ZbFramePlace* __restrict__ place, const ZbFrameInfo* __restrict__ info, const u64* __restrict__ dst_sizes,
+                                  ZbBlock* __restrict__ blocks, const ZbBlkDesc* __restrict__ bdesc, const ZbBlkExit* __restrict__ bexit,
+                                  const u64* __restrict__ frame_end, ZbDictDev dict, u32* __restrict__ status, u64* __restrict__ out_sizes,
+                                  u32* __restrict__ ck_expect, u32* __restrict__ entry_rep /* [n_blocks][3] */)
+{
+    u32 const f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    out_sizes[f] = 0;
+    if (status[f] != ZB_OK) return;
+    u64 const b0 = place[f].blk_off, b1 = place[f + 1].blk_off, cap = place[f].dst_cap;
+    u32 r[3] = {1, 4, 8};
+    if (dict.has_entropy) { r[0] = dict.rep[0]; r[1] = dict.rep[1]; r[2] = dict.rep[2]; }
+    u64 out_pos = 0; u32 err = ZB_OK;
+    for (u64 b = b0; b < b1; b++) {
+        if (bdesc[b].flags & ZB_BD_SKIP) break;
+        ZbBlkExit const X = bexit[b];
+        if (X.err) { err = X.err; break; }
+        entry_rep[3 * b] = r[0]; entry_rep[3 * b + 1] = r[1]; entry_rep[3 * b + 2] = r[2];
+        u32 const regen = blocks[b].regen;
+        if (regen > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+        blocks[b].out_pos = out_pos; out_pos += regen;
+        u32 nr[3];
+        for (int k = 0; k < 3; k++) {
+            u32 const x = X.rep[k];
+            if (x & 0x80000000u) { u32 const e = r[(x >> 29) & 3], d = x & 0x1FFFFFFFu; nr[k] = e > d ? e - d : 0xFFFFFFFFu; }   // (0: "offset 0" is corrupt, zstd/zstd.c:46905)
+            else nr[k] = x;
+        }
+        r[0] = nr[0]; r[1] = nr[1]; r[2] = nr[2];
+    }
+    if (!err) {
+        ZbFrameInfo const fi = info[f];
+        const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+        zb_skip_skippable(s, n);
+        u64 const pos = frame_end[f];
+        if (fi.content_size != ZB_CONTENT_UNKNOWN && out_pos != fi.content_size) err = ZB_E_CORRUPTION;
+        else if ((fi.flags & 1) && pos + 4 > n) err = ZB_E_CHECKSUM_WRONG;
+        else {
+            if (fi.flags & 1) ck_expect[f] = zb_rd32(s + pos);
+            if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;
+        }
+    }
+    if (err) { status[f] = err; out_sizes[f] = err == ZB_E_SIZE_MISMATCH ? out_pos : 0; } else out_sizes[f] = out_pos;
+}
+
+// K3c: zb_patch_blocks -- a warp per block: symbolic offsets become distances, and every offset is checked against what
+// has been regenerated in front of it (the check of ZSTD_execSequence, zstd/zstd.c:46666, that zb_entropy_blocks postponed).
+__global__ void __launch_bounds__(256)
+zb_patch_blocks(const ZbBlock* __restrict__ blocks, const ZbBlkDesc* __restrict__ bdesc, u64 n_blocks, ZbSeq* __restrict__ seqs,
+                const u32* __restrict__ entry_rep, ZbDictDev dict, u32* __restrict__ status)
+{
+    u32 const lane = threadIdx.x & 31;
+    u64 const b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_blocks) return;
+    ZbBlkDesc const D = bdesc[b];
+    if ((D.flags & ZB_BD_SKIP) || status[D.frame] != ZB_OK) return;
+    ZbBlock const B = blocks[b];
+    if (B.kind != ZB_BLK_COMPRESSED || B.n_seq == 0) return;
+    u32 const e0 = entry_rep[3 * b], e1 = entry_rep[3 * b + 1], e2 = entry_rep[3 * b + 2];
+    ZbSeq* const sq = seqs + B.seq_pos;
+    bool bad = false;
+    for (u32 i = lane; i < B.n_seq; i += 32) {
+        ZbSeq r = sq[i];
+        u32 const lit_next = sq[i + 1].x;
+        if (r.w & 0x80000000u) {
+            u32 const k = (r.w >> 29) & 3, d = r.w & 0x1FFFFFFFu, e = k == 0 ? e0 : (k == 1 ? e1 : e2);
+            r.w = e > d ? e - d : 0xFFFFFFFFu;
+            sq[i].w = r.w;
+        }
+        u64 const mstart = B.out_pos + r.y + (lit_next - r.x);            // frame-relative start of the match
+        if ((u64)r.w > mstart + dict.content_size) bad = true;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicCAS(&status[D.frame], (u32)ZB_OK, (u32)ZB_E_CORRUPTION);
+}
+
+// ===========================================================================
 // K4: LZ copy-execute -- one warp per frame
 // ===========================================================================
 
@@ -754,6 +912,29 @@ void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* in
 {
     zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info, window_limit);
 }
+
+void zb_launch_scan_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, ZbDictDev dict, u32* status,
+                           void* bdesc, u64* frame_end, cudaStream_t st)
+{
+    zb_scan_blocks<<<(n + 63) / 64, 64, 0, st>>>(src, segs, n, place, dict, status, (ZbBlkDesc*)bdesc, frame_end);
+}
+void zb_launch_entropy_blocks(const u8* src, const void* bdesc, u32 n_blocks, ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
+                              ZbDictDev dict, u32* status, void* bexit, u32 take, cudaStream_t st)
+{
+    cudaFuncSetAttribute(zb_entropy_blocks<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_ENT_SMEM(7));
+    zb_entropy_blocks<7><<<n_ctas, 7 * 32, ZB_ENT_SMEM(7), st>>>(src, (const ZbBlkDesc*)bdesc, n_blocks, blocks, seqs, lits, work_counter, dict, status,
+                                                                (ZbBlkExit*)bexit, take);
+}
+void zb_launch_resolve_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const ZbFrameInfo* info, const u64* dst_sizes,
+                              ZbBlock* blocks, const void* bdesc, const void* bexit, const u64* frame_end, u64 n_blocks, ZbSeq* seqs, ZbDictDev dict,
+                              u32* status, u64* out_sizes, u32* ck_expect, u32* entry_rep, cudaStream_t st)
+{
+    zb_resolve_blocks<<<(n + 63) / 64, 64, 0, st>>>(src, segs, n, place, info, dst_sizes, blocks, (const ZbBlkDesc*)bdesc, (const ZbBlkExit*)bexit,
+                                                   frame_end, dict, status, out_sizes, ck_expect, entry_rep);
+    if (n_blocks) zb_patch_blocks<<<(unsigned)((n_blocks + 7) / 8), 256, 0, st>>>(blocks, (const ZbBlkDesc*)bdesc, n_blocks, seqs, entry_rep, dict, status);
+}
+size_t zb_blkdesc_bytes() { return sizeof(ZbBlkDesc); }
+size_t zb_blkexit_bytes() { return sizeof(ZbBlkExit); }
 
 void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFramePlace* place, u64* totals,
                      u32* status, u64* partial, cudaStream_t st)

@@ -30,6 +30,20 @@
 enum : u32 { ZB_SRC_NONE = 0, ZB_SRC_PREDEF = 1, ZB_SRC_RLE = 2, ZB_SRC_NCOUNT = 3, ZB_SRC_DICT = 4 };
 struct ZbTabSrc { u32 kind; u32 sym; const u8* p; u32 n; };
 
+// ---- block-parallel decoding of frames with several blocks (zb_entropy_blocks below): what a lane needs to decode ONE block
+// without having decoded the blocks before it.  Written per block by zb_scan_blocks (header parsing only).
+enum : u32 { ZB_BD_FIRST = 1, ZB_BD_FSE_VALID = 2, ZB_BD_SKIP = 4 };
+struct ZbBlkDesc {
+    u64 hdr_off;                          // the block's 3-byte header, relative to src
+    u64 seq_off, lit_off;                 // its sequence records / literal scratch
+    u32 span;                             // header + payload bytes
+    u32 frame;
+    u32 flags;                            // ZB_BD_*
+    u32 block_max;
+    ZbTabSrc dHuf, dLL, dOF, dML;         // where the tables came from ON ENTRY ("treeless" / "repeat" re-read those headers)
+};
+struct ZbBlkExit { u32 rep[3]; u32 err; };   // repcode history on exit: concrete, or symbolic in the entry history (0x80000000 | k << 29 | d)
+
 __device__ __forceinline__ u32 zb_warp_incl_scan(u32 v, u32 lane)
 {
     #pragma unroll
@@ -519,5 +533,279 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
         if (lane < take && f < n_frames && status[f] == ZB_OK) {
             if (err) { status[f] = err; out_sizes[f] = err == ZB_E_SIZE_MISMATCH ? out_pos : 0; } else out_sizes[f] = out_pos;     // (the mismatch message names the size)
         } else if (lane < take && f < n_frames) out_sizes[f] = 0;
+    }
+}
+
+// ===========================================================================
+// The same per-block work with a lane per BLOCK instead of a lane per frame: frames of many blocks (one huge frame at the
+// limit: BASELINE config 5) are a single lane's serial chain above -- 4 ms per 128 KiB block.  Here every block of the call
+// is an item of its own.  What a block inherits from its predecessors is made explicit: the tables' sources (zb_scan_blocks
+// resolves "repeat" / "treeless" to the header that defined them), the repcode history (symbolic, resolved by
+// zb_resolve_blocks) and the output position (prefix sum of the regenerated sizes, same kernel).
+// ===========================================================================
+template <int ZB_ENT_WARPS>
+__global__ void __launch_bounds__(ZB_ENT_WARPS * 32)
+zb_entropy_blocks(const u8* __restrict__ src, const ZbBlkDesc* __restrict__ bdesc, u32 n_blocks,
+                  ZbBlock* __restrict__ blocks, ZbSeq* __restrict__ seqs, u8* __restrict__ lits,
+                  u32* __restrict__ work_counter, ZbDictDev dict, u32* status, ZbBlkExit* __restrict__ bexit, u32 take)
+{
+    extern __shared__ __align__(16) u8 zb_smem[];
+    u32 const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32* const lutLL = (u32*)zb_smem; u32* const lutML = lutLL + 36;      // baselines, indexed by symbol code
+    if (threadIdx.x < 36) lutLL[threadIdx.x] = c_LL_base[threadIdx.x];
+    if (threadIdx.x < 53) lutML[threadIdx.x] = c_ML_base[threadIdx.x];
+    __syncthreads();
+    u8* const pool = zb_smem + ZB_ENT_LUT_BYTES + warp * ZB_ENT_POOL_BYTES(ZB_ENT_WARPS);
+    u8* const ws = pool + lane * ZB_ENT_WS_BYTES;                       // lane workspace
+    u8* const tabs = pool + 32 * ZB_ENT_WS_BYTES;                       // claimable table space
+    u32 const TAB_BYTES = ZB_ENT_POOL_BYTES(ZB_ENT_WARPS) - 32 * ZB_ENT_WS_BYTES;
+
+    for (;;) {
+        u32 base = 0;
+        // `take` frames per warp and grab: 32 for small frames; fewer when frames (hence their tables) are large,
+        // so that a warp holds only as many frames as its table pool serves in one pass and the batch spreads over
+        // more warps and SMs
+        if (lane == 0) base = atomicAdd(work_counter, take);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_blocks) return;
+        u32 const bi = base + lane;                                   // this lane's BLOCK
+        ZbBlkDesc D; D.frame = 0; D.flags = 0;
+        if (lane < take && bi < n_blocks) D = bdesc[bi];
+        bool done = lane >= take || !(bi < n_blocks) || (D.flags & ZB_BD_SKIP) || status[D.frame] != ZB_OK;
+
+        // ---- per-frame lane state
+        // The block is decoded on its own: tables as they stood on entry (zb_scan_blocks), output positions relative to the
+        // block (the frame-relative start, the capacity and the offset-range checks follow in zb_resolve_blocks /
+        // zb_patch_blocks), and -- unless it is the frame's first block -- a SYMBOLIC repcode history: 0x80000000 | k << 29 | d
+        // stands for "entry repcode k, minus d".
+        const u8* s = src; u64 n = 0; u32 err = ZB_OK;
+        u64 const cap = ~0ull >> 1; u64 out_pos = 0, blk_i = bi, seq_i = 0, lit_i = 0, pos = 0; u32 block_max = 0;
+        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        ZbTabSrc dHuf = {ZB_SRC_NONE, 0, nullptr, 0}, dLL = dHuf, dOF = dHuf, dML = dHuf;
+        bool fse_valid = false;
+        if (!done) {
+            s = src + D.hdr_off; n = D.span; seq_i = D.seq_off; lit_i = D.lit_off; block_max = D.block_max;
+            dHuf = D.dHuf; dLL = D.dLL; dOF = D.dOF; dML = D.dML; fse_valid = (D.flags & ZB_BD_FSE_VALID) != 0;
+            if (D.flags & ZB_BD_FIRST) { if (dict.has_entropy) { rep0 = dict.rep[0]; rep1 = dict.rep[1]; rep2 = dict.rep[2]; } }
+            else { rep0 = 0x80000000u; rep1 = 0xA0000000u; rep2 = 0xC0000000u; }
+        }
+        u64 const hist_extra = 1ull << 40;                            // (no offset can fail the range check here)
+
+        long long t_ph = clock64();
+        // ---- one block per lane per round
+        while (__any_sync(0xFFFFFFFFu, !done)) {
+            ZB_EMARK(0);
+            ZbBlock B; B.kind = 0; B.regen = 0; B.n_seq = 0; B.n_lit = 0; B.lit_kind = 0; B.lit_byte = 0; B.src_pos = 0; B.seq_pos = seq_i; B.out_pos = out_pos;
+            bool comp = false, last = false;
+            u32 bsize = 0; const u8* bs = nullptr; const u8* bend = nullptr; const u8* ip = nullptr;
+            ZbLitHdr L; L.type = 0; L.regen = 0; L.hdr = 0; L.csize = 0; L.single = 0;
+            // -- A: block header
+            if (!done) {
+                do {
+                    if (pos + 3 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const bh = zb_rd24(s + pos); pos += 3;
+                    last = bh & 1; u32 const type = (bh >> 1) & 3; bsize = bh >> 3; B.kind = type;
+                    if (type == 3) { err = ZB_E_CORRUPTION; break; }
+                    if (type == ZB_BLK_RLE) {
+                        if (pos + 1 > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                        if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                        B.src_pos = (u64)(s + pos - src); B.regen = bsize; B.lit_byte = s[pos]; pos += 1;
+                    } else if (type == ZB_BLK_RAW) {
+                        if (pos + bsize > n) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        if (bsize > block_max) { err = ZB_E_CORRUPTION; break; }
+                        if (bsize > cap - out_pos) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                        B.src_pos = (u64)(s + pos - src); B.regen = bsize; pos += bsize;
+                    } else {
+                        if (pos + bsize > n || bsize > block_max) { err = ZB_E_SRCSIZE_WRONG; break; }
+                        bs = s + pos; bend = bs + bsize;
+                        err = zb_parse_lit_header(bs, bsize, L);
+                        if (err) break;
+                        if (L.regen > block_max) { err = ZB_E_CORRUPTION; break; }
+                        B.n_lit = L.regen; comp = true;
+                    }
+                } while (0);
+                if (err) { done = true; comp = false; }
+            }
+            ZB_EMARK(1);
+            // -- B: literals
+            bool wantH = false; u32 hlog = 0, hns = 0; u32 rank[13]; const u8* hp = nullptr; u32 hleft = 0;
+            if (comp) {
+                do {
+                    if (L.type == 0) {
+                        if (L.hdr + L.regen > bsize) { err = ZB_E_CORRUPTION; break; }
+                        B.lit_kind = ZB_LIT_RAW; B.src_pos = (u64)(bs + L.hdr - src); ip = bs + L.hdr + L.regen;
+                    } else if (L.type == 1) {
+                        if (L.hdr + 1 > bsize) { err = ZB_E_CORRUPTION; break; }
+                        B.lit_kind = ZB_LIT_RLE; B.lit_byte = bs[L.hdr]; ip = bs + L.hdr + 1;
+                    } else {
+                        if (L.type == 3 && dHuf.kind == ZB_SRC_NONE) { err = ZB_E_DICT_CORRUPTED; break; }
+                        if (!L.single && L.regen < 6) { err = ZB_E_LITERALS_HEADER_WRONG; break; }
+                        if (L.csize + L.hdr > bsize || L.regen == 0) { err = ZB_E_CORRUPTION; break; }
+                        hp = bs + L.hdr; hleft = L.csize;
+                        if (L.type == 2) { dHuf.kind = ZB_SRC_NCOUNT; dHuf.p = hp; dHuf.n = hleft; }
+                        if (dHuf.kind == ZB_SRC_NCOUNT) {
+                            u32 const used = zb_huf_weights(ws, dHuf.p, dHuf.n, hlog, hns, rank);
+                            if (used == 0 || (L.type == 2 && used >= hleft)) { err = ZB_E_CORRUPTION; break; }
+                            if (L.type == 2) { hp += used; hleft -= used; dHuf.n = used; }
+                            wantH = true;
+                        }
+                        B.lit_kind = ZB_LIT_SCRATCH; B.src_pos = lit_i; ip = bs + L.hdr + L.csize;
+                    }
+                } while (0);
+                if (err) { done = true; comp = false; wantH = false; }
+            }
+            // dictionary Huffman table: read in place from the digest (shared by every lane, cache resident)
+            if (comp && B.lit_kind == ZB_LIT_SCRATCH && dHuf.kind == ZB_SRC_DICT) {
+                if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, zb_huf_full(dict.huf, dict.huf_log))) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+            }
+            ZB_EMARK(2);
+            {   // claim pool space for the Huffman cells, decode; lanes that do not fit wait for the next pass
+                bool pending = wantH;
+                u32 hshift = 0, hT = 0, hbase = 0, hbytes = 0;
+                if (wantH) zb_huf_shape(hlog, rank, hshift, hT, hbase, hbytes);
+                while (__any_sync(0xFFFFFFFFu, pending)) {
+                    u32 const need = pending ? hbytes : 0;
+                    u32 const incl = zb_warp_incl_scan((need + 15) & ~15u, lane);
+                    if (pending && incl <= TAB_BYTES) {
+                        u16* cells = (u16*)(tabs + incl - ((need + 15) & ~15u));
+                        zb_huf_fill(cells, ws, hlog, hns, rank, hshift, hbase);
+                        ZbHufTab t; t.cells = cells; t.log = hlog; t.shift = hshift; t.T = hT; t.base = hbase;
+                        if (!zb_huf_block(lits + lit_i, L.regen, hp, hleft, L.single, t)) { err = ZB_E_CORRUPTION; done = true; comp = false; }
+                        pending = false;
+                    }
+                    __syncwarp();
+                }
+            }
+            ZB_EMARK(3);
+            if (comp && B.lit_kind == ZB_LIT_SCRATCH) lit_i += (L.regen + 15) & ~15u;
+            // -- C: sequences section header
+            u32 nseq = 0, logLL = 0, logOF = 0, logML = 0, msLL = 0, msOF = 0, msML = 0, needS = 0;
+            short* const normLL = (short*)ws; short* const normOF = normLL + 36; short* const normML = normOF + 32;
+            if (comp) {
+                do {
+                    if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    nseq = *ip++;
+                    if (nseq > 0x7F) {
+                        if (nseq == 0xFF) { if (ip + 2 > bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
+                        else { if (ip >= bend) { err = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
+                    }
+                    B.n_seq = nseq;
+                    if (nseq == 0) { if (ip != bend) err = ZB_E_CORRUPTION; break; }
+                    if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const modes = *ip++;
+                    if (modes & 3) { err = ZB_E_CORRUPTION; break; }
+                    u32 nd; int r;
+                    r = zb_seq_desc(dLL, modes >> 6, 35, 9, ip, (u32)(bend - ip), fse_valid, normLL, logLL, msLL, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    r = zb_seq_desc(dOF, (modes >> 4) & 3, 31, 8, ip, (u32)(bend - ip), fse_valid, normOF, logOF, msOF, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    r = zb_seq_desc(dML, (modes >> 2) & 3, 52, 9, ip, (u32)(bend - ip), fse_valid, normML, logML, msML, nd);
+                    if (r < 0) { err = ZB_E_CORRUPTION; break; } ip += r; needS += nd;
+                    fse_valid = true;
+                } while (0);
+                if (err) { done = true; comp = false; nseq = 0; }
+            }
+            ZB_EMARK(4);
+            // -- D: build the three tables in the pool and run the sequence stream
+            u32 lit_used = 0, produced = 0;
+            {
+                bool pending = comp && nseq > 0;
+                while (__any_sync(0xFFFFFFFFu, pending)) {
+                    u32 const need = pending ? ((needS + 15) & ~15u) : 0;
+                    u32 const incl = zb_warp_incl_scan(need, lane);
+                    if (pending && incl <= TAB_BYTES) {
+                        u8* q = tabs + incl - need;
+                        ZbTab tLL, tOF, tML;
+                        auto setup = [&](const ZbTabSrc& d, short* norm, u32 ms, u32 lg, int kind, const ZbFseCell* dct, u32 dlog,
+                                         const ZbFseCell* def, u32 deflog, ZbTab& t) {
+                            if (d.kind == ZB_SRC_NCOUNT) { zb_build_fse((ZbFseCell*)q, norm, ms, lg, kind); t.t = (ZbFseCell*)q; t.log = lg; q += 4u << lg; }
+                            else if (d.kind == ZB_SRC_RLE) { *(ZbFseCell*)q = ZB_CELL(0, 0, zb_code_add_bits(d.sym, kind), d.sym); t.t = (ZbFseCell*)q; t.log = 0; q += 4; }
+                            else if (d.kind == ZB_SRC_DICT) { t.t = dct; t.log = dlog; }
+                            else { t.t = def; t.log = deflog; }
+                        };
+                        setup(dLL, normLL, msLL, logLL, K_LL, dict.ll, dict.ll_log, g_defLL, 6, tLL);
+                        setup(dOF, normOF, msOF, logOF, K_OF, dict.of, dict.of_log, g_defOF, 5, tOF);
+                        setup(dML, normML, msML, logML, K_ML, dict.ml, dict.ml_log, g_defML, 6, tML);
+
+                        // the 3-state FSE sequence stream (restates ZSTD_decodeSequence, zstd/zstd.c:46862-46986)
+                        ZbBitR b;
+                        if (!b.init(ip, (u32)(bend - ip))) err = ZB_E_CORRUPTION;
+                        else {
+                            u32 sLL = b.read(tLL.log); u32 sOF = b.read(tOF.log); b.refill(); u32 sML = b.read(tML.log); b.refill();
+                            const ZbFseCell* const TL = tLL.t; const ZbFseCell* const TO = tOF.t; const ZbFseCell* const TM = tML.t;
+                            u64 const room = cap - out_pos;
+                            ZbSeq* const sq = seqs + seq_i;
+                            for (u32 i = 0; i < nseq; i++) {
+                                u32 const cl = TL[sLL], co = TO[sOF], cm = TM[sML];
+                                u32 const ofc = ZB_CELL_SYM(co), llc = ZB_CELL_SYM(cl);
+                                u32 ll = lutLL[llc], ml = lutML[ZB_CELL_SYM(cm)], off;      // baselines: off the state chain
+                                // (a branch-free select chain over {rep0, rep1, rep2, rep0 - 1, new} was measured 3-5 % slower than this branch)
+                                if (ofc > 1) {
+                                    off = (1u << ofc) - 3 + b.read(ofc);
+                                    rep2 = rep1; rep1 = rep0; rep0 = off;
+                                } else {
+                                    u32 const ll0 = (llc == 0);
+                                    if (ofc == 0) {
+                                        if (ll0) { off = rep1; rep1 = rep0; rep0 = off; } else off = rep0;
+                                    } else {
+                                        u32 const idx = 1 + ll0 + b.read(1);
+                                        u32 tmp = idx == 1 ? rep1 : (idx == 2 ? rep2 : ((rep0 & 0x80000000u) ? rep0 + 1 : rep0 - 1));     // symbolic: one more off
+                                        if (tmp == 0) tmp = 0xFFFFFFFFu;
+                                        if (idx != 1) rep2 = rep1;
+                                        rep1 = rep0; rep0 = off = tmp;
+                                    }
+                                }
+                                b.refill();
+                                {   // ML then LL additional bits in one read (<= 32 bits)
+                                    u32 const llb = ZB_CELL_ADD(cl), both = b.read(ZB_CELL_ADD(cm) + llb);
+                                    ml += both >> llb; ll += both & ((1u << llb) - 1);
+                                }
+                                b.refill();
+                                if (i + 1 < nseq) {   // the three state updates (LL, ML, OF) in one read (<= 26 bits)
+                                    u32 const nl = ZB_CELL_NB(cl), nm = ZB_CELL_NB(cm), no = ZB_CELL_NB(co);
+                                    u32 const v = b.read(nl + nm + no);
+                                    sLL = ZB_CELL_NEXT(cl) + (v >> (nm + no));
+                                    sML = ZB_CELL_NEXT(cm) + ((v >> no) & ((1u << nm) - 1));
+                                    sOF = ZB_CELL_NEXT(co) + (v & ((1u << no) - 1));
+                                    b.refill();
+                                }
+                                sq[i] = make_uint4(lit_used, produced, ml, off);
+                                // the checks of ZSTD_execSequence / ZSTD_execSequenceEnd (zstd/zstd.c:46540-46728)
+                                if ((u64)produced + ll + ml > room) { err = ZB_E_DSTSIZE_TOO_SMALL; break; }
+                                if (ll > L.regen - lit_used) { err = ZB_E_CORRUPTION; break; }
+                                lit_used += ll; produced += ll;
+                                if ((u64)off > out_pos + produced + hist_extra) { err = ZB_E_CORRUPTION; break; }
+                                produced += ml;
+                            }
+                            if (!err && b.left() != 0) err = ZB_E_CORRUPTION;
+                        }
+                        if (err) { done = true; comp = false; }
+                        pending = false;
+                    }
+                    __syncwarp();
+                }
+            }
+            ZB_EMARK(5);
+            // -- E: close the block
+            if (!done) {
+                if (comp) {
+                    seqs[seq_i + nseq] = make_uint4(lit_used, produced, 0, 0);
+                    seq_i += nseq + 1;
+                    u32 const tail = L.regen - lit_used;
+                    if ((u64)produced + tail > cap - out_pos) err = ZB_E_DSTSIZE_TOO_SMALL;
+                    B.regen = produced + tail;
+                    if (!err && B.regen > block_max) err = ZB_E_CORRUPTION;
+                    pos += bsize;
+                }
+                if (!err) blocks[blk_i] = B;
+                done = true;                                          // one block per lane
+            }
+        }
+        if (lane < take && bi < n_blocks && !(D.flags & ZB_BD_SKIP)) {
+            ZbBlkExit X; X.rep[0] = rep0; X.rep[1] = rep1; X.rep[2] = rep2; X.err = err;
+            bexit[bi] = X;
+            if (err) atomicCAS(&status[D.frame], (u32)ZB_OK, err);
+        }
     }
 }
