@@ -8,6 +8,9 @@ LIB = os.path.join(HERE, "libzb200.so")
 SOURCES = ["zb_decode.cu", "zb_encode.cu", "zb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math"]
+if os.environ.get("ZB200_DEBUG_BLOCKS"):                 # debugging build of the block-parallel decode path (device printf)
+    NVCC_FLAGS.append("-DZB_DEBUG_BLOCKS")
+    LIB = os.path.join(HERE, "libzb200_dbg.so")
 TIMERS = bool(os.environ.get("ZB200_PHASE_TIMERS"))     # tuning builds only: per-phase clock64 counters inside the kernels;
 if TIMERS:                                              # they go to their own library (load it with ZB200_LIB=...)
     NVCC_FLAGS.append("-DZB_PHASE_TIMERS")
@@ -28,7 +31,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs, procs = [], []
     for src in SOURCES:                                  # the three translation units compile side by side
-        obj = os.path.join(CSRC, src.replace(".cu", ".timers.o" if TIMERS else ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", ".timers.o" if TIMERS else (".dbg.o" if os.environ.get("ZB200_DEBUG_BLOCKS") else ".o")))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)

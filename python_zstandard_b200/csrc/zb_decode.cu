@@ -13,6 +13,9 @@
 //   K4 zb_execute         one WARP per frame : the LZ copy-execute, lane per sequence with a
 //                          frontier test for match dependencies, coalesced copies for long runs.
 #include "zb_common.cuh"
+#ifdef ZB_DEBUG_BLOCKS
+#include <cstdio>
+#endif
 
 // ---------------------------------------------------------------------------
 // format constants (RFC 8878 3.1.1.3.2.1; reference zstd/zstd.c:15615-15659, :41266-41290)
@@ -382,6 +385,20 @@ struct ZbTab { const ZbFseCell* t; u32 log; };
 
 #include "zb_entropy.cuh"
 
+// one sequence table's source after this block's mode: the rules of zb_seq_desc, without building anything
+__device__ static u32 zb_scan_seq_table(ZbTabSrc& d, u32 mode, u32 kmax, u32 lmax, const u8*& ip, const u8* bend, bool fse_valid)
+{
+    if (mode == 0) d.kind = ZB_SRC_PREDEF;
+    else if (mode == 1) { if (ip >= bend || ip[0] > kmax) return ZB_E_CORRUPTION; d.kind = ZB_SRC_RLE; d.sym = ip[0]; ip++; }
+    else if (mode == 2) {
+        short nn[64]; u32 lg = 0, ms = kmax;
+        u32 const u = zb_read_ncount(nn, ms, lg, ip, (u32)(bend - ip));
+        if (u == 0 || lg > lmax) return ZB_E_CORRUPTION;
+        d.kind = ZB_SRC_NCOUNT; d.p = ip; d.n = u; ip += u;
+    } else if (!fse_valid || d.kind == ZB_SRC_NONE) return ZB_E_CORRUPTION;
+    return ZB_OK;
+}
+
 // ===========================================================================
 // Block-parallel path, K1b: zb_scan_blocks -- one thread per frame walks the block chain once more and writes, for every
 // block, what zb_entropy_blocks needs on entry: where the block sits, where its records go, and where the Huffman tree and
@@ -437,20 +454,10 @@ __global__ void zb_scan_blocks(const u8* __restrict__ src, const ZbSegment* __re
             if (nseq) {
                 if (ip + 1 > bend) { err = ZB_E_SRCSIZE_WRONG; break; }
                 u32 const modes = *ip++;
-                short nn[64]; u32 lg, ms;
-                ZbTabSrc* const dd[3] = {&dLL, &dOF, &dML};
-                u32 const kmax[3] = {35, 31, 52}, lmax[3] = {9, 8, 9};
-                for (int t = 0; t < 3 && !err; t++) {
-                    u32 const mode = (modes >> (6 - 2 * t)) & 3; ZbTabSrc& d = *dd[t];
-                    if (mode == 0) d.kind = ZB_SRC_PREDEF;
-                    else if (mode == 1) { if (ip >= bend || ip[0] > kmax[t]) { err = ZB_E_CORRUPTION; break; } d.kind = ZB_SRC_RLE; d.sym = ip[0]; ip++; }
-                    else if (mode == 2) {
-                        ms = kmax[t];
-                        u32 const u = zb_read_ncount(nn, ms, lg, ip, (u32)(bend - ip));
-                        if (u == 0 || lg > lmax[t]) { err = ZB_E_CORRUPTION; break; }
-                        d.kind = ZB_SRC_NCOUNT; d.p = ip; d.n = u; ip += u;
-                    } else if (!fse_valid || d.kind == ZB_SRC_NONE) { err = ZB_E_CORRUPTION; break; }
-                }
+                err = zb_scan_seq_table(dLL, modes >> 6, 35, 9, ip, bend, fse_valid);
+                if (!err) err = zb_scan_seq_table(dOF, (modes >> 4) & 3, 31, 8, ip, bend, fse_valid);
+                if (!err) err = zb_scan_seq_table(dML, (modes >> 2) & 3, 52, 9, ip, bend, fse_valid);
+                if (err) break;
                 fse_valid = true;
             }
         }
@@ -459,6 +466,9 @@ __global__ void zb_scan_blocks(const u8* __restrict__ src, const ZbSegment* __re
     }
     for (; b < b1; b++) { bdesc[b].flags = ZB_BD_SKIP; bdesc[b].frame = f; }      // (after an error; a healthy frame has none left)
     frame_end[f] = pos;
+#ifdef ZB_DEBUG_BLOCKS
+    if (err) printf("[scan_blocks] frame %u err %u at block %llu pos %llu\n", f, err, (unsigned long long)(b - b0), (unsigned long long)pos);
+#endif
     if (err) status[f] = err;
 }
 
@@ -507,6 +517,10 @@ __global__ void zb_resolve_blocks(const u8* __restrict__ src, const ZbSegment* _
             if (dst_sizes && out_pos != cap) err = ZB_E_SIZE_MISMATCH;
         }
     }
+#ifdef ZB_DEBUG_BLOCKS
+    if (err) printf("[resolve] frame %u err %u out_pos %llu content %llu cap %llu blocks %llu..%llu\n", f, err, (unsigned long long)out_pos,
+                    (unsigned long long)info[f].content_size, (unsigned long long)cap, (unsigned long long)b0, (unsigned long long)b1);
+#endif
     if (err) { status[f] = err; out_sizes[f] = err == ZB_E_SIZE_MISMATCH ? out_pos : 0; } else out_sizes[f] = out_pos;
 }
 
@@ -535,7 +549,13 @@ zb_patch_blocks(const ZbBlock* __restrict__ blocks, const ZbBlkDesc* __restrict_
             sq[i].w = r.w;
         }
         u64 const mstart = B.out_pos + r.y + (lit_next - r.x);            // frame-relative start of the match
-        if ((u64)r.w > mstart + dict.content_size) bad = true;
+        if ((u64)r.w > mstart + dict.content_size) {
+            bad = true;
+#ifdef ZB_DEBUG_BLOCKS
+            printf("[patch] block %llu seq %u off %u (raw %u) mstart %llu out_pos %llu e %u %u %u\n", (unsigned long long)b, i, r.w, sq[i].w, (unsigned long long)mstart,
+                   (unsigned long long)B.out_pos, e0, e1, e2);
+#endif
+        }
     }
     if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicCAS(&status[D.frame], (u32)ZB_OK, (u32)ZB_E_CORRUPTION);
 }

@@ -253,6 +253,8 @@ __device__ static int zb_seq_desc(ZbTabSrc& d, u32 mode, u32 max_sym_kind, u32 m
 #ifdef ZB_PHASE_TIMERS
 __device__ unsigned long long g_zb_ent_phase[8];
 #define ZB_EMARK(k) do { if (lane == 0) { long long const t_ = clock64(); atomicAdd(&g_zb_ent_phase[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
+#elif defined(ZB_DEBUG_BLOCKS)
+#define ZB_EMARK(k) do { if (err && !(t_ph & 1)) { printf("[emark %d] lane %u err %u\n", k, lane, err); t_ph |= 1; } } while (0)
 #else
 #define ZB_EMARK(k) do { (void)t_ph; } while (0)
 #endif
@@ -307,7 +309,7 @@ zb_entropy_decode(const u8* __restrict__ src, const ZbSegment* __restrict__ segs
         }
         u64 const hist_extra = dict.content_size;
 
-        long long t_ph = clock64();
+        long long t_ph = clock64() & ~1ll;
         // ---- one block per lane per round
         while (__any_sync(0xFFFFFFFFu, !done)) {
             ZB_EMARK(0);
@@ -591,7 +593,7 @@ zb_entropy_blocks(const u8* __restrict__ src, const ZbBlkDesc* __restrict__ bdes
         }
         u64 const hist_extra = 1ull << 40;                            // (no offset can fail the range check here)
 
-        long long t_ph = clock64();
+        long long t_ph = clock64() & ~1ll;
         // ---- one block per lane per round
         while (__any_sync(0xFFFFFFFFu, !done)) {
             ZB_EMARK(0);
@@ -805,6 +807,11 @@ zb_entropy_blocks(const u8* __restrict__ src, const ZbBlkDesc* __restrict__ bdes
         if (lane < take && bi < n_blocks && !(D.flags & ZB_BD_SKIP)) {
             ZbBlkExit X; X.rep[0] = rep0; X.rep[1] = rep1; X.rep[2] = rep2; X.err = err;
             bexit[bi] = X;
+#ifdef ZB_DEBUG_BLOCKS
+            if (err) printf("[entropy_blocks] block %u frame %u err %u flags %u span %u | huf k%u n%u | LL k%u n%u s%u | OF k%u n%u s%u | ML k%u n%u s%u | hdr %02x %02x %02x | LLp-src %lld\n", bi, D.frame, err, D.flags, D.span,
+                            D.dHuf.kind, D.dHuf.n, D.dLL.kind, D.dLL.n, D.dLL.sym, D.dOF.kind, D.dOF.n, D.dOF.sym, D.dML.kind, D.dML.n, D.dML.sym,
+                            src[D.hdr_off], src[D.hdr_off + 1], src[D.hdr_off + 2], D.dLL.p ? (long long)(D.dLL.p - src) : -1ll);
+#endif
             if (err) atomicCAS(&status[D.frame], (u32)ZB_OK, err);
         }
     }
