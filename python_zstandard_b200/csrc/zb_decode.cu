@@ -828,6 +828,144 @@ zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ pla
 // content checksum: low 32 bits of XXH64(seed 0) over the regenerated frame (zstd/zstd.c:44260-44277).
 // One lane per checksummed frame (the four accumulators are a serial chain over 32-byte stripes).
 // ===========================================================================
+// K4 (block-tile variant): frames of many blocks when few frames are in flight (the block-parallel path: one huge frame at
+// the limit).  zb_execute walks such a frame with one warp straight in HBM/L2 -- every batch of 32 sequences pays global
+// round trips: 1.5 ms per 128 KiB block.  Here the frame's CTA regenerates block after block in SHARED MEMORY (output tile
+// 128 KiB + the block's literals) and writes each finished block with 128-bit stores; only matches that reach in front of
+// the block read global memory (the frame's own earlier output, or the dictionary).
+// ===========================================================================
+#define ZB_BIG_LIT_CAP  (90u << 10)
+#define ZB_BIG_SMEM     (ZB_BLOCK_MAX + 64 + ZB_BIG_LIT_CAP + 64)
+
+__global__ void __launch_bounds__(32)
+zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
+               const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
+               u8* dst, u32 first, u32 n_frames, ZbDictDev dict, u64 min_cap)
+{
+    extern __shared__ __align__(16) u8 zb_big[];
+    u32 const lane = threadIdx.x & 31;
+    u32 const f = first + blockIdx.x;
+    if (f >= n_frames) return;
+    if (status[f] != ZB_OK) return;
+    ZbFramePlace const pl = place[f];
+    if (pl.dst_cap < min_cap) return;                    // staged whole by zb_execute_tile
+    u8* const out = dst + pl.dst_off;
+    u64 const blk_end = place[f + 1].blk_off;
+    const u8* const dict_end = dict.content + dict.content_size;
+    u8* const sl = zb_big + ZB_BLOCK_MAX + 64;           // literal stage (16-byte aligned)
+
+    for (u64 bi = pl.blk_off; bi < blk_end; bi++) {
+        ZbBlock const B = blocks[bi];
+        u8* const gout = out + B.out_pos;
+        if (B.kind == ZB_BLK_RAW) { zb_warp_copy(gout, src + B.src_pos, B.regen, lane); continue; }
+        if (B.kind == ZB_BLK_RLE) { for (u32 i = lane; i < B.regen; i += 32) gout[i] = (u8)B.lit_byte; continue; }
+        if (B.kind != ZB_BLK_COMPRESSED) return;
+        u32 const skew = (u32)((uintptr_t)gout & 15);    // same 16-byte phase in the tile as in dst
+        u8* const so = zb_big + skew;                    // so[i] = byte i of the block
+        long long const base = (long long)B.out_pos;     // frame-relative position of so[0]
+        bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
+        const u8* lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
+        if (!lit_rle && B.n_lit <= ZB_BIG_LIT_CAP) {     // the block's literals -> shared memory
+            if (B.lit_kind == ZB_LIT_SCRATCH) { const uint4* g = (const uint4*)lit; uint4* d4 = (uint4*)sl; for (u32 i = lane; i < (B.n_lit + 15) / 16; i += 32) d4[i] = g[i]; }
+            else for (u32 i = lane; i < B.n_lit; i += 32) sl[i] = lit[i];
+            lit = sl;
+        }
+        __syncwarp();
+        const ZbSeq* const sq = seqs + B.seq_pos;
+        u32 const nseq = B.n_seq;
+        ZbSeq rn = lane < nseq ? sq[lane] : make_uint4(0, 0, 0, 0);
+        for (u32 g = 0; g < nseq; g += 32) {
+            u32 const i = g + lane; bool const valid = i < nseq;
+            ZbSeq const r = rn;
+            if (g + 32 < nseq) rn = g + 32 + lane < nseq ? sq[g + 32 + lane] : make_uint4(0, 0, 0, 0);      // the next batch's records: off the critical path
+            u32 nx = __shfl_down_sync(0xFFFFFFFFu, r.x, 1);
+            if (lane == 31 || i + 1 >= nseq) nx = valid ? sq[i + 1].x : 0;
+            u32 const ll = nx - r.x, ml = r.z, off = r.w;
+            u32 const ostart = r.y, mstart = r.y + ll;
+            if (valid) {
+                u8* o = so + ostart;
+                if (lit_rle) for (u32 k = 0; k < ll; k++) o[k] = lit_byte;
+                else zb_copy_fwd8(o, lit + r.x, ll);
+            }
+            __syncwarp();
+            bool pending = valid;
+            int const m = (int)mstart;                                  // block-relative match start
+            long long const srcp = (long long)m - (long long)off;       // block-relative source: negative = in front of the block
+            int const need = (int)min(srcp + (long long)ml, (long long)ostart);
+            for (;;) {
+                u32 const pm = __ballot_sync(0xFFFFFFFFu, pending);
+                if (!pm) break;
+                int const fu = __ffs(pm) - 1;
+                int const F = __shfl_sync(0xFFFFFFFFu, m, fu);
+                bool const ready = pending && need <= F;
+                u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 32);
+                while (big) {          // long matches: the whole warp copies
+                    int const l = __ffs(big) - 1; big &= big - 1;
+                    int const m0 = __shfl_sync(0xFFFFFFFFu, m, l);
+                    u32 const o = __shfl_sync(0xFFFFFFFFu, off, l), len = __shfl_sync(0xFFFFFFFFu, ml, l);
+                    u8* d = so + m0;
+                    if ((long long)o > (long long)m0) {                 // starts in front of the block: byte-wise with the source select
+                        for (u32 j = lane; j < len; j += 32) {
+                            long long const sp = (long long)m0 - (long long)o + (long long)(j % o);
+                            u8 v;
+                            if (sp >= 0) v = so[sp];
+                            else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                            d[j] = v;
+                        }
+                    } else if (o >= 32) {
+                        const u8* sp = d - o;
+                        for (u32 j = 0; j < len; j += 32) { if (j + lane < len) d[j + lane] = sp[j + lane]; __syncwarp(); }
+                    } else {
+                        const u8* sp = d - o;
+                        for (u32 j = lane; j < len; j += 32) d[j] = sp[j % o];
+                    }
+                    __syncwarp();
+                }
+                if (ready) {
+                    if (ml < 32) {
+                        u8* d = so + m;
+                        if (srcp >= 0) {
+                            const u8* sp = so + srcp;
+                            if (off >= 8) zb_copy_fwd8(d, sp, ml);      // 8-byte chunks never read their own output
+                            else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
+                        } else {
+                            for (u32 k = 0; k < ml; k++) {
+                                long long const sp = srcp + (long long)(k % off);
+                                u8 v;
+                                if (sp >= 0) v = so[sp];
+                                else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                                d[k] = v;
+                            }
+                        }
+                    }
+                    pending = false;
+                }
+                __syncwarp();
+            }
+        }
+        {   // last literals of the block
+            ZbSeq const e = sq[nseq];
+            u32 const tail = B.n_lit - e.x;
+            if (lit_rle) { for (u32 k = lane; k < tail; k += 32) so[e.y + k] = lit_byte; }
+            else for (u32 k = lane; k < tail; k += 32) so[e.y + k] = lit[e.x + k];
+        }
+        __syncwarp();
+        {   // finished block -> HBM, 128-bit stores (so and gout share the same 16-byte phase)
+            u32 const total = B.regen;
+            u32 head = (16 - skew) & 15; if (head > total) head = total;
+            if (lane < head) gout[lane] = so[lane];
+            u32 const nv = (total - head) >> 4;
+            const uint4* s4 = (const uint4*)(so + head); uint4* d4 = (uint4*)(gout + head);
+            for (u32 i = lane; i < nv; i += 32) d4[i] = s4[i];
+            u32 const done = head + (nv << 4);
+            if (done + lane < total) gout[done + lane] = so[done + lane];
+        }
+        __threadfence();          // later blocks of this frame read these bytes through L2 (__ldcg)
+        __syncwarp();
+    }
+}
+
+// ===========================================================================
 __device__ static u64 zb_xxh64(const u8* p, u64 len)
 {
     u64 const P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
@@ -978,6 +1116,18 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
         zb_entropy_decode<7><<<n_ctas, 7 * 32, ZB_ENT_SMEM(7), st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
                                                                     work_counter, dict, status, out_sizes, ck_expect, take);
     }
+}
+
+void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
+                           const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st)
+{
+    // the block-parallel path: few frames of many blocks.  Small frames as always, the others a CTA (one warp, 219 KB of shared memory) each
+    cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM);
+    cudaFuncSetAttribute(zb_execute_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZB_BIG_SMEM);
+    u32 const n = end - first;
+    zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
+                                                                                                 seqs, lits, dst, first, end, dict);
+    zb_execute_big<<<n, 32, ZB_BIG_SMEM, st>>>(src, place, status, blocks, seqs, lits, dst, first, end, dict, (u64)ZB_TILE_CAP + 1);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
