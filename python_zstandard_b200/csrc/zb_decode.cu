@@ -836,14 +836,19 @@ zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ pla
 // ===========================================================================
 #define ZB_BIG_LIT_CAP  (90u << 10)
 #define ZB_BIG_SMEM     (ZB_BLOCK_MAX + 64 + ZB_BIG_LIT_CAP + 64)
+#define ZB_BIG_NT       512
 
-__global__ void __launch_bounds__(32)
+// One CTA of 16 warps per frame.  Sequences are taken 512 at a time, a thread each: all literal runs first (independent),
+// then rounds over the matches: a match may run when every byte it reads lies below F, the start of the first unfinished
+// match of the 512 (a CTA-wide minimum per round); matches of 32 bytes and more are copied by their whole warp.
+__global__ void __launch_bounds__(ZB_BIG_NT)
 zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
                const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
                u8* dst, u32 first, u32 n_frames, ZbDictDev dict, u64 min_cap)
 {
     extern __shared__ __align__(16) u8 zb_big[];
-    u32 const lane = threadIdx.x & 31;
+    __shared__ int s_min[ZB_BIG_NT / 32];
+    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u32 const f = first + blockIdx.x;
     if (f >= n_frames) return;
     if (status[f] != ZB_OK) return;
@@ -857,46 +862,56 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
     for (u64 bi = pl.blk_off; bi < blk_end; bi++) {
         ZbBlock const B = blocks[bi];
         u8* const gout = out + B.out_pos;
-        if (B.kind == ZB_BLK_RAW) { zb_warp_copy(gout, src + B.src_pos, B.regen, lane); continue; }
-        if (B.kind == ZB_BLK_RLE) { for (u32 i = lane; i < B.regen; i += 32) gout[i] = (u8)B.lit_byte; continue; }
+        if (B.kind == ZB_BLK_RAW) { const u8* p = src + B.src_pos; for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = p[i]; continue; }
+        if (B.kind == ZB_BLK_RLE) { for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = (u8)B.lit_byte; continue; }
         if (B.kind != ZB_BLK_COMPRESSED) return;
         u32 const skew = (u32)((uintptr_t)gout & 15);    // same 16-byte phase in the tile as in dst
         u8* const so = zb_big + skew;                    // so[i] = byte i of the block
         long long const base = (long long)B.out_pos;     // frame-relative position of so[0]
         bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
         const u8* lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
+        __syncthreads();                                  // (the tile and the literal stage are free again)
         if (!lit_rle && B.n_lit <= ZB_BIG_LIT_CAP) {     // the block's literals -> shared memory
-            if (B.lit_kind == ZB_LIT_SCRATCH) { const uint4* g = (const uint4*)lit; uint4* d4 = (uint4*)sl; for (u32 i = lane; i < (B.n_lit + 15) / 16; i += 32) d4[i] = g[i]; }
-            else for (u32 i = lane; i < B.n_lit; i += 32) sl[i] = lit[i];
+            if (B.lit_kind == ZB_LIT_SCRATCH) { const uint4* g = (const uint4*)lit; uint4* d4 = (uint4*)sl; for (u32 i = tid; i < (B.n_lit + 15) / 16; i += ZB_BIG_NT) d4[i] = g[i]; }
+            else for (u32 i = tid; i < B.n_lit; i += ZB_BIG_NT) sl[i] = lit[i];
             lit = sl;
         }
-        __syncwarp();
+        __syncthreads();
         const ZbSeq* const sq = seqs + B.seq_pos;
         u32 const nseq = B.n_seq;
-        ZbSeq rn = lane < nseq ? sq[lane] : make_uint4(0, 0, 0, 0);
-        for (u32 g = 0; g < nseq; g += 32) {
-            u32 const i = g + lane; bool const valid = i < nseq;
-            ZbSeq const r = rn;
-            if (g + 32 < nseq) rn = g + 32 + lane < nseq ? sq[g + 32 + lane] : make_uint4(0, 0, 0, 0);      // the next batch's records: off the critical path
-            u32 nx = __shfl_down_sync(0xFFFFFFFFu, r.x, 1);
-            if (lane == 31 || i + 1 >= nseq) nx = valid ? sq[i + 1].x : 0;
-            u32 const ll = nx - r.x, ml = r.z, off = r.w;
+        ZbSeq rn = tid < nseq ? sq[tid] : make_uint4(0, 0, 0, 0);
+        u32 rn_next = tid + 1 <= nseq ? sq[tid + 1 <= nseq ? tid + 1 : nseq].x : 0;
+        for (u32 g = 0; g < nseq; g += ZB_BIG_NT) {
+            u32 const i = g + tid; bool const valid = i < nseq;
+            ZbSeq const r = rn; u32 const nx = rn_next;
+            if (g + ZB_BIG_NT < nseq) {                   // the next round's records: off the critical path
+                u32 const j = g + ZB_BIG_NT + tid;
+                rn = j < nseq ? sq[j] : make_uint4(0, 0, 0, 0);
+                rn_next = j < nseq ? sq[j + 1].x : 0;
+            }
+            u32 const ll = valid ? nx - r.x : 0, ml = r.z, off = r.w;
             u32 const ostart = r.y, mstart = r.y + ll;
             if (valid) {
                 u8* o = so + ostart;
                 if (lit_rle) for (u32 k = 0; k < ll; k++) o[k] = lit_byte;
                 else zb_copy_fwd8(o, lit + r.x, ll);
             }
-            __syncwarp();
             bool pending = valid;
             int const m = (int)mstart;                                  // block-relative match start
             long long const srcp = (long long)m - (long long)off;       // block-relative source: negative = in front of the block
             int const need = (int)min(srcp + (long long)ml, (long long)ostart);
             for (;;) {
-                u32 const pm = __ballot_sync(0xFFFFFFFFu, pending);
-                if (!pm) break;
-                int const fu = __ffs(pm) - 1;
-                int const F = __shfl_sync(0xFFFFFFFFu, m, fu);
+                // F: the start of the first unfinished match of the round
+                int mn = pending ? m : 0x7FFFFFFF;
+                #pragma unroll
+                for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+                __syncthreads();                          // literals / the previous round's copies are in place; s_min is free
+                if (lane == 0) s_min[warp] = mn;
+                __syncthreads();
+                int F = 0x7FFFFFFF;
+                #pragma unroll
+                for (int w = 0; w < ZB_BIG_NT / 32; w++) F = min(F, s_min[w]);
+                if (F == 0x7FFFFFFF) break;
                 bool const ready = pending && need <= F;
                 u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 32);
                 while (big) {          // long matches: the whole warp copies
@@ -940,28 +955,27 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                     }
                     pending = false;
                 }
-                __syncwarp();
             }
         }
+        __syncthreads();
         {   // last literals of the block
             ZbSeq const e = sq[nseq];
             u32 const tail = B.n_lit - e.x;
-            if (lit_rle) { for (u32 k = lane; k < tail; k += 32) so[e.y + k] = lit_byte; }
-            else for (u32 k = lane; k < tail; k += 32) so[e.y + k] = lit[e.x + k];
+            if (lit_rle) { for (u32 k = tid; k < tail; k += ZB_BIG_NT) so[e.y + k] = lit_byte; }
+            else for (u32 k = tid; k < tail; k += ZB_BIG_NT) so[e.y + k] = lit[e.x + k];
         }
-        __syncwarp();
+        __syncthreads();
         {   // finished block -> HBM, 128-bit stores (so and gout share the same 16-byte phase)
             u32 const total = B.regen;
             u32 head = (16 - skew) & 15; if (head > total) head = total;
-            if (lane < head) gout[lane] = so[lane];
+            if (tid < head) gout[tid] = so[tid];
             u32 const nv = (total - head) >> 4;
             const uint4* s4 = (const uint4*)(so + head); uint4* d4 = (uint4*)(gout + head);
-            for (u32 i = lane; i < nv; i += 32) d4[i] = s4[i];
+            for (u32 i = tid; i < nv; i += ZB_BIG_NT) d4[i] = s4[i];
             u32 const done = head + (nv << 4);
-            if (done + lane < total) gout[done + lane] = so[done + lane];
+            if (done + tid < total) gout[done + tid] = so[done + tid];
         }
         __threadfence();          // later blocks of this frame read these bytes through L2 (__ldcg)
-        __syncwarp();
     }
 }
 
@@ -1121,13 +1135,13 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
 void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
                            const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st)
 {
-    // the block-parallel path: few frames of many blocks.  Small frames as always, the others a CTA (one warp, 219 KB of shared memory) each
+    // the block-parallel path: few frames of many blocks.  Small frames as always, the others a CTA (16 warps, 219 KB of shared memory) each
     cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM);
     cudaFuncSetAttribute(zb_execute_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZB_BIG_SMEM);
     u32 const n = end - first;
     zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
                                                                                                  seqs, lits, dst, first, end, dict);
-    zb_execute_big<<<n, 32, ZB_BIG_SMEM, st>>>(src, place, status, blocks, seqs, lits, dst, first, end, dict, (u64)ZB_TILE_CAP + 1);
+    zb_execute_big<<<n, ZB_BIG_NT, ZB_BIG_SMEM, st>>>(src, place, status, blocks, seqs, lits, dst, first, end, dict, (u64)ZB_TILE_CAP + 1);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,

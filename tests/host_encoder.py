@@ -330,7 +330,7 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     else if (warps == 8) simt::launch(n_ctas, 8 * 32, [&] { zb_entropy_decode<8>(src, segs.data(), n, place.data(), dst_sizes, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
     else simt::launch(n_ctas, 7 * 32, [&] { zb_entropy_decode<7>(src, segs.data(), n, place.data(), dst_sizes, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
     simt::launch((n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, [&] { zb_execute_tile(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict); });
-    if (g_block_path) simt::launch(n, 32, [&] { zb_execute_big(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict, (u64)ZB_TILE_CAP + 1); });
+    if (g_block_path) simt::launch(n, ZB_BIG_NT, [&] { zb_execute_big(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict, (u64)ZB_TILE_CAP + 1); });
     else simt::launch((n + 7) / 8, 256, [&] { zb_execute(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict, (u64)ZB_TILE_CAP + 1); });
     if (totals[4]) simt::launch((n + 127) / 128, 128, [&] { zb_verify_checksums(out, place.data(), out_sizes.data(), info.data(), ck.data(), 0, n, status.data()); });
     std::vector<ZbSegment> out_segs(n); u32 first_error = 0xFFFFFFFFu;
