@@ -839,15 +839,18 @@ zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ pla
 #define ZB_BIG_NT       512
 
 // One CTA of 16 warps per frame.  Sequences are taken 512 at a time, a thread each: all literal runs first (independent),
-// then rounds over the matches: a match may run when every byte it reads lies below F, the start of the first unfinished
-// match of the 512 (a CTA-wide minimum per round); matches of 32 bytes and more are copied by their whole warp.
+// then rounds over the matches: a match may run when the matches of this round that OVERLAP ITS SOURCE are finished (their
+// index range comes from two binary searches over the round's match starts / ends, a done-bitmap tells the rest), so the
+// number of rounds is the depth of the dependency chains, not their count; matches of 32 bytes and more are copied by
+// their whole warp.
 __global__ void __launch_bounds__(ZB_BIG_NT)
 zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
                const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
                u8* dst, u32 first, u32 n_frames, ZbDictDev dict, u64 min_cap)
 {
     extern __shared__ __align__(16) u8 zb_big[];
-    __shared__ int s_min[ZB_BIG_NT / 32];
+    __shared__ int s_m[ZB_BIG_NT], s_e[ZB_BIG_NT];       // match start / end of every sequence of the round (block-relative)
+    __shared__ u32 s_done[ZB_BIG_NT / 32];
     u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u32 const f = first + blockIdx.x;
     if (f >= n_frames) return;
@@ -899,20 +902,26 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
             bool pending = valid;
             int const m = (int)mstart;                                  // block-relative match start
             long long const srcp = (long long)m - (long long)off;       // block-relative source: negative = in front of the block
-            int const need = (int)min(srcp + (long long)ml, (long long)ostart);
+            __syncthreads();                                            // (the previous round is over: s_m / s_e / s_done are free)
+            s_m[tid] = valid ? m : 0x7FFFFFFF; s_e[tid] = valid ? m + (int)ml : 0x7FFFFFFF;
+            if (tid < ZB_BIG_NT / 32) s_done[tid] = 0;
+            __syncthreads();                                            // literals of the round are in place, too
+            // the matches of this round my source overlaps: [ja, jb) -- ends above my source start, starts below my source end
+            u32 ja = 0, jb = 0;
+            if (valid) {
+                long long const s_lo = srcp, s_hi = min(srcp + (long long)ml, (long long)m);
+                { u32 lo = 0, hi = tid; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)s_e[md] > s_lo) hi = md; else lo = md + 1; } ja = lo; }
+                { u32 lo = ja, hi = tid; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)s_m[md] >= s_hi) hi = md; else lo = md + 1; } jb = lo; }
+            }
             for (;;) {
-                // F: the start of the first unfinished match of the round
-                int mn = pending ? m : 0x7FFFFFFF;
-                #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-                __syncthreads();                          // literals / the previous round's copies are in place; s_min is free
-                if (lane == 0) s_min[warp] = mn;
-                __syncthreads();
-                int F = 0x7FFFFFFF;
-                #pragma unroll
-                for (int w = 0; w < ZB_BIG_NT / 32; w++) F = min(F, s_min[w]);
-                if (F == 0x7FFFFFFF) break;
-                bool const ready = pending && need <= F;
+                bool ready = pending;
+                if (pending && jb > ja) {
+                    for (u32 w = ja >> 5; w <= (jb - 1) >> 5; w++) {
+                        u32 const lo_b = w == (ja >> 5) ? (ja & 31) : 0u, hi_b = w == ((jb - 1) >> 5) ? ((jb - 1) & 31) : 31u;
+                        u32 const mask = (0xFFFFFFFFu << lo_b) & (0xFFFFFFFFu >> (31 - hi_b));
+                        if ((s_done[w] & mask) != mask) { ready = false; break; }
+                    }
+                }
                 u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 32);
                 while (big) {          // long matches: the whole warp copies
                     int const l = __ffs(big) - 1; big &= big - 1;
@@ -954,7 +963,9 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                         }
                     }
                     pending = false;
+                    atomicOr(&s_done[warp], 1u << lane);
                 }
+                if (!__syncthreads_or(pending ? 1 : 0)) break;          // (also: this round's copies and done bits are visible)
             }
         }
         __syncthreads();
