@@ -952,6 +952,18 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                             const u8* sp = so + srcp;
                             if (off >= 8) zb_copy_fwd8(d, sp, ml);      // 8-byte chunks never read their own output
                             else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
+                        } else if (off >= ml) {
+                            // the source starts in front of the block and does not overlap the match: ALL loads first (the
+                            // global ones cost ~700 cycles each when they wait for one another), then the stores
+                            u8 t[32];
+                            #pragma unroll
+                            for (u32 k = 0; k < 32; k++) if (k < ml) {
+                                long long const sp = srcp + (long long)k;
+                                if (sp >= 0) t[k] = so[sp];
+                                else { long long const fp = base + sp; t[k] = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                            }
+                            #pragma unroll
+                            for (u32 k = 0; k < 32; k++) if (k < ml) d[k] = t[k];
                         } else {
                             for (u32 k = 0; k < ml; k++) {
                                 long long const sp = srcp + (long long)(k % off);
