@@ -914,10 +914,6 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                 { u32 lo = ja, hi = tid; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)s_m[md] >= s_hi) hi = md; else lo = md + 1; } jb = lo; }
             }
             for (;;) {
-              // inner rounds: what a warp's own lanes unlock for one another is settled with warp synchronisation only (most
-              // short-distance dependencies point at the few sequences right in front); the CTA-wide round follows when no
-              // lane of the warp can move
-              for (;;) {
                 bool ready = pending;
                 if (pending && jb > ja) {
                     for (u32 w = ja >> 5; w <= (jb - 1) >> 5; w++) {
@@ -981,9 +977,6 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                     pending = false;
                     atomicOr(&s_done[warp], 1u << lane);
                 }
-                __syncwarp();
-                if (!__any_sync(0xFFFFFFFFu, ready)) break;
-              }
                 if (!__syncthreads_or(pending ? 1 : 0)) break;          // (also: this round's copies and done bits are visible)
             }
         }
