@@ -955,15 +955,21 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                         } else if (off >= ml) {
                             // the source starts in front of the block and does not overlap the match: ALL loads first (the
                             // global ones cost ~700 cycles each when they wait for one another), then the stores
-                            u8 t[32];
-                            #pragma unroll
-                            for (u32 k = 0; k < 32; k++) if (k < ml) {
-                                long long const sp = srcp + (long long)k;
-                                if (sp >= 0) t[k] = so[sp];
-                                else { long long const fp = base + sp; t[k] = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                            for (u32 k0 = 0; k0 < ml; k0 += 8) {          // eight at a time
+                                u8 t[8];
+                                #pragma unroll
+                                for (u32 q = 0; q < 8; q++) {
+                                    long long const sp = srcp + (long long)(k0 + q);
+                                    u8 v = 0;
+                                    if (k0 + q < ml) {
+                                        if (sp >= 0) v = so[sp];
+                                        else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                                    }
+                                    t[q] = v;
+                                }
+                                #pragma unroll
+                                for (u32 q = 0; q < 8; q++) if (k0 + q < ml) d[k0 + q] = t[q];
                             }
-                            #pragma unroll
-                            for (u32 k = 0; k < 32; k++) if (k < ml) d[k] = t[k];
                         } else {
                             for (u32 k = 0; k < ml; k++) {
                                 long long const sp = srcp + (long long)(k % off);
