@@ -276,9 +276,18 @@ def run_large_frame_arm(zstd, ref):
     t = corpus.text_corpus(8 << 20)
     data = np.tile(t, (mb << 20) // len(t) + 1)[:mb << 20].tobytes()
     frame = ref.compress(data, level=3)
-    t0 = time.perf_counter(); back = ref.decompress(frame, len(data)); tcpu = time.perf_counter() - t0
-    assert back == data
-    del back
+    import ctypes as C
+    Z = ref.Z
+    dc = Z.ZSTD_createDCtx()
+    outbuf = np.empty(len(data), dtype=np.uint8); outbuf[:] = 0          # pages touched before the clock starts
+    tcpu = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter()
+        got = Z.ZSTD_decompressDCtx(dc, C.c_void_p(outbuf.ctypes.data), len(data), frame, len(frame))
+        tcpu = min(tcpu, time.perf_counter() - t0)
+    Z.ZSTD_freeDCtx(dc)
+    assert got == len(data) and outbuf.tobytes() == data
+    del outbuf
     d = zstd.ZstdDecompressor(max_window_size=1 << 31)
     best = 1e9
     for _ in range(3):

@@ -34,8 +34,10 @@ void zb_launch_place(const ZbFrameInfo* info, const u64* dst_sizes, u32 n, ZbFra
 void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const u64* dst_sizes,
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                        ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, u32 warps, cudaStream_t st);
-void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
-                           const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st);
+size_t zb_wave_bytes(u64 n_frames, u64 n_blocks);
+void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
+                           const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, u64 blk_first, u64 blk_last,
+                           u64 n_frames, u64 n_blocks, void* wave_mem, u32 n_ctas, ZbDictDev dict, cudaStream_t st);
 void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_sizes, const ZbFrameInfo* info, const u32* ck_expect,
                       u32 first, u32 end, u32* status, cudaStream_t st);
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
@@ -98,7 +100,7 @@ struct zb200_ctx {
     // device arenas (grow-only)
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
     DevBuf jobs, seginfo, slots, bouts, escratch, fsizes, ck;
-    DevBuf bdesc, bexit, erep, fend;          // block-parallel decode path
+    DevBuf bdesc, bexit, erep, fend, wave;    // block-parallel decode path
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -408,6 +410,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         CK(ctx->bexit.ensure((nb + 1) * zb_blkexit_bytes()));
         CK(ctx->erep.ensure((nb + 1) * 3 * sizeof(u32)));
         CK(ctx->fend.ensure(n * sizeof(u64)));
+        CK(ctx->wave.ensure(zb_wave_bytes(nf, nb)));
         { KSpan s(ctx, ZB200_K_SCAN);
           zb_launch_scan_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), dd, ctx->status.as<u32>(), ctx->bdesc.p, ctx->fend.as<u64>(), ctx->stream); }
         u32 const take = 3, EW = 7;
@@ -442,8 +445,10 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
                             ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, EW, ctx->stream); }
         { KSpan s(ctx, ZB200_K_EXECUTE);
-          if (block_path) zb_launch_execute_big(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
-                                                ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out, f0, f1, dd, ctx->stream);
+          if (block_path) zb_launch_execute_big(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(), ctx->bdesc.p,
+                                                ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out, f0, f1,
+                                                n_chunks > 1 ? cpl[k].blk_off : 0, n_chunks > 1 ? cpl[k + 1].blk_off : totals[1],
+                                                nf, totals[1], ctx->wave.p, ctas, dd, ctx->stream);
           else zb_launch_execute(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(),
                                  ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out, f0, f1, dd, ctx->stream); }
         if (totals[4]) { KSpan s(ctx, ZB200_K_VERIFY);

@@ -834,156 +834,230 @@ zb_execute_tile(const u8* __restrict__ src, const ZbFramePlace* __restrict__ pla
 // 128 KiB + the block's literals) and writes each finished block with 128-bit stores; only matches that reach in front of
 // the block read global memory (the frame's own earlier output, or the dictionary).
 // ===========================================================================
-#define ZB_BIG_LIT_CAP  (90u << 10)
-#define ZB_BIG_SMEM     (ZB_BLOCK_MAX + 64 + ZB_BIG_LIT_CAP + 64)
 #define ZB_BIG_NT       512
+#define ZB_BIG_SEQCAP   6144u                      // sequences in flight at once (a block with more runs in chunks)
+#define ZB_BIG_PER      (ZB_BIG_SEQCAP / ZB_BIG_NT)
+#define ZB_BIG_SMEM     (ZB_BLOCK_MAX + 64 + (4 * ZB_BIG_SEQCAP + 4 + ZB_BIG_SEQCAP / 32) * 4)
 
-// One CTA of 16 warps per frame.  Sequences are taken 512 at a time, a thread each: all literal runs first (independent),
-// then rounds over the matches: a match may run when the matches of this round that OVERLAP ITS SOURCE are finished (their
-// index range comes from two binary searches over the round's match starts / ends, a done-bitmap tells the rest), so the
-// number of rounds is the depth of the dependency chains, not their count; matches of 32 bytes and more are copied by
-// their whole warp.
+// A persistent grid of CTAs (16 warps each) takes the BLOCKS of all frames in order from a ticket counter -- the blocks of one
+// frame run on many SMs at once, each in its own 128 KiB shared-memory tile.  Inside a block up to 6144 sequences are IN
+// FLIGHT together, 12 per thread: all literal runs are copied first (independent, straight from the literal buffer), then
+// every warp sweeps over its pending matches without CTA barriers.  A match runs when
+//   * the matches of the block that OVERLAP ITS SOURCE are finished: their index range [ja, jb) comes from two binary
+//     searches over the sorted sequence starts / match starts, a done-bitmap in shared memory tells the rest -- so the
+//     number of sweeps is the depth of the dependency chains, not their count;
+//   * the part of its source in front of the block is final in global memory: the frame's FINISHED PREFIX (wave.done_pos:
+//     every block below it is stored and fenced) covers it.
+// Matches of 64 bytes and more are copied by their whole warp.  Matches only point backwards and tickets are handed out in
+// order, so the lowest unfinished block never waits: no deadlock for any grid size.
+__device__ __forceinline__ u32 zb_warp_or(u32 v)
+{
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+struct ZbWave {                     // zeroed before every launch
+    unsigned long long* done_pos;   // per frame: output bytes [0, done_pos) are final in global memory
+    u32* pre_blk;                   // per frame: blocks [0, pre_blk) of the frame are finished
+    u32* blk_flag;                  // per block (absolute index): finished
+    u32* ticket;                    // next block to hand out, relative to blk_first
+};
+
 __global__ void __launch_bounds__(ZB_BIG_NT)
 zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
-               const ZbBlock* __restrict__ blocks, const ZbSeq* __restrict__ seqs, const u8* __restrict__ lits,
-               u8* dst, u32 first, u32 n_frames, ZbDictDev dict, u64 min_cap)
+               const ZbBlock* __restrict__ blocks, const ZbBlkDesc* __restrict__ bdesc, const ZbSeq* __restrict__ seqs,
+               const u8* __restrict__ lits, u8* dst, u64 blk_first, u64 blk_last, ZbDictDev dict, u64 min_cap, ZbWave wave)
 {
     extern __shared__ __align__(16) u8 zb_big[];
-    __shared__ int s_m[ZB_BIG_NT], s_e[ZB_BIG_NT];       // match start / end of every sequence of the round (block-relative)
-    __shared__ u32 s_done[ZB_BIG_NT / 32];
-    u32 const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    u32 const f = first + blockIdx.x;
-    if (f >= n_frames) return;
-    if (status[f] != ZB_OK) return;
-    ZbFramePlace const pl = place[f];
-    if (pl.dst_cap < min_cap) return;                    // staged whole by zb_execute_tile
-    u8* const out = dst + pl.dst_off;
-    u64 const blk_end = place[f + 1].blk_off;
+    __shared__ u32 s_ticket;
+    u32 const tid = threadIdx.x, lane = tid & 31;
     const u8* const dict_end = dict.content + dict.content_size;
-    u8* const sl = zb_big + ZB_BLOCK_MAX + 64;           // literal stage (16-byte aligned)
+    u32* const sO = (u32*)(zb_big + ZB_BLOCK_MAX + 64);  // [SEQCAP + 1] output start of every sequence of the chunk (block-relative)
+    u32* const sM = sO + ZB_BIG_SEQCAP + 4;              // [SEQCAP] its match start
+    u32* const sF = sM + ZB_BIG_SEQCAP;                  // [SEQCAP] its offset
+    u32* const sD = sF + ZB_BIG_SEQCAP;                  // [SEQCAP] ja | jb << 14 | (source in front of the block) << 31
+    u32* const sB = sD + ZB_BIG_SEQCAP;                  // [SEQCAP / 32] done bitmap
 
-    for (u64 bi = pl.blk_off; bi < blk_end; bi++) {
+    for (;;) {
+        __syncthreads();                                  // (s_ticket and the tile are free again)
+        if (tid == 0) s_ticket = atomicAdd(wave.ticket, 1u);
+        __syncthreads();
+        u64 const bi = blk_first + s_ticket;
+        if (bi >= blk_last) return;
+        u32 const f = bdesc[bi].frame;
+        if (status[f] != ZB_OK) continue;
+        ZbFramePlace const pl = place[f];
+        if (pl.dst_cap < min_cap) continue;              // staged whole by zb_execute_tile
+        u8* const out = dst + pl.dst_off;
         ZbBlock const B = blocks[bi];
         u8* const gout = out + B.out_pos;
-        if (B.kind == ZB_BLK_RAW) { const u8* p = src + B.src_pos; for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = p[i]; continue; }
-        if (B.kind == ZB_BLK_RLE) { for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = (u8)B.lit_byte; continue; }
-        if (B.kind != ZB_BLK_COMPRESSED) return;
+        if (B.kind == ZB_BLK_RAW) { const u8* p = src + B.src_pos; for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = p[i]; }
+        else if (B.kind == ZB_BLK_RLE) { for (u32 i = tid; i < B.regen; i += ZB_BIG_NT) gout[i] = (u8)B.lit_byte; }
+        else if (B.kind == ZB_BLK_COMPRESSED) {
         u32 const skew = (u32)((uintptr_t)gout & 15);    // same 16-byte phase in the tile as in dst
         u8* const so = zb_big + skew;                    // so[i] = byte i of the block
         long long const base = (long long)B.out_pos;     // frame-relative position of so[0]
         bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
-        const u8* lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
-        __syncthreads();                                  // (the tile and the literal stage are free again)
-        if (!lit_rle && B.n_lit <= ZB_BIG_LIT_CAP) {     // the block's literals -> shared memory
-            if (B.lit_kind == ZB_LIT_SCRATCH) { const uint4* g = (const uint4*)lit; uint4* d4 = (uint4*)sl; for (u32 i = tid; i < (B.n_lit + 15) / 16; i += ZB_BIG_NT) d4[i] = g[i]; }
-            else for (u32 i = tid; i < B.n_lit; i += ZB_BIG_NT) sl[i] = lit[i];
-            lit = sl;
-        }
-        __syncthreads();
+        const u8* const lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
         const ZbSeq* const sq = seqs + B.seq_pos;
         u32 const nseq = B.n_seq;
-        ZbSeq rn = tid < nseq ? sq[tid] : make_uint4(0, 0, 0, 0);
-        u32 rn_next = tid + 1 <= nseq ? sq[tid + 1 <= nseq ? tid + 1 : nseq].x : 0;
-        for (u32 g = 0; g < nseq; g += ZB_BIG_NT) {
-            u32 const i = g + tid; bool const valid = i < nseq;
-            ZbSeq const r = rn; u32 const nx = rn_next;
-            if (g + ZB_BIG_NT < nseq) {                   // the next round's records: off the critical path
-                u32 const j = g + ZB_BIG_NT + tid;
-                rn = j < nseq ? sq[j] : make_uint4(0, 0, 0, 0);
-                rn_next = j < nseq ? sq[j + 1].x : 0;
+        long long seen = 0;                               // the frame's finished prefix as last polled (warp-uniform)
+        for (u32 c0 = 0; c0 < nseq; c0 += ZB_BIG_SEQCAP) {
+            u32 const cn = nseq - c0 < ZB_BIG_SEQCAP ? nseq - c0 : ZB_BIG_SEQCAP;
+            __syncthreads();                              // (the previous chunk is over: its arrays are free, its bytes final)
+            // ---- all literal runs of the chunk, and its sequences into shared memory
+            for (u32 w = tid; w < ZB_BIG_SEQCAP / 32; w += ZB_BIG_NT) sB[w] = 0;
+            for (u32 k = 0; k < ZB_BIG_PER; k++) {
+                u32 const il = tid + k * ZB_BIG_NT;
+                if (il < cn) {
+                    ZbSeq const r = sq[c0 + il]; u32 const nx = sq[c0 + il + 1].x;
+                    u32 const ll = nx - r.x;
+                    sO[il] = r.y; sM[il] = r.y + ll; sF[il] = r.w;
+                    u8* o = so + r.y;
+                    if (lit_rle) for (u32 q = 0; q < ll; q++) o[q] = lit_byte;
+                    else zb_copy_fwd8(o, lit + r.x, ll);
+                }
             }
-            u32 const ll = valid ? nx - r.x : 0, ml = r.z, off = r.w;
-            u32 const ostart = r.y, mstart = r.y + ll;
-            if (valid) {
-                u8* o = so + ostart;
-                if (lit_rle) for (u32 k = 0; k < ll; k++) o[k] = lit_byte;
-                else zb_copy_fwd8(o, lit + r.x, ll);
+            if (tid == 0) sO[cn] = sq[c0 + cn].y;
+            __syncthreads();
+            // ---- the matches of this chunk my sources overlap: [ja, jb) -- spans that end above my source start, matches that
+            //      start below my source end
+            for (u32 k = 0; k < ZB_BIG_PER; k++) {
+                u32 const il = tid + k * ZB_BIG_NT;
+                if (il >= cn) break;
+                long long const m = (long long)sM[il], ml = (long long)sO[il + 1] - m, srcp = m - (long long)sF[il];
+                long long const s_lo = srcp, s_hi = min(srcp + ml, m);
+                u32 ja, jb;
+                { u32 lo = 0, hi = il; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)sO[md + 1] > s_lo) hi = md; else lo = md + 1; } ja = lo; }
+                { u32 lo = ja, hi = il; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)sM[md] >= s_hi) hi = md; else lo = md + 1; } jb = lo; }
+                bool const ext = srcp < 0 && base + min(srcp + ml, 0ll) > 0;
+                sD[il] = ja | (jb << 14) | (ext ? 0x80000000u : 0u);
             }
-            bool pending = valid;
-            int const m = (int)mstart;                                  // block-relative match start
-            long long const srcp = (long long)m - (long long)off;       // block-relative source: negative = in front of the block
-            __syncthreads();                                            // (the previous round is over: s_m / s_e / s_done are free)
-            s_m[tid] = valid ? m : 0x7FFFFFFF; s_e[tid] = valid ? m + (int)ml : 0x7FFFFFFF;
-            if (tid < ZB_BIG_NT / 32) s_done[tid] = 0;
-            __syncthreads();                                            // literals of the round are in place, too
-            // the matches of this round my source overlaps: [ja, jb) -- ends above my source start, starts below my source end
-            u32 ja = 0, jb = 0;
-            if (valid) {
-                long long const s_lo = srcp, s_hi = min(srcp + (long long)ml, (long long)m);
-                { u32 lo = 0, hi = tid; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)s_e[md] > s_lo) hi = md; else lo = md + 1; } ja = lo; }
-                { u32 lo = ja, hi = tid; while (lo < hi) { u32 const md = (lo + hi) >> 1; if ((long long)s_m[md] >= s_hi) hi = md; else lo = md + 1; } jb = lo; }
+            __syncthreads();
+            // ---- who copies what: warps 0-7 the matches whose source lies in the block (shared memory only: a hop of a
+            //      dependency chain costs a few hundred cycles), warps 8-15 the ones that read in front of the block (global
+            //      memory: ~1 us per hop) -- thread t of a group has the sequences t + 256 k of its kind
+            u32 const grp = tid >> 8, t8 = tid & 255u;
+            u32 pend = 0;
+            for (u32 k = 0; k < ZB_BIG_SEQCAP / 256; k++) {
+                u32 const il = t8 + k * 256;
+                if (il < cn && (sD[il] >> 31) == grp) pend |= 1u << k;
             }
+            // ---- sweeps over the pending matches; no CTA barrier until the warp's matches are all done
+            bool poll = true;
             for (;;) {
-                bool ready = pending;
-                if (pending && jb > ja) {
-                    for (u32 w = ja >> 5; w <= (jb - 1) >> 5; w++) {
-                        u32 const lo_b = w == (ja >> 5) ? (ja & 31) : 0u, hi_b = w == ((jb - 1) >> 5) ? ((jb - 1) & 31) : 31u;
-                        u32 const mask = (0xFFFFFFFFu << lo_b) & (0xFFFFFFFFu >> (31 - hi_b));
-                        if ((s_done[w] & mask) != mask) { ready = false; break; }
-                    }
+                if (grp && seen < base && __any_sync(0xFFFFFFFFu, poll)) {
+                    unsigned long long v = 0;
+                    if (lane == 0) { v = *(volatile unsigned long long*)(wave.done_pos + f); __threadfence(); }
+                    seen = (long long)__shfl_sync(0xFFFFFFFFu, v, 0);
                 }
-                u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 32);
-                while (big) {          // long matches: the whole warp copies
-                    int const l = __ffs(big) - 1; big &= big - 1;
-                    int const m0 = __shfl_sync(0xFFFFFFFFu, m, l);
-                    u32 const o = __shfl_sync(0xFFFFFFFFu, off, l), len = __shfl_sync(0xFFFFFFFFu, ml, l);
-                    u8* d = so + m0;
-                    if ((long long)o > (long long)m0) {                 // starts in front of the block: byte-wise with the source select
-                        for (u32 j = lane; j < len; j += 32) {
-                            long long const sp = (long long)m0 - (long long)o + (long long)(j % o);
-                            u8 v;
-                            if (sp >= 0) v = so[sp];
-                            else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
-                            d[j] = v;
-                        }
-                    } else if (o >= 32) {
-                        const u8* sp = d - o;
-                        for (u32 j = 0; j < len; j += 32) { if (j + lane < len) d[j + lane] = sp[j + lane]; __syncwarp(); }
-                    } else {
-                        const u8* sp = d - o;
-                        for (u32 j = lane; j < len; j += 32) d[j] = sp[j % o];
-                    }
-                    __syncwarp();
-                }
-                if (ready) {
-                    if (ml < 32) {
-                        u8* d = so + m;
-                        if (srcp >= 0) {
-                            const u8* sp = so + srcp;
-                            if (off >= 8) zb_copy_fwd8(d, sp, ml);      // 8-byte chunks never read their own output
-                            else { u32 q = 0; for (u32 k = 0; k < ml; k++) { d[k] = sp[q]; if (++q == off) q = 0; } }
-                        } else if (off >= ml) {
-                            // the source starts in front of the block and does not overlap the match: ALL loads first (the
-                            // global ones cost ~700 cycles each when they wait for one another), then the stores
-                            for (u32 k0 = 0; k0 < ml; k0 += 8) {          // eight at a time
-                                u8 t[8];
-                                #pragma unroll
-                                for (u32 q = 0; q < 8; q++) {
-                                    long long const sp = srcp + (long long)(k0 + q);
-                                    u8 v = 0;
-                                    if (k0 + q < ml) {
-                                        if (sp >= 0) v = so[sp];
-                                        else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
-                                    }
-                                    t[q] = v;
-                                }
-                                #pragma unroll
-                                for (u32 q = 0; q < 8; q++) if (k0 + q < ml) d[k0 + q] = t[q];
+                poll = false;
+                for (u32 un = zb_warp_or(pend); un; un &= un - 1) {
+                    u32 const k = (u32)__ffs((int)un) - 1u;
+                    bool const mine = (pend >> k) & 1u;
+                    u32 const il = t8 + k * 256;
+                    bool ready = mine;
+                    int m = 0; u32 ml = 0, off = 0;
+                    if (mine) {
+                        u32 const d = sD[il]; u32 const ja = d & 0x3FFFu, jb = (d >> 14) & 0x7FFFu;
+                        if (jb > ja) {
+                            for (u32 w = ja >> 5; w <= (jb - 1) >> 5; w++) {
+                                u32 const lo_b = w == (ja >> 5) ? (ja & 31) : 0u, hi_b = w == ((jb - 1) >> 5) ? ((jb - 1) & 31) : 31u;
+                                u32 const mask = (0xFFFFFFFFu << lo_b) & (0xFFFFFFFFu >> (31 - hi_b));
+                                if ((((volatile u32*)sB)[w] & mask) != mask) { ready = false; break; }
                             }
-                        } else {
-                            for (u32 k = 0; k < ml; k++) {
-                                long long const sp = srcp + (long long)(k % off);
+                        }
+                        m = (int)sM[il]; ml = sO[il + 1] - (u32)m; off = sF[il];
+                        if (ready && (d >> 31) && seen < base) {
+                            long long const need = min(base, base + (long long)m - (long long)off + (long long)ml);
+                            if (seen < need) { ready = false; poll = true; }
+                        }
+                        __threadfence_block();            // (the bitmap was read before the bytes are)
+                    }
+                    long long const srcp = (long long)m - (long long)off;       // block-relative source: negative = in front of the block
+                    u32 big = __ballot_sync(0xFFFFFFFFu, ready && ml >= 64);
+                    while (big) {          // long matches: the whole warp copies
+                        int const l = __ffs(big) - 1; big &= big - 1;
+                        int const m0 = __shfl_sync(0xFFFFFFFFu, m, l);
+                        u32 const o = __shfl_sync(0xFFFFFFFFu, off, l), len = __shfl_sync(0xFFFFFFFFu, ml, l);
+                        u8* d = so + m0;
+                        if ((long long)o > (long long)m0) {                 // starts in front of the block: byte-wise with the source select
+                            for (u32 j = lane; j < len; j += 32) {
+                                long long const sp = (long long)m0 - (long long)o + (long long)(j % o);
                                 u8 v;
                                 if (sp >= 0) v = so[sp];
                                 else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
-                                d[k] = v;
+                                d[j] = v;
+                            }
+                        } else if (o >= 32) {
+                            const u8* sp = d - o;
+                            for (u32 j = 0; j < len; j += 32) { if (j + lane < len) d[j + lane] = sp[j + lane]; __syncwarp(); }
+                        } else {
+                            const u8* sp = d - o;
+                            for (u32 j = lane; j < len; j += 32) d[j] = sp[j % o];
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                    }
+                    if (ready) {
+                        if (ml < 64) {
+                            u8* d = so + m;
+                            if (srcp >= 0) {
+                                const u8* sp = so + srcp;
+                                if (off >= 8) zb_copy_fwd8(d, sp, ml);      // 8-byte chunks never read their own output
+                                else { u32 q = 0; for (u32 j = 0; j < ml; j++) { d[j] = sp[q]; if (++q == off) q = 0; } }
+                            } else if (off >= ml && srcp + (long long)ml <= 0 && base + srcp >= 0) {
+                                // the whole source is earlier output of the frame: up to nine aligned 8-byte words, all loads in
+                                // flight together (one trip to L2 instead of one per byte)
+                                const u8* const gp = out + (base + srcp);
+                                u32 const mis = (u32)((uintptr_t)gp & 7u);
+                                const unsigned long long* const ga = (const unsigned long long*)(gp - mis);
+                                unsigned long long w[9];
+                                #pragma unroll
+                                for (u32 q = 0; q < 9; q++) w[q] = q * 8 < mis + ml ? __ldcg(ga + q) : 0ull;
+                                #pragma unroll
+                                for (u32 q = 0; q < 9; q++) {
+                                    #pragma unroll
+                                    for (u32 bq = 0; bq < 8; bq++) {
+                                        int const idx = (int)(q * 8 + bq) - (int)mis;
+                                        if (idx >= 0 && idx < (int)ml) d[idx] = (u8)(w[q] >> (8 * bq));
+                                    }
+                                }
+                            } else if (off >= ml) {
+                                // the source starts in front of the block (dictionary, or straddling the block start) and does not
+                                // overlap the match: eight loads, then eight stores
+                                for (u32 k0 = 0; k0 < ml; k0 += 8) {
+                                    u8 t[8];
+                                    #pragma unroll
+                                    for (u32 q = 0; q < 8; q++) {
+                                        long long const sp = srcp + (long long)(k0 + q);
+                                        u8 v = 0;
+                                        if (k0 + q < ml) {
+                                            if (sp >= 0) v = so[sp];
+                                            else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                                        }
+                                        t[q] = v;
+                                    }
+                                    #pragma unroll
+                                    for (u32 q = 0; q < 8; q++) if (k0 + q < ml) d[k0 + q] = t[q];
+                                }
+                            } else {
+                                for (u32 j = 0; j < ml; j++) {
+                                    long long const sp = srcp + (long long)(j % off);
+                                    u8 v;
+                                    if (sp >= 0) v = so[sp];
+                                    else { long long const fp = base + sp; v = fp >= 0 ? __ldcg(out + fp) : dict_end[fp]; }
+                                    d[j] = v;
+                                }
                             }
                         }
+                        __threadfence_block();            // the bytes before the bit
+                        atomicOr(&sB[il >> 5], 1u << (il & 31));
+                        pend &= ~(1u << k);
                     }
-                    pending = false;
-                    atomicOr(&s_done[warp], 1u << lane);
                 }
-                if (!__syncthreads_or(pending ? 1 : 0)) break;          // (also: this round's copies and done bits are visible)
+                if (!__any_sync(0xFFFFFFFFu, pend != 0)) break;
             }
         }
         __syncthreads();
@@ -1004,7 +1078,26 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
             u32 const done = head + (nv << 4);
             if (done + tid < total) gout[done + tid] = so[done + tid];
         }
+        }
+        // the block is in global memory: publish it and move the frame's finished prefix over every finished block behind it
         __threadfence();          // later blocks of this frame read these bytes through L2 (__ldcg)
+        __syncthreads();
+        if (tid == 0) {
+            u32 const nblk = (u32)(place[f + 1].blk_off - pl.blk_off);
+            atomicExch(wave.blk_flag + bi, 1u);
+            __threadfence();
+            for (;;) {
+                u32 const cur = *(volatile u32*)(wave.pre_blk + f);
+                if (cur >= nblk) break;
+                if (*(volatile u32*)(wave.blk_flag + pl.blk_off + cur) == 0) break;
+                __threadfence();
+                if (atomicCAS(wave.pre_blk + f, cur, cur + 1) == cur) {
+                    ZbBlock const Bc = blocks[pl.blk_off + cur];
+                    __threadfence();
+                    atomicMax(wave.done_pos + f, (unsigned long long)(Bc.out_pos + Bc.regen));
+                }
+            }
+        }
     }
 }
 
@@ -1161,16 +1254,29 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
     }
 }
 
-void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
-                           const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, ZbDictDev dict, cudaStream_t st)
+size_t zb_wave_bytes(u64 n_frames, u64 n_blocks) { return (size_t)(n_frames * 12 + n_blocks * 4 + 64); }
+
+void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
+                           const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, u64 blk_first, u64 blk_last,
+                           u64 n_frames, u64 n_blocks, void* wave_mem, u32 n_ctas, ZbDictDev dict, cudaStream_t st)
 {
-    // the block-parallel path: few frames of many blocks.  Small frames as always, the others a CTA (16 warps, 219 KB of shared memory) each
+    // the block-parallel path: few frames of many blocks.  Small frames as always; the blocks of the others are taken in
+    // order by a persistent grid (16 warps and 219 KB of shared memory per CTA, one CTA per SM)
     cudaFuncSetAttribute(zb_execute_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, ZB_TILE_SMEM);
     cudaFuncSetAttribute(zb_execute_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZB_BIG_SMEM);
     u32 const n = end - first;
     zb_execute_tile<<<(n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, ZB_TILE_SMEM, st>>>(src, place, status, blocks,
                                                                                                  seqs, lits, dst, first, end, dict);
-    zb_execute_big<<<n, ZB_BIG_NT, ZB_BIG_SMEM, st>>>(src, place, status, blocks, seqs, lits, dst, first, end, dict, (u64)ZB_TILE_CAP + 1);
+    if (blk_last <= blk_first) return;
+    cudaMemsetAsync(wave_mem, 0, zb_wave_bytes(n_frames, n_blocks), st);
+    ZbWave w;
+    w.done_pos = (unsigned long long*)wave_mem;
+    w.pre_blk = (u32*)(w.done_pos + n_frames);
+    w.blk_flag = w.pre_blk + n_frames;
+    w.ticket = w.blk_flag + n_blocks;
+    u64 grid = blk_last - blk_first; if (grid > n_ctas) grid = n_ctas;
+    zb_execute_big<<<(unsigned)grid, ZB_BIG_NT, ZB_BIG_SMEM, st>>>(src, place, status, blocks, (const ZbBlkDesc*)bdesc, seqs, lits, dst,
+                                                                  blk_first, blk_last, dict, (u64)ZB_TILE_CAP + 1, w);
 }
 
 void zb_launch_execute(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks,
