@@ -35,6 +35,10 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
                        ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                        ZbDictDev dict, u32* status, u64* out_sizes, u32* ck_expect, u32 take, u32 warps, cudaStream_t st);
 size_t zb_wave_bytes(u64 n_frames, u64 n_blocks);
+size_t zb_chase_bytes(u64 n_total);
+int zb_launch_execute_chase(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
+                            const ZbSeq* seqs, const u8* lits, u8* dst, u64 lo, u64 hi, u64 n_total, u64 blk_first, u64 blk_last,
+                            void* ptr_mem, u32* d_changed, u32 n_ctas, ZbDictDev dict, cudaStream_t st);
 void zb_launch_execute_big(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
                            const ZbSeq* seqs, const u8* lits, u8* dst, u32 first, u32 end, u64 blk_first, u64 blk_last,
                            u64 n_frames, u64 n_blocks, void* wave_mem, u32 n_ctas, ZbDictDev dict, cudaStream_t st);
@@ -101,6 +105,8 @@ struct zb200_ctx {
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
     DevBuf jobs, seginfo, slots, bouts, escratch, fsizes, ck;
     DevBuf bdesc, bexit, erep, fend, wave;    // block-parallel decode path
+    DevBuf chase;                             // its pointer-jumping execute stage: a source pointer per output byte
+    int last_chase_rounds = 0;
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -226,7 +232,7 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->bdesc.release(); ctx->bexit.release(); ctx->erep.release(); ctx->fend.release();
+    ctx->bdesc.release(); ctx->bexit.release(); ctx->erep.release(); ctx->fend.release(); ctx->wave.release(); ctx->chase.release();
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
                      &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial,
                      &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes, &ctx->ck};
@@ -404,6 +410,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     // instead of a lane per frame for the entropy stage (zb_scan_blocks -> zb_entropy_blocks -> zb_resolve_blocks / zb_patch_blocks)
     static int const force_blocks = getenv("ZB200_BLOCK_PATH") ? atoi(getenv("ZB200_BLOCK_PATH")) : -1;
     bool const block_path = force_blocks >= 0 ? force_blocks != 0 : (totals[1] > n && n < 3000);
+    bool chase_path = false;
     if (block_path) {
         u64 const nb = totals[1];
         CK(ctx->bdesc.ensure((nb + 1) * zb_blkdesc_bytes()));
@@ -411,6 +418,11 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         CK(ctx->erep.ensure((nb + 1) * 3 * sizeof(u32)));
         CK(ctx->fend.ensure(n * sizeof(u64)));
         CK(ctx->wave.ensure(zb_wave_bytes(nf, nb)));
+        // FEW frames of many blocks (one huge frame at the limit): the copy-execute chain of a frame is serial however it is
+        // mapped, so it is shortened by pointer doubling instead (zb_chase_*); many frames keep the machine busy frame-parallel
+        static int const force_chase = getenv("ZB200_CHASE") ? atoi(getenv("ZB200_CHASE")) : -1;
+        chase_path = force_chase >= 0 ? force_chase != 0 : (nf < 64 && nb >= 8ull * nf);
+        if (chase_path && ctx->chase.ensure(zb_chase_bytes(totals[0])) != cudaSuccess) { cudaGetLastError(); chase_path = false; }
         { KSpan s(ctx, ZB200_K_SCAN);
           zb_launch_scan_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), dd, ctx->status.as<u32>(), ctx->bdesc.p, ctx->fend.as<u64>(), ctx->stream); }
         u32 const take = 3, EW = 7;
@@ -445,7 +457,16 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
                             ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), cc, counter, dd,
                             ctx->status.as<u32>(), ctx->out_sizes.as<u64>(), ctx->ck.as<u32>(), take, EW, ctx->stream); }
         { KSpan s(ctx, ZB200_K_EXECUTE);
-          if (block_path) zb_launch_execute_big(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(), ctx->bdesc.p,
+          if (chase_path) {
+              int const r = zb_launch_execute_chase(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(), ctx->bdesc.p,
+                                                    ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out,
+                                                    n_chunks > 1 ? cpl[k].dst_off : 0, n_chunks > 1 ? cpl[k + 1].dst_off : totals[0], totals[0],
+                                                    n_chunks > 1 ? cpl[k].blk_off : 0, n_chunks > 1 ? cpl[k + 1].blk_off : totals[1],
+                                                    ctx->chase.p, d_counter + 48, ctas, dd, ctx->stream);
+              if (r < 0) return fail(ctx, "pointer-jumping execute", cudaGetLastError());
+              ctx->last_chase_rounds = r;
+          }
+          else if (block_path) zb_launch_execute_big(d_src, ctx->place.as<ZbFramePlace>(), ctx->status.as<u32>(), ctx->blocks.as<ZbBlock>(), ctx->bdesc.p,
                                                 ctx->seqs.as<ZbSeq>(), ctx->lits.as<u8>(), d_out, f0, f1,
                                                 n_chunks > 1 ? cpl[k].blk_off : 0, n_chunks > 1 ? cpl[k + 1].blk_off : totals[1],
                                                 nf, totals[1], ctx->wave.p, ctas, dd, ctx->stream);

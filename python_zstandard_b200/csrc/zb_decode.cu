@@ -857,6 +857,13 @@ __device__ __forceinline__ u32 zb_warp_or(u32 v)
     return v;
 }
 
+#ifdef ZB_DEBUG_BLOCKS
+__device__ __forceinline__ unsigned long long zb_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ZB_BIGT(...) __VA_ARGS__
+#else
+#define ZB_BIGT(...)
+#endif
+
 struct ZbWave {                     // zeroed before every launch
     unsigned long long* done_pos;   // per frame: output bytes [0, done_pos) are final in global memory
     u32* pre_blk;                   // per frame: blocks [0, pre_blk) of the frame are finished
@@ -885,6 +892,7 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
         __syncthreads();
         u64 const bi = blk_first + s_ticket;
         if (bi >= blk_last) return;
+        ZB_BIGT(unsigned long long const tg0 = zb_gtime(); unsigned long long tg1 = 0, tg_seen = 0, tg2 = 0, tg3 = 0; u32 n_sweeps = 0; u32 n_ext = 0;)
         u32 const f = bdesc[bi].frame;
         if (status[f] != ZB_OK) continue;
         ZbFramePlace const pl = place[f];
@@ -946,11 +954,14 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
             }
             // ---- sweeps over the pending matches; no CTA barrier until the warp's matches are all done
             bool poll = true;
+            ZB_BIGT(if (tid == 0 && c0 == 0) tg1 = zb_gtime(); n_ext += grp ? __popc(pend) : 0;)
             for (;;) {
+                ZB_BIGT(n_sweeps++;)
                 if (grp && seen < base && __any_sync(0xFFFFFFFFu, poll)) {
                     unsigned long long v = 0;
                     if (lane == 0) { v = *(volatile unsigned long long*)(wave.done_pos + f); __threadfence(); }
                     seen = (long long)__shfl_sync(0xFFFFFFFFu, v, 0);
+                    ZB_BIGT(if (seen >= base && tid == 256) tg_seen = zb_gtime();)
                 }
                 poll = false;
                 for (u32 un = zb_warp_or(pend); un; un &= un - 1) {
@@ -1060,7 +1071,9 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                 if (!__any_sync(0xFFFFFFFFu, pend != 0)) break;
             }
         }
+        ZB_BIGT(u32 const my_sweeps = n_sweeps; if (tid == 256 && bi >= 2000 && bi < 2024) printf("  [blk %llu] ext warp 8: sweeps %u, seen at %llu, ext seqs of thread %u\n", bi, my_sweeps, tg_seen - tg0, n_ext);)
         __syncthreads();
+        ZB_BIGT(tg2 = zb_gtime();)
         {   // last literals of the block
             ZbSeq const e = sq[nseq];
             u32 const tail = B.n_lit - e.x;
@@ -1097,7 +1110,112 @@ zb_execute_big(const u8* __restrict__ src, const ZbFramePlace* __restrict__ plac
                     atomicMax(wave.done_pos + f, (unsigned long long)(Bc.out_pos + Bc.regen));
                 }
             }
+            ZB_BIGT(tg3 = zb_gtime(); if (bi >= 2000 && bi < 2024) printf("[blk %llu] start %llu  setup %llu  matches done +%llu  published +%llu  (abs publish %llu) nseq %u sweeps(warp0) %u\n", bi, tg0 % 100000000ull, tg1 - tg0, tg2 - tg0, tg3 - tg0, tg3 % 100000000ull, blocks[bi].n_seq, n_sweeps);)
         }
+    }
+}
+
+// ===========================================================================
+// K4 (pointer-jumping variant): FEW frames of very many blocks -- one huge frame at the limit (BASELINE config 5).  Copy-
+// execute is a dependency chain: a match copies bytes that earlier matches produced (on text ~60 dependent hops inside a
+// 128 KiB block, and the chains run on through the whole frame), so executing the blocks of one frame in order -- however
+// many threads work on a block -- is bound by that chain (measured: 0.3-0.4 ms per block whatever the mapping).  Here the
+// chain is not followed, it is SHORTENED: every output byte gets a source pointer, pointer doubling makes every byte point
+// at the byte that first held its value (a literal, or a dictionary byte), one gather finishes the frame:
+//   zb_chase_init    a thread per sequence: literal bytes are written to dst and point at themselves (DONE); match byte p
+//                    points at p - offset (bytes that come from the dictionary are written at once and are DONE)
+//   zb_chase_round   ptr[p] = ptr[ptr[p]] for every byte that is not DONE; DONE propagates; the host stops when a round
+//                    changes nothing: ceil(log2(longest chain)) rounds, each a streaming pass plus one gather per open byte
+//   zb_chase_gather  dst[p] = dst[ptr[p]]
+// All three are embarrassingly parallel over the whole frame.  The price is a pointer per output byte (4 bytes below
+// 2 GiB of output, 8 beyond) and ~10 passes over it.
+// ===========================================================================
+template <typename P> __device__ __forceinline__ P zb_chase_done() { return (P)1 << (sizeof(P) * 8 - 1); }
+
+template <typename P>
+__global__ void __launch_bounds__(256)
+zb_chase_init(const u8* __restrict__ src, const ZbFramePlace* __restrict__ place, const u32* __restrict__ status,
+              const ZbBlock* __restrict__ blocks, const ZbBlkDesc* __restrict__ bdesc, const ZbSeq* __restrict__ seqs,
+              const u8* __restrict__ lits, u8* __restrict__ dst, P* __restrict__ ptr, u64 blk_first, u64 blk_last, ZbDictDev dict)
+{
+    P const DONE = zb_chase_done<P>();
+    u32 const tid = threadIdx.x, lane = tid & 31;
+    const u8* const dict_end = dict.content + dict.content_size;
+    for (u64 bi = blk_first + blockIdx.x; bi < blk_last; bi += gridDim.x) {
+        u32 const f = bdesc[bi].frame;
+        if (status[f] != ZB_OK) continue;
+        ZbFramePlace const pl = place[f];
+        ZbBlock const B = blocks[bi];
+        u64 const gbase = pl.dst_off + B.out_pos;           // position of the block's first byte in dst
+        u8* const gout = dst + gbase; P* const gp = ptr + gbase;
+        if (B.kind == ZB_BLK_RAW) { const u8* q = src + B.src_pos; for (u32 i = tid; i < B.regen; i += 256) { gout[i] = q[i]; gp[i] = (P)(gbase + i) | DONE; } continue; }
+        if (B.kind == ZB_BLK_RLE) { for (u32 i = tid; i < B.regen; i += 256) { gout[i] = (u8)B.lit_byte; gp[i] = (P)(gbase + i) | DONE; } continue; }
+        if (B.kind != ZB_BLK_COMPRESSED) continue;
+        bool const lit_rle = B.lit_kind == ZB_LIT_RLE; u8 const lit_byte = (u8)B.lit_byte;
+        const u8* const lit = B.lit_kind == ZB_LIT_RAW ? src + B.src_pos : lits + B.src_pos;
+        const ZbSeq* const sq = seqs + B.seq_pos;
+        u32 const nseq = B.n_seq;
+        long long const fstart = (long long)pl.dst_off;    // sources below it come from the dictionary
+        for (u32 g = 0; g < nseq; g += 256) {
+            u32 const i = g + tid; bool const valid = i < nseq;
+            ZbSeq r = make_uint4(0, 0, 0, 0); u32 nx = 0;
+            if (valid) { r = sq[i]; nx = sq[i + 1].x; }
+            u32 const ll = nx - r.x, ml = r.z, off = r.w, m = r.y + ll;
+            for (u32 k = 0; k < ll; k++) { gout[r.y + k] = lit_rle ? lit_byte : lit[r.x + k]; gp[r.y + k] = (P)(gbase + r.y + k) | DONE; }
+            u32 big = __ballot_sync(0xFFFFFFFFu, valid && ml >= 128);
+            if (valid && ml < 128) {
+                for (u32 k = 0; k < ml; k++) {
+                    long long const pos = (long long)(gbase + m + k), sp = pos - (long long)off;
+                    if (sp >= fstart) gp[m + k] = (P)sp;
+                    else { gout[m + k] = dict_end[sp - fstart]; gp[m + k] = (P)pos | DONE; }
+                }
+            }
+            while (big) {          // long matches: the whole warp writes the pointers
+                int const l = __ffs((int)big) - 1; big &= big - 1;
+                u32 const m0 = __shfl_sync(0xFFFFFFFFu, m, l), len = __shfl_sync(0xFFFFFFFFu, ml, l), o = __shfl_sync(0xFFFFFFFFu, off, l);
+                for (u32 k = lane; k < len; k += 32) {
+                    long long const pos = (long long)(gbase + m0 + k), sp = pos - (long long)o;
+                    if (sp >= fstart) gp[m0 + k] = (P)sp;
+                    else { gout[m0 + k] = dict_end[sp - fstart]; gp[m0 + k] = (P)pos | DONE; }
+                }
+            }
+        }
+        {   // last literals of the block
+            ZbSeq const e = sq[nseq];
+            u32 const tail = B.n_lit - e.x;
+            for (u32 k = tid; k < tail; k += 256) { gout[e.y + k] = lit_rle ? lit_byte : lit[e.x + k]; gp[e.y + k] = (P)(gbase + e.y + k) | DONE; }
+        }
+    }
+}
+
+// one round of pointer doubling over [lo, hi).  Racing updates are harmless: whatever a thread reads from ptr[q] is an ancestor
+// of q (or q's final source), so it is one of p, too.
+template <typename P>
+__global__ void __launch_bounds__(256)
+zb_chase_round(P* __restrict__ ptr, u64 lo, u64 hi, u32* __restrict__ changed)
+{
+    P const DONE = zb_chase_done<P>();
+    bool ch = false;
+    u64 const stride = (u64)gridDim.x * 256;
+    for (u64 p = lo + (u64)blockIdx.x * 256 + threadIdx.x; p < hi; p += stride) {
+        P const v = ptr[p];
+        if (v & DONE) continue;
+        P const w = __ldcg(ptr + v);
+        ptr[p] = w;
+        if (!(w & DONE)) ch = true;
+    }
+    if (__syncthreads_or(ch ? 1 : 0) && threadIdx.x == 0) *changed = 1;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256)
+zb_chase_gather(const P* __restrict__ ptr, u8* dst, u64 lo, u64 hi, u64 n_total)
+{
+    P const DONE = zb_chase_done<P>();
+    u64 const stride = (u64)gridDim.x * 256;
+    for (u64 p = lo + (u64)blockIdx.x * 256 + threadIdx.x; p < hi; p += stride) {
+        P const t = ptr[p] & ~DONE;
+        if ((u64)t != p && (u64)t < n_total) dst[p] = __ldcg(dst + t);
     }
 }
 
@@ -1252,6 +1370,44 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
         zb_entropy_decode<7><<<n_ctas, 7 * 32, ZB_ENT_SMEM(7), st>>>(src, segs, n, place, dst_sizes, blocks, seqs, lits,
                                                                     work_counter, dict, status, out_sizes, ck_expect, take);
     }
+}
+
+// the pointer-jumping execute stage over the blocks [blk_first, blk_last) whose output is dst[lo, hi).  ptr_mem: (n_total + 16)
+// pointers of 4 bytes (n_total < 2^31) or 8.  Returns the number of doubling rounds, or -1 on a CUDA error.
+size_t zb_chase_bytes(u64 n_total) { return (size_t)((n_total + 16) * (n_total < (1ull << 31) ? 4 : 8)); }
+
+template <typename P>
+static int zb_chase_run(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
+                        const ZbSeq* seqs, const u8* lits, u8* dst, u64 lo, u64 hi, u64 n_total, u64 blk_first, u64 blk_last,
+                        void* ptr_mem, u32* d_changed, u32 n_ctas, ZbDictDev dict, cudaStream_t st)
+{
+    P* const ptr = (P*)ptr_mem;
+    if (hi <= lo || blk_last <= blk_first) return 0;
+    if (cudaMemsetAsync(ptr + lo, 0xFF, (hi - lo) * sizeof(P), st) != cudaSuccess) return -1;      // frames that failed stay "done, no source"
+    u64 const nb = blk_last - blk_first;
+    zb_chase_init<P><<<(unsigned)(nb < n_ctas * 8ull ? nb : n_ctas * 8ull), 256, 0, st>>>(src, place, status, blocks, (const ZbBlkDesc*)bdesc, seqs, lits,
+                                                                                         dst, ptr, blk_first, blk_last, dict);
+    u64 const want = (hi - lo + 255) / 256;
+    unsigned const grid = (unsigned)(want < n_ctas * 16ull ? want : n_ctas * 16ull);
+    int rounds = 0;
+    for (; rounds < 72; rounds++) {
+        u32 h = 0;
+        if (cudaMemsetAsync(d_changed, 0, sizeof(u32), st) != cudaSuccess) return -1;
+        zb_chase_round<P><<<grid, 256, 0, st>>>(ptr, lo, hi, d_changed);
+        if (cudaMemcpyAsync(&h, d_changed, sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        if (!h) { rounds++; break; }
+    }
+    zb_chase_gather<P><<<grid, 256, 0, st>>>(ptr, dst, lo, hi, n_total);
+    return rounds;
+}
+
+int zb_launch_execute_chase(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
+                            const ZbSeq* seqs, const u8* lits, u8* dst, u64 lo, u64 hi, u64 n_total, u64 blk_first, u64 blk_last,
+                            void* ptr_mem, u32* d_changed, u32 n_ctas, ZbDictDev dict, cudaStream_t st)
+{
+    if (n_total < (1ull << 31)) return zb_chase_run<u32>(src, place, status, blocks, bdesc, seqs, lits, dst, lo, hi, n_total, blk_first, blk_last, ptr_mem, d_changed, n_ctas, dict, st);
+    return zb_chase_run<u64>(src, place, status, blocks, bdesc, seqs, lits, dst, lo, hi, n_total, blk_first, blk_last, ptr_mem, d_changed, n_ctas, dict, st);
 }
 
 size_t zb_wave_bytes(u64 n_frames, u64 n_blocks) { return (size_t)(n_frames * 12 + n_blocks * 4 + 64); }

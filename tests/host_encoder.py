@@ -331,7 +331,13 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     else if (warps == 8) simt::launch(n_ctas, 8 * 32, [&] { zb_entropy_decode<8>(src, segs.data(), n, place.data(), dst_sizes, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
     else simt::launch(n_ctas, 7 * 32, [&] { zb_entropy_decode<7>(src, segs.data(), n, place.data(), dst_sizes, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), out_sizes.data(), ck.data(), take); });
     simt::launch((n + ZB_TILE_WARPS - 1) / ZB_TILE_WARPS, ZB_TILE_WARPS * 32, [&] { zb_execute_tile(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict); });
-    if (g_block_path) {
+    if (g_block_path == 2) {     // pointer-jumping execute stage (zb_chase_*): init, doubling rounds until nothing changes, gather
+        std::vector<u32> ptr(totals[0] + 16, 0xFFFFFFFFu); u32 changed = 0; int rounds = 0;
+        simt::launch(3, 256, [&] { zb_chase_init<u32>(src, place.data(), status.data(), blocks.data(), (const ZbBlkDesc*)bdesc.data(), seqs.data(), lits.data(), out, ptr.data(), 0, totals[1], dict); });
+        do { changed = 0; simt::launch(4, 256, [&] { zb_chase_round<u32>(ptr.data(), 0, totals[0], &changed); }); rounds++; } while (changed && rounds < 72);
+        simt::launch(4, 256, [&] { zb_chase_gather<u32>(ptr.data(), out, 0, totals[0], totals[0]); });
+    }
+    else if (g_block_path) {
         std::vector<unsigned long long> w_done(n + 1, 0); std::vector<u32> w_pre(n + 1, 0), w_flag(totals[1] + 1, 0); u32 w_ticket = 0;
         ZbWave w; w.done_pos = w_done.data(); w.pre_blk = w_pre.data(); w.blk_flag = w_flag.data(); w.ticket = &w_ticket;
         simt::launch(3, ZB_BIG_NT, [&] { zb_execute_big(src, place.data(), status.data(), blocks.data(), (const ZbBlkDesc*)bdesc.data(), seqs.data(), lits.data(), out,

@@ -19,12 +19,12 @@ pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref is 
 PAD = 64
 
 
-@pytest.fixture(scope="module", params=["lane-per-frame", "lane-per-block"])
+@pytest.fixture(scope="module", params=["lane-per-frame", "lane-per-block", "lane-per-block+pointer-jumping"])
 def sim(request):
     """Every test runs twice: through zb_entropy_decode (a lane per frame) and through the block-parallel path
     (zb_scan_blocks -> zb_entropy_blocks -> zb_resolve_blocks -> zb_patch_blocks: a lane per block, symbolic repcodes)."""
     L = host_encoder.build_decode_sim()
-    L.t_set_block_path(1 if request.param == "lane-per-block" else 0)
+    L.t_set_block_path({"lane-per-frame": 0, "lane-per-block": 1}.get(request.param, 2))
     yield L
     L.t_set_block_path(0)
 
