@@ -1376,6 +1376,7 @@ void zb_launch_entropy(const u8* src, const ZbSegment* segs, u32 n, const ZbFram
 // pointers of 4 bytes (n_total < 2^31) or 8.  Returns the number of doubling rounds, or -1 on a CUDA error.
 size_t zb_chase_bytes(u64 n_total) { return (size_t)((n_total + 16) * (n_total < (1ull << 31) ? 4 : 8)); }
 
+extern "C++" {
 template <typename P>
 static int zb_chase_run(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
                         const ZbSeq* seqs, const u8* lits, u8* dst, u64 lo, u64 hi, u64 n_total, u64 blk_first, u64 blk_last,
@@ -1400,6 +1401,7 @@ static int zb_chase_run(const u8* src, const ZbFramePlace* place, const u32* sta
     }
     zb_chase_gather<P><<<grid, 256, 0, st>>>(ptr, dst, lo, hi, n_total);
     return rounds;
+}
 }
 
 int zb_launch_execute_chase(const u8* src, const ZbFramePlace* place, const u32* status, const ZbBlock* blocks, const void* bdesc,
