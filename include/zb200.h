@@ -75,6 +75,10 @@ void* zb200_device_alloc(zb200_ctx* ctx, size_t bytes);
 void  zb200_device_free(zb200_ctx* ctx, void* p);
 int   zb200_memcpy_h2d(zb200_ctx* ctx, void* dst, const void* src, size_t bytes);
 int   zb200_memcpy_d2h(zb200_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* host-to-host copy on several threads: moving a large result out of the pinned pool into a caller's (not yet touched)
+   buffer is bound by page faults on one thread (~3 GB/s); the reference writes into its PyBytes in place
+   (c-ext/decompressor.c:283-352), this is the equivalent step after the device-to-host copy */
+void  zb200_host_copy(void* dst, const void* src, size_t bytes);
 
 /* ---- dictionaries (device-resident digest) */
 int  zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddict** out);

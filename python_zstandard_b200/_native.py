@@ -65,6 +65,7 @@ def lib():
             "zb200_device_free": (None, [vp, vp]),
             "zb200_memcpy_h2d": (i, [vp, vp, vp, sz]),
             "zb200_memcpy_d2h": (i, [vp, vp, vp, sz]),
+            "zb200_host_copy": (None, [vp, vp, sz]),
             "zb200_ddict_create": (i, [vp, vp, sz, C.POINTER(vp)]),
             "zb200_ddict_free": (None, [vp]),
             "zb200_ddict_id": (u32, [vp]),
@@ -151,6 +152,23 @@ class Context:
             if name and n[k]:
                 out[name] = (float(ms[k]), int(n[k]))
         return out
+
+
+_bytes_new = C.pythonapi.PyBytes_FromStringAndSize
+_bytes_new.restype = C.py_object
+_bytes_new.argtypes = [C.c_void_p, C.c_ssize_t]
+_bytes_data = C.pythonapi.PyBytes_AsString
+_bytes_data.restype = C.c_void_p
+_bytes_data.argtypes = [C.py_object]
+
+
+def bytes_from_address(addr, n):
+    """bytes(n) filled from host memory at addr; large results are copied on several threads (zb200_host_copy)."""
+    if n < (8 << 20):
+        return C.string_at(addr, n) if n else b""
+    b = _bytes_new(None, n)
+    lib().zb200_host_copy(_bytes_data(b), addr, n)
+    return b
 
 
 def device_count():

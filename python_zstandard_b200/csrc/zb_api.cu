@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <thread>
 
 extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
@@ -298,6 +299,24 @@ int zb200_memcpy_d2h(zb200_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     cudaSetDevice(ctx->device);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return 0;
+}
+
+void zb200_host_copy(void* dst, const void* src, size_t bytes)
+{
+    size_t const piece = 4u << 20;
+    unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 4;
+    size_t nt = bytes / (8u << 20); if (nt > 16) nt = 16; if (nt > hw) nt = hw;
+    if (nt < 2) { memcpy(dst, src, bytes); return; }
+    size_t const n_pieces = (bytes + piece - 1) / piece;
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=] {
+            for (size_t k = t; k < n_pieces; k += nt) {
+                size_t const o = k * piece, len = o + piece <= bytes ? piece : bytes - o;
+                memcpy((char*)dst + o, (const char*)src + o, len);
+            }
+        });
+    for (auto& x : th) x.join();
 }
 
 // ---------------------------------------------------------------- dictionaries

@@ -68,10 +68,25 @@ class _FrameWalker:
 
 
 def _decode_frame(dctx, frame, walker):
-    """One complete frame -> bytes on the GPU (frames without a content size get their block count x 128 KiB as capacity)."""
+    """One complete frame on the GPU -> its output, still in the native result (frames without a content size get their
+    block count x 128 KiB as capacity)."""
     if walker.content_size is not None:
-        return dctx.decompress(frame)
-    return dctx.decompress(frame, max_output_size=max(1, walker.blocks) * 131072)
+        return dctx._decompress_frame(frame)
+    return dctx._decompress_frame(frame, max_output_size=max(1, walker.blocks) * 131072)
+
+
+def _take_frame(dctx, buf, end, walker):
+    """Decode buf[:end] (a bytearray) without copying it first, then drop it from the buffer."""
+    mv = memoryview(buf)[:end]
+    try:
+        out = _decode_frame(dctx, mv, walker)
+    finally:
+        try:
+            mv.release()
+        except BufferError:          # (an exception's traceback still holds the view)
+            pass
+    del buf[:end]
+    return out
 
 
 class ZstdDecompressionObj:
@@ -96,8 +111,9 @@ class ZstdDecompressionObj:
             end = self._walker.feed(self._buf)
             if end is None:
                 break
-            out.append(_decode_frame(self._dctx, bytes(self._buf[:end]), self._walker))
-            del self._buf[:end]
+            fr = _take_frame(self._dctx, self._buf, end, self._walker)
+            out.append(fr.tobytes())
+            fr.close()
             self._walker = _FrameWalker()
             if not self._across:
                 self._finished = True
@@ -139,7 +155,8 @@ class ZstdDecompressionReader(io.RawIOBase):
         if not hasattr(source, "read"):
             self._src_view = memoryview(source).cast("B")
         self._walker = _FrameWalker()
-        self._out = b""
+        self._out = None             # the current frame's output (_FrameOutput), served from where the device copied it
+        self._out_len = 0
         self._out_pos = 0
         self._finished = False
         self._returned = 0
@@ -177,8 +194,14 @@ class ZstdDecompressionReader(io.RawIOBase):
         if self.closed:
             return
         super().close()
+        self._drop_frame()
         if self._closefd and hasattr(self._source, "close"):
             self._source.close()
+
+    def _drop_frame(self):
+        if self._out is not None:
+            self._out.close()
+        self._out, self._out_len, self._out_pos = None, 0, 0
 
     def _more_input(self):
         if self._src_done:
@@ -207,9 +230,9 @@ class ZstdDecompressionReader(io.RawIOBase):
                     raise ZstdError("zstd decompress error: Src size is incorrect")      # input ends inside a frame
                 self._finished = True
                 return False
-        self._out = _decode_frame(self._dctx, bytes(self._in[:end]), self._walker)
-        self._out_pos = 0
-        del self._in[:end]
+        self._drop_frame()
+        self._out = _take_frame(self._dctx, self._in, end, self._walker)
+        self._out_len = len(self._out)
         self._walker = _FrameWalker()
         if not self._across:
             self._finished = True
@@ -221,12 +244,12 @@ class ZstdDecompressionReader(io.RawIOBase):
         mv = memoryview(b).cast("B")
         got = 0
         while got < len(mv):
-            if self._out_pos >= len(self._out):
+            if self._out_pos >= self._out_len:
                 if not self._next_frame():
                     break
                 continue
-            k = min(len(mv) - got, len(self._out) - self._out_pos)
-            mv[got:got + k] = self._out[self._out_pos:self._out_pos + k]
+            k = min(len(mv) - got, self._out_len - self._out_pos)
+            self._out.copy_into(mv[got:got + k], self._out_pos, k)
             self._out_pos += k
             got += k
         self._returned += got
@@ -239,6 +262,13 @@ class ZstdDecompressionReader(io.RawIOBase):
             raise ValueError("cannot read negative amounts less than -1")
         if size == -1:
             return self.readall()
+        if self._out_pos >= self._out_len and not self._next_frame():
+            return b""
+        if self._out_len - self._out_pos >= size:           # the common case: one copy, pinned result -> bytes
+            data = self._out.tobytes(self._out_pos, self._out_pos + size)
+            self._out_pos += size
+            self._returned += size
+            return data
         buf = bytearray(size)
         n = self.readinto(buf)
         return bytes(buf[:n])
@@ -246,11 +276,11 @@ class ZstdDecompressionReader(io.RawIOBase):
     def read1(self, size=-1):
         if self.closed:
             raise ValueError("stream is closed")
-        if self._out_pos >= len(self._out) and not self._next_frame():
+        if self._out_pos >= self._out_len and not self._next_frame():
             return b""
-        avail = len(self._out) - self._out_pos
+        avail = self._out_len - self._out_pos
         k = avail if size < 0 else min(size, avail)
-        data = self._out[self._out_pos:self._out_pos + k]
+        data = self._out.tobytes(self._out_pos, self._out_pos + k)
         self._out_pos += k
         self._returned += k
         return data
@@ -265,10 +295,10 @@ class ZstdDecompressionReader(io.RawIOBase):
             raise ValueError("stream is closed")
         parts = []
         while True:
-            if self._out_pos < len(self._out):
-                parts.append(self._out[self._out_pos:])
-                self._returned += len(self._out) - self._out_pos
-                self._out_pos = len(self._out)
+            if self._out_pos < self._out_len:
+                parts.append(self._out.tobytes(self._out_pos))
+                self._returned += self._out_len - self._out_pos
+                self._out_pos = self._out_len
             if not self._next_frame():
                 break
         return b"".join(parts)
