@@ -20,9 +20,9 @@
 
 extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
-void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, cudaStream_t st);
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, u32* big_list, cudaStream_t st);
 void zb_launch_scan_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, ZbDictDev dict, u32* status,
-                           void* bdesc, u64* frame_end, cudaStream_t st);
+                           void* bdesc, u64* frame_end, const u32* big_list, cudaStream_t st);
 void zb_launch_entropy_blocks(const u8* src, const void* bdesc, u32 n_blocks, ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                               ZbDictDev dict, u32* status, void* bexit, u32 take, cudaStream_t st);
 void zb_launch_resolve_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, const ZbFrameInfo* info, const u64* dst_sizes,
@@ -106,6 +106,7 @@ struct zb200_ctx {
     DevBuf src, segs, dst_sizes, info, place, status, out_sizes, blocks, seqs, lits, dst, lane, small, out_segs, partial;
     DevBuf jobs, seginfo, slots, bouts, escratch, fsizes, ck;
     DevBuf bdesc, bexit, erep, fend, wave;    // block-parallel decode path
+    DevBuf biglist;                           // frames whose scans are a warp's work (zb_scan_frames_big)
     DevBuf chase;                             // its pointer-jumping execute stage: a source pointer per output byte
     int last_chase_rounds = 0;
     u32 entropy_warps = 0;
@@ -233,7 +234,7 @@ void zb200_ctx_destroy(zb200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->bdesc.release(); ctx->bexit.release(); ctx->erep.release(); ctx->fend.release(); ctx->wave.release(); ctx->chase.release();
+    ctx->bdesc.release(); ctx->bexit.release(); ctx->erep.release(); ctx->fend.release(); ctx->wave.release(); ctx->chase.release(); ctx->biglist.release();
     DevBuf* all[] = {&ctx->src, &ctx->segs, &ctx->dst_sizes, &ctx->info, &ctx->place, &ctx->status, &ctx->out_sizes,
                      &ctx->blocks, &ctx->seqs, &ctx->lits, &ctx->dst, &ctx->lane, &ctx->small, &ctx->out_segs, &ctx->partial,
                      &ctx->jobs, &ctx->seginfo, &ctx->slots, &ctx->bouts, &ctx->escratch, &ctx->fsizes, &ctx->ck};
@@ -393,7 +394,8 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     CK(cudaMemsetAsync(d_totals, 0, 8 * sizeof(u64), ctx->stream));
     CK(ctx->ck.ensure(n * sizeof(u32)));
 
-    { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), window_limit, ctx->stream); }
+    CK(ctx->biglist.ensure(((size_t)n + 1) * sizeof(u32)));
+    { KSpan s(ctx, ZB200_K_SCAN); zb_launch_scan(d_src, d_segs, nf, ctx->info.as<ZbFrameInfo>(), window_limit, ctx->biglist.as<u32>(), ctx->stream); }
     { KSpan s(ctx, ZB200_K_PLACE);
       zb_launch_place(ctx->info.as<ZbFrameInfo>(), d_dst_sizes, nf, ctx->place.as<ZbFramePlace>(), d_totals,
                       ctx->status.as<u32>(), ctx->partial.as<u64>(), ctx->stream); }
@@ -443,7 +445,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         chase_path = force_chase >= 0 ? force_chase != 0 : (nf < 64 && nb >= 8ull * nf);
         if (chase_path && ctx->chase.ensure(zb_chase_bytes(totals[0])) != cudaSuccess) { cudaGetLastError(); chase_path = false; }
         { KSpan s(ctx, ZB200_K_SCAN);
-          zb_launch_scan_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), dd, ctx->status.as<u32>(), ctx->bdesc.p, ctx->fend.as<u64>(), ctx->stream); }
+          zb_launch_scan_blocks(d_src, d_segs, nf, ctx->place.as<ZbFramePlace>(), dd, ctx->status.as<u32>(), ctx->bdesc.p, ctx->fend.as<u64>(), ctx->biglist.as<u32>(), ctx->stream); }
         u32 const take = 3, EW = 7;
         u32 cc = ctas; { u64 const need = (nb + EW * take - 1) / (EW * take); if (cc > need) cc = (u32)need; if (cc == 0) cc = 1; }
         { KSpan s(ctx, ZB200_K_ENTROPY);

@@ -117,8 +117,86 @@ __device__ static u32 zb_parse_lit_header(const u8* s, u32 n, ZbLitHdr& L)
 // ===========================================================================
 // K1: frame scan -- one lane per frame
 // ===========================================================================
+// Frames above ZB_SCAN_BIG compressed bytes are not walked by a single lane (every block costs it a chain of dependent global
+// loads: ~7 us): they go onto big_list (big_list[0] = count) and a WARP walks each of them (zb_scan_frames_big below).
+#ifndef ZB_SCAN_BIG
+#define ZB_SCAN_BIG (512u << 10)
+#endif
+
+// the part of a compressed block the scan needs: literal scratch bytes and sequence records it will produce
+__device__ static u32 zb_scan_block_counts(const u8* bs, u32 bsize, u64& n_lit, u64& n_seq_rec)
+{
+    ZbLitHdr L; u32 e = zb_parse_lit_header(bs, bsize, L);
+    if (e) return e;
+    u32 lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
+    if (L.regen > ZB_BLOCK_MAX || lsec > bsize) return ZB_E_CORRUPTION;
+    if (L.type >= 2) n_lit += (L.regen + 15) & ~15u;             // 16-byte aligned scratch slices
+    if (lsec >= bsize) return ZB_E_SRCSIZE_WRONG;
+    const u8* q = bs + lsec; u32 left = bsize - lsec;
+    u32 nseq = q[0];
+    if (nseq > 0x7F) {
+        if (nseq == 0xFF) { if (left < 3) return ZB_E_SRCSIZE_WRONG; nseq = zb_rd16(q + 1) + 0x7F00; }
+        else { if (left < 2) return ZB_E_SRCSIZE_WRONG; nseq = ((nseq - 0x80) << 8) + q[1]; }
+    }
+    n_seq_rec += nseq + 1;
+    return ZB_OK;
+}
+
+// K1 for one big frame per warp: lane 0 walks the block-header chain 32 blocks ahead (one dependent load per block), then
+// every lane parses the sections of its block.
+__global__ void __launch_bounds__(128)
+zb_scan_frames_big(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, const u32* __restrict__ big_list,
+                   ZbFrameInfo* __restrict__ info)
+{
+    __shared__ u64 sh_pos[4][32]; __shared__ u32 sh_bh[4][32];
+    u32 const lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    u32 const n_big = big_list[0];
+    for (u32 w = blockIdx.x * 4 + wib; w < n_big; w += gridDim.x * 4) {
+        u32 const f = big_list[1 + w];
+        const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+        zb_skip_skippable(s, n);
+        ZbHdr h; zb_parse_header(s, n, h);
+        ZbFrameInfo fi; fi.content_size = h.content_size; fi.dict_id = h.dict_id; fi.flags = h.checksum; fi.status = ZB_OK;
+        u64 pos = h.hdr_size, n_lit = 0, n_seq_rec = 0, n_blocks = 0;
+        u32 err = ZB_OK; bool last = false;
+        while (!last && !err) {
+            u32 cnt = 0, cerr = ZB_OK;
+            if (lane == 0) {
+                while (cnt < 32) {
+                    if (pos + 3 > n) { cerr = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const bh = zb_rd24(s + pos); u32 const type = (bh >> 1) & 3; u32 bsize = bh >> 3;
+                    if (type == 3) { cerr = ZB_E_CORRUPTION; break; }
+                    if (type == 1) bsize = 1;
+                    if (pos + 3 + bsize > n) { cerr = ZB_E_SRCSIZE_WRONG; break; }
+                    sh_pos[wib][cnt] = pos + 3; sh_bh[wib][cnt] = bh; cnt++;
+                    pos += 3 + bsize;
+                    if (bh & 1) { last = true; break; }
+                }
+            }
+            __syncwarp();
+            cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0); cerr = __shfl_sync(0xFFFFFFFFu, cerr, 0);
+            last = __shfl_sync(0xFFFFFFFFu, (int)last, 0) != 0;
+            u32 e = ZB_OK;
+            if (lane < cnt) {
+                u32 const bh = sh_bh[wib][lane];
+                if (((bh >> 1) & 3) == 2) e = zb_scan_block_counts(s + sh_pos[wib][lane], bh >> 3, n_lit, n_seq_rec);
+            }
+            u32 const bad = __ballot_sync(0xFFFFFFFFu, e != ZB_OK);
+            if (bad) err = __shfl_sync(0xFFFFFFFFu, e, __ffs((int)bad) - 1);
+            else err = cerr;
+            n_blocks += cnt;
+            __syncwarp();
+        }
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { n_lit += __shfl_xor_sync(0xFFFFFFFFu, n_lit, d); n_seq_rec += __shfl_xor_sync(0xFFFFFFFFu, n_seq_rec, d); }
+        if (!err && (n_lit > 0xFFFFFFFFull || n_seq_rec > 0xFFFFFFFFull || n_blocks > 0xFFFFFFFFull)) err = ZB_E_MEMORY;
+        fi.status = err; fi.n_lit = (u32)n_lit; fi.n_seq_rec = (u32)n_seq_rec; fi.n_blocks = (u32)n_blocks;
+        if (lane == 0) info[f] = fi;
+    }
+}
+
 __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
-                               ZbFrameInfo* __restrict__ info, u64 window_limit)
+                               ZbFrameInfo* __restrict__ info, u64 window_limit, u32* __restrict__ big_list)
 {
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
@@ -134,6 +212,7 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
     if (h.status == ZB_OK && h.content_size == ZB_CONTENT_UNKNOWN && h.window > window_limit) h.status = ZB_E_WINDOW_TOO_LARGE;
     if (h.status != ZB_OK) { fi.status = h.status; info[f] = fi; return; }
     fi.content_size = h.content_size; fi.dict_id = h.dict_id; fi.flags = h.checksum;
+    if (big_list && n > ZB_SCAN_BIG) { big_list[1 + atomicAdd(big_list, 1u)] = f; return; }      // a warp's work: zb_scan_frames_big
     u64 pos = h.hdr_size;
     for (;;) {
         if (pos + 3 > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
@@ -144,19 +223,8 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
         if (type == 1) bsize = 1;
         if (pos + bsize > n) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
         if (type == 2) {
-            ZbLitHdr L; u32 e = zb_parse_lit_header(s + pos, bsize, L);
+            u32 const e = zb_scan_block_counts(s + pos, bsize, n_lit, n_seq_rec);
             if (e) { fi.status = e; break; }
-            u32 lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
-            if (L.regen > ZB_BLOCK_MAX || lsec > bsize) { fi.status = ZB_E_CORRUPTION; break; }
-            if (L.type >= 2) n_lit += (L.regen + 15) & ~15u;             // 16-byte aligned scratch slices
-            if (lsec >= bsize) { fi.status = ZB_E_SRCSIZE_WRONG; break; }
-            const u8* q = s + pos + lsec; u32 left = bsize - lsec;
-            u32 nseq = q[0];
-            if (nseq > 0x7F) {
-                if (nseq == 0xFF) { if (left < 3) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(q + 1) + 0x7F00; }
-                else { if (left < 2) { fi.status = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + q[1]; }
-            }
-            n_seq_rec += nseq + 1;
         }
         pos += bsize;
         if (bh & 1) break;
@@ -406,12 +474,152 @@ __device__ static u32 zb_scan_seq_table(ZbTabSrc& d, u32 mode, u32 kmax, u32 lma
 // litEntropy, zstd/zstd.c:45840-45870, and ZSTD_decodeSeqHeaders' LLTptr / OFTptr / MLTptr + fseEntropy, :46328-46400).
 // Header parsing only; a frame whose headers do not parse is failed here.
 // ===========================================================================
+#define ZB_SRC_INHERIT 0xFFFFFFFFu            // (zb_scan_blocks_big: "this block does not redefine the table")
+
+__device__ __forceinline__ ZbTabSrc zb_shfl_tab(ZbTabSrc const& t, int j)
+{
+    ZbTabSrc r;
+    r.kind = __shfl_sync(0xFFFFFFFFu, t.kind, j); r.sym = __shfl_sync(0xFFFFFFFFu, t.sym, j); r.n = __shfl_sync(0xFFFFFFFFu, t.n, j);
+    r.p = (const u8*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)t.p, j);
+    return r;
+}
+
+// K1b for one big frame per warp (the frames zb_scan_frames left on big_list): lane 0 walks the block-header chain 32 blocks
+// ahead, every lane parses the sections of its block into "what this block redefines", then the 32 blocks' entry states are
+// chained through the warp with shuffles.  Same records, same errors as the one-lane walk below.
+__global__ void __launch_bounds__(128)
+zb_scan_blocks_big(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, const u32* __restrict__ big_list,
+                   const ZbFramePlace* __restrict__ place, ZbDictDev dict, u32* __restrict__ status,
+                   ZbBlkDesc* __restrict__ bdesc, u64* __restrict__ frame_end)
+{
+    __shared__ u64 sh_pos[4][32]; __shared__ u32 sh_bh[4][32];
+    u32 const lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    u32 const n_big = big_list[0];
+    for (u32 w = blockIdx.x * 4 + wib; w < n_big; w += gridDim.x * 4) {
+        u32 const f = big_list[1 + w];
+        u64 const b0 = place[f].blk_off, b1 = place[f + 1].blk_off;
+        if (status[f] != ZB_OK) { for (u64 b = b0 + lane; b < b1; b += 32) { bdesc[b].flags = ZB_BD_SKIP; bdesc[b].frame = f; } continue; }
+        const u8* s = src + segs[f].offset; u64 n = segs[f].length;
+        zb_skip_skippable(s, n);
+        ZbHdr h; zb_parse_header(s, n, h);
+        u32 err = ZB_OK;
+        if (h.dict_id && dict.dict_id && h.dict_id != dict.dict_id) err = ZB_E_DICT_WRONG;
+        u32 const block_max = h.window < ZB_BLOCK_MAX ? (u32)h.window : ZB_BLOCK_MAX;
+        ZbTabSrc dHuf = {ZB_SRC_NONE, 0, nullptr, 0}, dLL = dHuf, dOF = dHuf, dML = dHuf;       // the state after the blocks so far (warp-uniform)
+        bool fse_valid = false;
+        if (dict.has_entropy) { dHuf.kind = dLL.kind = dOF.kind = dML.kind = ZB_SRC_DICT; fse_valid = true; }
+        u64 pos = h.hdr_size, seq_i = place[f].seq_off, lit_i = place[f].lit_off, b = b0;
+        bool last = false;
+        while (b < b1 && !err && !last) {
+            u32 cnt = 0, cerr = ZB_OK;
+            if (lane == 0) {
+                u32 const want = b1 - b < 32 ? (u32)(b1 - b) : 32u;
+                while (cnt < want) {
+                    if (pos + 3 > n) { cerr = ZB_E_SRCSIZE_WRONG; break; }
+                    u32 const bh = zb_rd24(s + pos); u32 const type = (bh >> 1) & 3; u32 bsize = bh >> 3;
+                    if (type == 3) { cerr = ZB_E_CORRUPTION; break; }
+                    if (type == 1) bsize = 1;
+                    if (pos + 3 + bsize > n) { cerr = ZB_E_SRCSIZE_WRONG; break; }
+                    sh_pos[wib][cnt] = pos; sh_bh[wib][cnt] = bh; cnt++;
+                    pos += 3 + bsize;
+                    if (bh & 1) { last = true; break; }
+                }
+            }
+            __syncwarp();
+            cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0); cerr = __shfl_sync(0xFFFFFFFFu, cerr, 0);
+            last = __shfl_sync(0xFFFFFFFFu, (int)last, 0) != 0;
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            // ---- my block: what it redefines
+            u32 e = ZB_OK, lit_add = 0, seq_add = 0, rep_mask = 0, bsize = 0; bool new_huf = false, has_seq = false;
+            u64 my_pos = 0;
+            ZbTabSrc tHuf = {ZB_SRC_INHERIT, 0, nullptr, 0}, tLL = tHuf, tOF = tHuf, tML = tHuf;
+            if (lane < cnt) {
+                u32 const bh = sh_bh[wib][lane]; u32 const type = (bh >> 1) & 3;
+                my_pos = sh_pos[wib][lane]; bsize = type == 1 ? 1u : bh >> 3;
+                if (type == 2) do {
+                    const u8* const bs = s + my_pos + 3;
+                    ZbLitHdr L; e = zb_parse_lit_header(bs, bsize, L);
+                    if (e) break;
+                    u32 const lsec = L.type == 0 ? L.hdr + L.regen : (L.type == 1 ? L.hdr + 1 : L.hdr + L.csize);
+                    if (L.regen > ZB_BLOCK_MAX || lsec >= bsize) { e = ZB_E_CORRUPTION; break; }
+                    if (L.type == 2) { new_huf = true; tHuf.kind = ZB_SRC_NCOUNT; tHuf.p = bs + L.hdr; tHuf.n = L.csize; }
+                    if (L.type >= 2) lit_add = (L.regen + 15) & ~15u;
+                    const u8* ip = bs + lsec; const u8* const bend = bs + bsize;
+                    u32 nseq = *ip++;
+                    if (nseq > 0x7F) {
+                        if (nseq == 0xFF) { if (ip + 2 > bend) { e = ZB_E_SRCSIZE_WRONG; break; } nseq = zb_rd16(ip) + 0x7F00; ip += 2; }
+                        else { if (ip >= bend) { e = ZB_E_SRCSIZE_WRONG; break; } nseq = ((nseq - 0x80) << 8) + *ip++; }
+                    }
+                    seq_add = nseq + 1;
+                    if (nseq) {
+                        if (ip + 1 > bend) { e = ZB_E_SRCSIZE_WRONG; break; }
+                        u32 const modes = *ip++;
+                        if ((modes >> 6) == 3) rep_mask |= 1; if (((modes >> 4) & 3) == 3) rep_mask |= 2; if (((modes >> 2) & 3) == 3) rep_mask |= 4;
+                        e = zb_scan_seq_table(tLL, modes >> 6, 35, 9, ip, bend, true);
+                        if (!e) e = zb_scan_seq_table(tOF, (modes >> 4) & 3, 31, 8, ip, bend, true);
+                        if (!e) e = zb_scan_seq_table(tML, (modes >> 2) & 3, 52, 9, ip, bend, true);
+                        if (e) break;
+                        has_seq = true;
+                    }
+                } while (0);
+            }
+            // ---- where my block's records go: exclusive sums over the lanes before me
+            u32 sx = seq_add, lx = lit_add;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 const ys = __shfl_up_sync(0xFFFFFFFFu, sx, d), yl = __shfl_up_sync(0xFFFFFFFFu, lx, d);
+                if (lane >= (u32)d) { sx += ys; lx += yl; }
+            }
+            u64 const my_seq = seq_i + (sx - seq_add), my_lit = lit_i + (lx - lit_add);
+            seq_i += __shfl_sync(0xFFFFFFFFu, sx, 31); lit_i += __shfl_sync(0xFFFFFFFFu, lx, 31);
+            // ---- the state on entry of every block: chained through the lanes
+            ZbTabSrc eHuf = dHuf, eLL = dLL, eOF = dOF, eML = dML; bool e_valid = fse_valid;
+            for (u32 j = 0; j < cnt; j++) {
+                if (lane == j) {
+                    eHuf = dHuf; eLL = dLL; eOF = dOF; eML = dML; e_valid = fse_valid;
+                    if (!e && rep_mask && (!fse_valid || ((rep_mask & 1) && dLL.kind == ZB_SRC_NONE) || ((rep_mask & 2) && dOF.kind == ZB_SRC_NONE)
+                                           || ((rep_mask & 4) && dML.kind == ZB_SRC_NONE))) e = ZB_E_CORRUPTION;
+                }
+                ZbTabSrc const jH = zb_shfl_tab(tHuf, (int)j), jL = zb_shfl_tab(tLL, (int)j), jO = zb_shfl_tab(tOF, (int)j), jM = zb_shfl_tab(tML, (int)j);
+                bool const jseq = __shfl_sync(0xFFFFFFFFu, (int)has_seq, (int)j) != 0;
+                if (jH.kind != ZB_SRC_INHERIT) dHuf = jH;
+                if (jL.kind != ZB_SRC_INHERIT) dLL = jL;
+                if (jO.kind != ZB_SRC_INHERIT) dOF = jO;
+                if (jM.kind != ZB_SRC_INHERIT) dML = jM;
+                fse_valid = fse_valid || jseq;
+            }
+            (void)new_huf;
+            u32 const bad = __ballot_sync(0xFFFFFFFFu, lane < cnt && e != ZB_OK);
+            u32 nvalid = cnt;
+            if (bad) { nvalid = (u32)__ffs((int)bad) - 1; err = __shfl_sync(0xFFFFFFFFu, e, (int)nvalid); }
+            else err = cerr;
+            if (lane < cnt && (!bad || lane <= nvalid)) {
+                ZbBlkDesc D;
+                D.hdr_off = (u64)(s + my_pos - src); D.seq_off = my_seq; D.lit_off = my_lit; D.frame = f; D.block_max = block_max;
+                D.flags = (b + lane == b0 ? ZB_BD_FIRST : 0u) | (e_valid ? ZB_BD_FSE_VALID : 0u);
+                D.dHuf = eHuf; D.dLL = eLL; D.dOF = eOF; D.dML = eML;
+                D.span = 3 + bsize;
+                bdesc[b + lane] = D;
+            }
+            b += nvalid;
+            __syncwarp();
+        }
+        for (u64 k = b + lane; k < b1; k += 32) { bdesc[k].flags = ZB_BD_SKIP; bdesc[k].frame = f; }      // (after an error; a healthy frame has none left)
+        if (lane == 0) { frame_end[f] = pos; if (err) status[f] = err; }
+    }
+}
+
 __global__ void zb_scan_blocks(const u8* __restrict__ src, const ZbSegment* __restrict__ segs, u32 n_frames,
                                const ZbFramePlace* __restrict__ place, ZbDictDev dict, u32* __restrict__ status,
-                               ZbBlkDesc* __restrict__ bdesc, u64* __restrict__ frame_end)
+                               ZbBlkDesc* __restrict__ bdesc, u64* __restrict__ frame_end, const u32* __restrict__ big_list)
 {
     u32 const f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
+    if (big_list && big_list[0] && segs[f].length > ZB_SCAN_BIG) {          // zb_scan_blocks_big's, if zb_scan_frames listed it
+        const u8* s0 = src + segs[f].offset; u64 n0 = segs[f].length;
+        zb_skip_skippable(s0, n0);
+        if (n0 > ZB_SCAN_BIG) return;
+    }
     u64 const b0 = place[f].blk_off, b1 = place[f + 1].blk_off;
     if (status[f] != ZB_OK) { for (u64 b = b0; b < b1; b++) { bdesc[b].flags = ZB_BD_SKIP; bdesc[b].frame = f; } return; }
     const u8* s = src + segs[f].offset; u64 n = segs[f].length;
@@ -1320,15 +1528,19 @@ extern "C" {
 
 void zb_launch_default_tables(cudaStream_t st) { zb_build_default_tables<<<1, 32, 0, st>>>(); }
 
-void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, cudaStream_t st)
+void zb_launch_scan(const u8* src, const ZbSegment* segs, u32 n, ZbFrameInfo* info, u64 window_limit, u32* big_list, cudaStream_t st)
 {
-    zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info, window_limit);
+    // big_list: n + 1 words; [0] = number of frames left to zb_scan_frames_big
+    cudaMemsetAsync(big_list, 0, sizeof(u32), st);
+    zb_scan_frames<<<(n + 127) / 128, 128, 0, st>>>(src, segs, n, info, window_limit, big_list);
+    zb_scan_frames_big<<<n < 128 ? (n + 3) / 4 : 32, 128, 0, st>>>(src, segs, big_list, info);
 }
 
 void zb_launch_scan_blocks(const u8* src, const ZbSegment* segs, u32 n, const ZbFramePlace* place, ZbDictDev dict, u32* status,
-                           void* bdesc, u64* frame_end, cudaStream_t st)
+                           void* bdesc, u64* frame_end, const u32* big_list, cudaStream_t st)
 {
-    zb_scan_blocks<<<(n + 63) / 64, 64, 0, st>>>(src, segs, n, place, dict, status, (ZbBlkDesc*)bdesc, frame_end);
+    zb_scan_blocks<<<(n + 63) / 64, 64, 0, st>>>(src, segs, n, place, dict, status, (ZbBlkDesc*)bdesc, frame_end, big_list);
+    zb_scan_blocks_big<<<n < 128 ? (n + 3) / 4 : 32, 128, 0, st>>>(src, segs, big_list, place, dict, status, (ZbBlkDesc*)bdesc, frame_end);
 }
 void zb_launch_entropy_blocks(const u8* src, const void* bdesc, u32 n_blocks, ZbBlock* blocks, ZbSeq* seqs, u8* lits, u32 n_ctas, u32* work_counter,
                               ZbDictDev dict, u32* status, void* bexit, u32 take, cudaStream_t st)

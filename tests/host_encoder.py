@@ -313,7 +313,9 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     std::vector<ZbSegment> segs(n); for (u32 i = 0; i < n; i++) { segs[i].offset = seg_off[i]; segs[i].length = seg_len[i]; }
     std::vector<ZbFrameInfo> info(n); std::vector<ZbFramePlace> place(n + 1); std::vector<u32> status(n, 0);
     u64 totals[8] = {0}; u32 const pctas = (n + ZB_PLACE_CTA - 1) / ZB_PLACE_CTA; std::vector<u64> partial(pctas * 4 + 4);
-    simt::launch((n + 127) / 128, 128, [&] { zb_scan_frames(src, segs.data(), n, info.data(), (1ull << 27) + 1); });
+    std::vector<u32> big(n + 1, 0);            // frames above ZB_SCAN_BIG (24 KB in this build) are scanned by a warp each
+    simt::launch((n + 127) / 128, 128, [&] { zb_scan_frames(src, segs.data(), n, info.data(), (1ull << 27) + 1, big.data()); });
+    simt::launch(n < 128 ? (n + 3) / 4 : 32, 128, [&] { zb_scan_frames_big(src, segs.data(), big.data(), info.data()); });
     simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_reduce(info.data(), dst_sizes, n, partial.data()); });
     simt::launch(pctas, ZB_PLACE_CTA, [&] { zb_place_scan(info.data(), dst_sizes, n, partial.data(), place.data(), totals, status.data()); });
     if (totals[0] > out_cap) return -1000;
@@ -323,7 +325,8 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     if (g_block_path) {          // a lane per BLOCK: zb_scan_blocks -> zb_entropy_blocks -> zb_resolve_blocks -> zb_patch_blocks
         u64 const nb = totals[1];
         bdesc.resize(nb + 1); std::vector<ZbBlkExit> bexit(nb + 1); std::vector<u32> erep(3 * (nb + 1)); std::vector<u64> fend(n);
-        simt::launch((n + 63) / 64, 64, [&] { zb_scan_blocks(src, segs.data(), n, place.data(), dict, status.data(), bdesc.data(), fend.data()); });
+        simt::launch((n + 63) / 64, 64, [&] { zb_scan_blocks(src, segs.data(), n, place.data(), dict, status.data(), bdesc.data(), fend.data(), big.data()); });
+        simt::launch(n < 128 ? (n + 3) / 4 : 32, 128, [&] { zb_scan_blocks_big(src, segs.data(), big.data(), place.data(), dict, status.data(), bdesc.data(), fend.data()); });
         simt::launch(n_ctas, 7 * 32, [&] { zb_entropy_blocks<7>(src, bdesc.data(), (u32)nb, blocks.data(), seqs.data(), lits.data(), &counter, dict, status.data(), bexit.data(), take > 3 ? 3 : take); });
         simt::launch((n + 63) / 64, 64, [&] { zb_resolve_blocks(src, segs.data(), n, place.data(), info.data(), dst_sizes, blocks.data(), bdesc.data(), bexit.data(), fend.data(), dict, status.data(), out_sizes.data(), ck.data(), erep.data()); });
         if (nb) simt::launch((unsigned)((nb + 7) / 8), 256, [&] { zb_patch_blocks(blocks.data(), bdesc.data(), nb, seqs.data(), erep.data(), dict, status.data()); });
@@ -366,7 +369,7 @@ def build_decode_sim():
     body = dec[a:b].replace('#include "zb_entropy.cuh"', open(DEC_SRC).read().replace("#pragma once", ""))
     body = re.sub(r"extern __shared__ __align__\(16\) u8 (\w+)\[\];", r"u8* const \1 = simt_dyn_smem;", body)
     text = (LIT_PRELUDE + "#include <cmath>\n#include <vector>\n" + '#include "%s"\n' % os.path.join(csrc, "zb_common.cuh")
-            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n" + body + DSIM_WRAPPERS)
+            + '#include "%s"\n' % os.path.join(HERE, "simt.h") + "alignas(16) static u8 simt_dyn_smem[256 << 10];\n#define ZB_SCAN_BIG 24000u\n" + body + DSIM_WRAPPERS)
     cpp = os.path.join(BUILD, "zd_sim.cpp")
     if not (os.path.exists(DSIM_LIB) and os.path.exists(cpp) and open(cpp).read() == text
             and os.path.getmtime(DSIM_LIB) >= os.path.getmtime(os.path.join(HERE, "simt.h"))):
@@ -422,7 +425,7 @@ extern "C" int t_decode_frame(const u8* src, u64 n, const u8* dict_raw, u32 dict
         } else { dict.content = dict_raw; dict.content_size = dict_n; }
     }
     ZbSegment seg; seg.offset = 0; seg.length = n;
-    ZbFrameInfo fi; zb_scan_frames(src, &seg, 1, &fi, (1ull << 27) + 1);
+    ZbFrameInfo fi; zb_scan_frames(src, &seg, 1, &fi, (1ull << 27) + 1, nullptr);
     if (fi.status != ZB_OK) return (int)fi.status;
     u64 const want = fi.content_size != ZB_CONTENT_UNKNOWN ? fi.content_size : cap;
     if (want > cap) return (int)ZB_E_DSTSIZE_TOO_SMALL;

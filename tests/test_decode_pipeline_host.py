@@ -165,3 +165,41 @@ def test_batches_with_random_damage_follow_the_reference(sim, ref):
             elif st[i] == 0:
                 assert outs[i] == want, (b, i)
     assert healthy == 4 * 44 and rejected > 40
+
+
+def test_damaged_multi_block_frames_follow_the_reference(sim, ref):
+    """Frames of several blocks (in this build anything above 24 KB compressed is scanned by a warp: zb_scan_frames_big /
+    zb_scan_blocks_big), half of them damaged in a header, a table description or a payload, or cut short."""
+    rng = np.random.default_rng(77)
+    text = corpus.text_corpus(2 << 20)
+    segs, frames = [], []
+    for i in range(10):
+        o = int(rng.integers(0, len(text) - 400000)); size = int(rng.integers(140000, 330000))
+        s = bytes(text[o:o + size]) if i % 3 else rng.integers(0, 256, size // 3).astype(np.uint8).tobytes() + bytes(text[o:o + size // 2])
+        segs.append(s); frames.append(ref.compress(s, level=int(rng.integers(1, 5)), checksum=bool(i & 1)))
+    bad = {1, 3, 4, 6, 8}
+    for i in bad:
+        f = bytearray(frames[i])
+        if i % 4 == 0:
+            f = f[:int(rng.integers(len(f) // 3, len(f)))]
+        else:
+            for _ in range(2):
+                f[int(rng.integers(6, len(f)))] ^= 1 << int(rng.integers(0, 8))
+        frames[i] = bytes(f)
+    outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=2, warps=7, take=3, exact_sizes=True)
+    rejected = 0
+    for i, s in enumerate(segs):
+        if i not in bad:
+            assert st[i] == 0 and outs[i] == s, i
+            continue
+        try:
+            want = ref.batch(False, np.frombuffer(frames[i], dtype=np.uint8), np.zeros(1, dtype=np.uint64),
+                             np.array([len(frames[i])], dtype=np.uint64), dst_len=np.array([len(s)], dtype=np.uint64), threads=1)[0].tobytes()
+        except Exception:
+            want = None
+        if want is None:
+            assert st[i] != 0, i
+            rejected += 1
+        elif st[i] == 0:
+            assert outs[i] == want, i
+    assert rejected >= 3
