@@ -166,6 +166,8 @@ int  zb200_profile_read(zb200_ctx* ctx, float ms[ZB200_K_COUNT], uint32_t launch
 const char* zb200_kernel_name(int k);
 /* bytes of intermediate state the last batch call allocated (sequence records, literals, tables) */
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx);
+/* pointer-doubling rounds of the last decompress call that took the pointer-jumping execute stage (0: it did not) */
+int      zb200_last_chase_rounds(const zb200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,7 @@ def lib():
             "zb200_profile_read": (i, [vp, C.POINTER(C.c_float), C.POINTER(u32)]),
             "zb200_kernel_name": (C.c_char_p, [i]),
             "zb200_last_scratch_bytes": (u64, [vp]),
+            "zb200_last_chase_rounds": (i, [vp]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(L, name, None)

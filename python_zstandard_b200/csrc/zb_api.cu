@@ -432,6 +432,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     static int const force_blocks = getenv("ZB200_BLOCK_PATH") ? atoi(getenv("ZB200_BLOCK_PATH")) : -1;
     bool const block_path = force_blocks >= 0 ? force_blocks != 0 : (totals[1] > n && n < 3000);
     bool chase_path = false;
+    ctx->last_chase_rounds = 0;
     if (block_path) {
         u64 const nb = totals[1];
         CK(ctx->bdesc.ensure((nb + 1) * zb_blkdesc_bytes()));
@@ -841,5 +842,6 @@ const char* zb200_kernel_name(int k)
     return (k >= 0 && k < ZB200_K_COUNT && names[k]) ? names[k] : "";
 }
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }
+int zb200_last_chase_rounds(const zb200_ctx* ctx) { return ctx->last_chase_rounds; }
 
 }  // extern "C"

@@ -117,7 +117,7 @@ def build_frame_header():
     src = open(SRC).read()
     a = src.index("__device__ __forceinline__ u32 ze_frame_header")
     b = src.index("\n}\n", a) + 3
-    text = (PRELUDE + "struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; };\n"
+    text = (PRELUDE + "struct ZeParams { u32 checksum; u32 content_size; u32 dict_id; u32 level; u32 window_log = 0; };\n"
             + src[a:b].replace("__device__ __forceinline__", "static inline")
             + 'extern "C" u32 t_frame_header(u8* o, u64 size, u32 checksum, u32 content_size, u32 dict_id)\n'
               "{ ZeParams P; P.checksum = checksum; P.content_size = content_size; P.dict_id = dict_id; P.level = 3; return ze_frame_header(o, size, P); }\n")
@@ -390,6 +390,9 @@ static ZbDim3 zb_tid = {0, 0, 0}, zb_bid = {0, 0, 0}, zb_bdim = {256, 1, 1};
 #define threadIdx zb_tid
 #define blockIdx zb_bid
 #define blockDim zb_bdim
+static ZbDim3 zb_gdim = {1, 1, 1};
+#define gridDim zb_gdim
+template <class T, class U, class V> static inline T atomicCAS(T* p, U cmp, V v) { T o = *p; if (o == (T)cmp) *p = (T)v; return o; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }

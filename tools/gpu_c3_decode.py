@@ -31,3 +31,9 @@ def decode_timed(cblob, coff, clens, label):
 rc, rl = ref.batch(True, blob, off, ln, level=3, threads=os.cpu_count())
 ro = np.concatenate([[0], np.cumsum(rl)[:-1]]).astype(np.uint64)
 decode_timed(rc, ro, rl.astype(np.uint64), "reference-made 128 KiB frames:")
+# (a) our own frames of the same segments: ~10 blocks each, so the batch takes the block-parallel path (ZB200_BLOCK_PATH=0 for the other)
+segs_in = np.stack([off, ln], axis=1).astype(np.uint64)
+coll = zstd.ZstdCompressor(level=3).multi_compress_to_buffer(zstd.BufferWithSegments(blob.tobytes(), segs_in.tobytes()))
+ours = [coll[i].tobytes() for i in range(n)]
+ol = np.array([len(x) for x in ours], dtype=np.uint64); oo = np.concatenate([[0], np.cumsum(ol)[:-1]]).astype(np.uint64)
+decode_timed(np.frombuffer(b"".join(ours), dtype=np.uint8), oo, ol, "our own 128 KiB frames (ZB200_BLOCK_PATH=%s):" % os.environ.get("ZB200_BLOCK_PATH", "auto"))

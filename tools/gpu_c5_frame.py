@@ -23,7 +23,7 @@ for it in range(3):
     assert out == data
     print("decompress(): %.3f s = %.2f GB/s" % (dt, len(data) / dt / 1e9), flush=True)
 ctx.profile(True); out = d.decompress(frame); pr = ctx.profile_read(); ctx.profile(False)
-print("kernels (ms):", {k: round(v[0], 2) for k, v in pr.items()}, flush=True)
+print("kernels (ms):", {k: round(v[0], 2) for k, v in pr.items()}, " pointer-doubling rounds:", ctx.L.zb200_last_chase_rounds(ctx.h), flush=True)
 t0 = time.perf_counter()
 with d.stream_reader(io.BytesIO(frame)) as r:
     n = 0

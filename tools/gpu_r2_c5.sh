@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
 (MB=512 timeout 600 python tools/gpu_c5_frame.py) 2>&1 | tail -n 8
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 4
-(N=200 timeout 300 python tools/gpu_c3_decode.py) 2>&1 | tail -n 3
