@@ -429,8 +429,11 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
     }
     // Frames of several blocks when the batch alone does not fill the machine (one huge frame at the limit): a lane per BLOCK
     // instead of a lane per frame for the entropy stage (zb_scan_blocks -> zb_entropy_blocks -> zb_resolve_blocks / zb_patch_blocks)
-    static int const force_blocks = getenv("ZB200_BLOCK_PATH") ? atoi(getenv("ZB200_BLOCK_PATH")) : -1;
-    bool const block_path = force_blocks >= 0 ? force_blocks != 0 : (totals[1] > n && n < 3000);
+    // Measured (tools/gpu_c3_decode.py, tools/gpu_c5_frame.py): frames of one 128 KiB chunk -- the reference's single block or
+    // our ten sub-blocks -- are faster a lane per frame at any batch size (2048 of ours: 18.4 vs 6.6 GB/s); from a few full
+    // blocks per frame on the lane's serial chain (4-5 ms per 128 KiB) is what the block path removes.
+    int const force_blocks = getenv("ZB200_BLOCK_PATH") ? atoi(getenv("ZB200_BLOCK_PATH")) : -1;      // (read per call: tests switch it)
+    bool const block_path = force_blocks >= 0 ? force_blocks != 0 : (totals[1] > n && n < 3000 && totals[0] >= (u64)n * (512u << 10));
     bool chase_path = false;
     ctx->last_chase_rounds = 0;
     if (block_path) {
@@ -442,7 +445,7 @@ static int run_decompress(zb200_ctx* ctx, const u8* d_src, const ZbSegment* d_se
         CK(ctx->wave.ensure(zb_wave_bytes(nf, nb)));
         // FEW frames of many blocks (one huge frame at the limit): the copy-execute chain of a frame is serial however it is
         // mapped, so it is shortened by pointer doubling instead (zb_chase_*); many frames keep the machine busy frame-parallel
-        static int const force_chase = getenv("ZB200_CHASE") ? atoi(getenv("ZB200_CHASE")) : -1;
+        int const force_chase = getenv("ZB200_CHASE") ? atoi(getenv("ZB200_CHASE")) : -1;
         chase_path = force_chase >= 0 ? force_chase != 0 : (nf < 64 && nb >= 8ull * nf);
         if (chase_path && ctx->chase.ensure(zb_chase_bytes(totals[0])) != cudaSuccess) { cudaGetLastError(); chase_path = false; }
         { KSpan s(ctx, ZB200_K_SCAN);
