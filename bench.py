@@ -421,6 +421,23 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     assert last == blob[-FRAME:].tobytes()
 
+    # ---------------- the same call with DEVICE buffers: DeviceBufferWithSegments in, DeviceBufferWithSegments
+    # out through the public Python API -- what a GPU-resident caller (torch tensors) sees; only the segment table crosses PCIe
+    dbuf = zstd.DeviceBufferWithSegments(d_src[:Cb], segs.tobytes())
+    for _ in range(args.warmup):
+        r = dctx.multi_decompress_to_buffer(dbuf)
+        del r
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = dctx.multi_decompress_to_buffer(dbuf)
+        if _ + 1 < args.steps:
+            del r
+    barrier()
+    dev_api_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    assert r[n_frames - 1].tobytes() == blob[-FRAME:].tobytes()
+    del r
+
     # ---------------- secondary arm: multi_compress_to_buffer on 128 KiB Silesia-mix segments (configs[2], scaled)
     # BASELINE.json configs[2] in full: 65536 x 128 KiB, ONE batch cut by segment index over the ranks (strong scaling:
     # every GPU gets 65536 / N segments, no data-path collective).  ZB_BENCH_COMPRESS_SEGMENTS shrinks it for experiments.
@@ -481,10 +498,10 @@ def main():
     ctx.profile(False)
     del d_cin, cpin, cbws, cctx
 
-    times = torch.tensor([dev_ms, e2e_ms, comp_ms, comp_e2e_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_ms, comp_ms, comp_e2e_ms, dev_api_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, comp_ms, comp_e2e_ms = (float(times[i]) for i in range(4))
+    dev_ms, e2e_ms, comp_ms, comp_e2e_ms, dev_api_ms = (float(times[i]) for i in range(5))
 
     # ---------------- one call, one batch, N devices: the in-process partition (threads -> devices) of the public API
     sharded = None
@@ -597,6 +614,10 @@ def main():
         "e2e": {"value": world * U / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": Cb + 16 * n_frames, "d2h_bytes_per_step": U + 16 * n_frames,
                 "api": "ZstdDecompressor.multi_decompress_to_buffer(BufferWithSegments in pinned host memory)"},
+        "device_api": {"value": world * U / (dev_api_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": dev_api_ms,
+                       "h2d_bytes_per_step": 16 * n_frames, "d2h_bytes_per_step": 0,
+                       "api": "ZstdDecompressor.multi_decompress_to_buffer(DeviceBufferWithSegments) -> DeviceBufferWithSegments: the "
+                              "public Python call for GPU-resident callers (wall clock, result checked)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -79,6 +79,9 @@ int   zb200_memcpy_d2h(zb200_ctx* ctx, void* dst, const void* src, size_t bytes)
    buffer is bound by page faults on one thread (~3 GB/s); the reference writes into its PyBytes in place
    (c-ext/decompressor.c:283-352), this is the equivalent step after the device-to-host copy */
 void  zb200_host_copy(void* dst, const void* src, size_t bytes);
+/* the device a pointer belongs to (cudaPointerGetAttributes), -1 for host memory: device-resident callers hand in
+   buffers they did not get from zb200_device_alloc (a torch tensor, a __cuda_array_interface__ object) */
+int   zb200_pointer_device(const void* p);
 
 /* ---- dictionaries (device-resident digest) */
 int  zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddict** out);

@@ -7,12 +7,13 @@ buffer types) so a caller can ``import python_zstandard_b200 as zstandard``:
     ZstdDecompressor(...).multi_decompress_to_buffer / .decompress
     BufferWithSegments, BufferSegments, BufferSegment, BufferWithSegmentsCollection
     ZstdCompressionDict, ZstdError, frame helpers and constants
+    DeviceBufferWithSegments (not in the reference): the same batch calls on device-resident data, device-resident results
 
 All codec work runs as CUDA kernels in ``libzb200.so`` (C ABI: include/zb200.h).
 """
 from .errors import ZstdError  # noqa: F401
 from .buffers import (BufferSegment, BufferSegments, BufferWithSegments,  # noqa: F401
-                      BufferWithSegmentsCollection)
+                      BufferWithSegmentsCollection, DeviceBufferWithSegments, DeviceBufferSegment)
 from .dictionary import (ZstdCompressionDict, DICT_TYPE_AUTO, DICT_TYPE_RAWCONTENT,  # noqa: F401
                          DICT_TYPE_FULLDICT)
 from .decompressor import ZstdDecompressor, FORMAT_ZSTD1, FORMAT_ZSTD1_MAGICLESS  # noqa: F401
@@ -24,7 +25,7 @@ from .streams import (COMPRESSOBJ_FLUSH_FINISH, COMPRESSOBJ_FLUSH_BLOCK, DECOMPR
 
 __version__ = "0.25.0+b200"
 backend = "b200"
-backend_features = {"buffer_types", "multi_compress_to_buffer", "multi_decompress_to_buffer"}
+backend_features = {"buffer_types", "multi_compress_to_buffer", "multi_decompress_to_buffer", "device_buffers"}
 
 ZSTD_VERSION = (1, 5, 7)
 FRAME_HEADER = b"\x28\xb5\x2f\xfd"

@@ -66,6 +66,7 @@ def lib():
             "zb200_memcpy_h2d": (i, [vp, vp, vp, sz]),
             "zb200_memcpy_d2h": (i, [vp, vp, vp, sz]),
             "zb200_host_copy": (None, [vp, vp, sz]),
+            "zb200_pointer_device": (i, [vp]),
             "zb200_ddict_create": (i, [vp, vp, sz, C.POINTER(vp)]),
             "zb200_ddict_free": (None, [vp]),
             "zb200_ddict_id": (u32, [vp]),

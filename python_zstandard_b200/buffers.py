@@ -128,6 +128,131 @@ class BufferWithSegments:
         pass
 
 
+class DeviceBufferSegment:
+    """One item of a DeviceBufferWithSegments: a view of device memory (``__cuda_array_interface__``), ``tobytes()`` copies
+    it to the host."""
+
+    __slots__ = ("_parent", "_offset", "_length")
+
+    def __init__(self, parent, offset, length):
+        self._parent, self._offset, self._length = parent, offset, length
+
+    @property
+    def offset(self):
+        return self._offset
+
+    def __len__(self):
+        return self._length
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self._length,), "typestr": "|u1", "data": (self._parent._ptr + self._offset, False), "version": 3}
+
+    def tobytes(self):
+        return self._parent._download(self._offset, self._length)
+
+
+class DeviceBufferWithSegments:
+    """BufferWithSegments whose bytes stay in DEVICE memory: the batch calls take it without a
+    host->device copy and -- given one -- return one, so the user-visible rate is the kernels', not PCIe's.
+
+    ``data``: any object with ``__cuda_array_interface__`` (a torch CUDA tensor, a cupy array, another of these), 1-D bytes;
+    it must be ready (no kernel of another stream still writing it) when a batch call reads it.  ``segments``: the same
+    ``{u64 offset; u64 length}`` table as BufferWithSegments takes (host memory).  The object exposes
+    ``__cuda_array_interface__`` itself: ``torch.as_tensor(buf, device="cuda")`` is a zero-copy view."""
+
+    def __init__(self, data, segments):
+        from . import _native
+        cai = getattr(data, "__cuda_array_interface__", None)
+        if cai is None:
+            raise TypeError("data must expose __cuda_array_interface__ (a CUDA tensor or array)")
+        shape = cai["shape"]
+        if len(shape) != 1 or cai.get("strides") not in (None, (np_itemsize(cai["typestr"]),)):
+            raise TypeError("data must be a contiguous 1-D device array")
+        size = int(shape[0]) * np_itemsize(cai["typestr"])
+        ptr = int(cai["data"][0]) if size else 0
+        seg = bytes(memoryview(segments))
+        if len(seg) % SEGMENT_SIZE:
+            raise ValueError("segments array size is not a multiple of %d" % SEGMENT_SIZE)
+        n = len(seg) // SEGMENT_SIZE
+        for i in range(n):
+            off, length = _SEG.unpack_from(seg, i * SEGMENT_SIZE)
+            if off + length > size:
+                raise ValueError("offset within segments array references memory outside buffer")
+        dev = _native.lib().zb200_pointer_device(ptr) if size else 0
+        if dev < 0:
+            raise TypeError("data does not live in device memory")
+        self._keep = data            # keeps the caller's allocation alive
+        self._ptr, self._size, self._segments, self._count, self._device = ptr, size, seg, n, dev
+        self._owner = None
+
+    @classmethod
+    def _from_result(cls, ctx, handle):
+        """A device-resident result of libzb200 (zb200_result with ZB200_DST_DEVICE): the result owns its allocation."""
+        L = ctx.L
+        self = cls.__new__(cls)
+        n = L.zb200_result_count(handle)
+        self._keep = None
+        self._ptr = L.zb200_result_data(handle) or 0
+        self._size = L.zb200_result_size(handle)
+        self._segments = C.string_at(L.zb200_result_segments(handle), n * SEGMENT_SIZE) if n else b""
+        self._count = n
+        self._device = ctx.device
+        self._ctx = ctx
+        self._owner = weakref.finalize(self, L.zb200_result_free, handle)
+        return self
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def size(self):
+        return self._size
+
+    def __len__(self):
+        return self._count
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self._size,), "typestr": "|u1", "data": (self._ptr, False), "version": 3}
+
+    def segments(self):
+        return BufferSegments(self, self._segments)
+
+    def __getitem__(self, i):
+        if i < 0:
+            raise IndexError("offset must be non-negative")
+        if i >= self._count:
+            raise IndexError("offset must be less than %d" % self._count)
+        off, length = _SEG.unpack_from(self._segments, i * SEGMENT_SIZE)
+        return DeviceBufferSegment(self, off, length)
+
+    def _download(self, offset, length):
+        from . import _native
+        if not length:
+            return b""
+        ctx = _native.Context.get(self._device)
+        out = bytearray(length)
+        dst = (C.c_ubyte * length).from_buffer(out)
+        with ctx.lock:
+            rc = ctx.L.zb200_memcpy_d2h(ctx.h, C.addressof(dst), self._ptr + offset, length)
+        del dst
+        ctx.check(rc, "zb200_memcpy_d2h")
+        return bytes(out)
+
+    def tobytes(self):
+        return self._download(0, self._size)
+
+    def to_host(self):
+        """The same items as an ordinary BufferWithSegments (one device->host copy)."""
+        return BufferWithSegments(self.tobytes(), self._segments)
+
+
+def np_itemsize(typestr):
+    return int(typestr[2:]) if len(typestr) > 2 else 1
+
+
 class BufferWithSegmentsCollection:
     """Several BufferWithSegments addressed as one flat sequence (bufferutil.c:372-520)."""
 

@@ -320,6 +320,13 @@ void zb200_host_copy(void* dst, const void* src, size_t bytes)
     for (auto& x : th) x.join();
 }
 
+int zb200_pointer_device(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged ? a.device : -1;
+}
+
 // ---------------------------------------------------------------- dictionaries
 int zb200_ddict_create(zb200_ctx* ctx, const void* dict, size_t size, zb200_ddict** out)
 {
