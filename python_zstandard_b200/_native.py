@@ -13,6 +13,7 @@ _LIB_PATH = os.environ.get("ZB200_LIB") or os.path.join(_HERE, "libzb200.so")   
 K_COUNT = 16
 SRC_DEVICE = 1
 DST_DEVICE = 2
+SEGS_HOST = 8
 
 
 class Segment(C.Structure):

@@ -202,20 +202,13 @@ class ZstdCompressor:
             raise ValueError("source elements are empty")
         ctx = _native.Context.get(data.device)
         L = ctx.L
-        d_segs = L.zb200_device_alloc(ctx.h, len(data._segments))
-        if not d_segs:
-            raise MemoryError("device allocation of the segment table failed")
-        try:
-            dd = self._dict(ctx)
-            p = self._params()
-            res = C.c_void_p()
-            with ctx.lock:
-                ctx.check(L.zb200_memcpy_h2d(ctx.h, d_segs, data._segments, len(data._segments)), "zb200_memcpy_h2d")
-                rc = L.zb200_compress_batch(ctx.h, data._ptr, d_segs, n, C.byref(p), dd,
-                                            _native.SRC_DEVICE | _native.DST_DEVICE, C.byref(res))
-            ctx.check(rc, "zb200_compress_batch")
-        finally:
-            L.zb200_device_free(ctx.h, d_segs)
+        dd = self._dict(ctx)
+        p = self._params()
+        res = C.c_void_p()
+        with ctx.lock:
+            rc = L.zb200_compress_batch(ctx.h, data._ptr, data._segments, n, C.byref(p), dd,
+                                        _native.SRC_DEVICE | _native.DST_DEVICE | _native.SEGS_HOST, C.byref(res))
+        ctx.check(rc, "zb200_compress_batch")
         return DeviceBufferWithSegments._from_result(ctx, res)
 
     # one call keeps the whole device busy for milliseconds per 128 KiB block, so sub-batches only pay once a

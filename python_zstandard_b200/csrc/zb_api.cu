@@ -548,7 +548,16 @@ static int decompress_common(zb200_ctx* ctx, const void* src_base, const zb200_s
     if (!ctx || !segs || n == 0 || n > 0x7FFFFFF0u) return fail(ctx, "zb200_decompress_batch: bad arguments", cudaSuccess);
     cudaSetDevice(ctx->device);
     const u8* d_src; const ZbSegment* d_segs; const u64* d_dst_sizes = nullptr;
-    if (flags & ZB200_SRC_DEVICE) {
+    if ((flags & ZB200_SRC_DEVICE) && (flags & ZB200_SEGS_HOST)) {
+        // the frames are on the device, their table (and the sizes) on the host: only those are uploaded
+        CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
+        if (dst_sizes) CK(ctx->dst_sizes.ensure(n * sizeof(u64)));
+        CK(cudaMemcpyAsync(ctx->segs.p, segs, n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        if (dst_sizes) CK(cudaMemcpyAsync(ctx->dst_sizes.p, dst_sizes, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));          // (the caller's tables may go away)
+        d_src = (const u8*)src_base; d_segs = ctx->segs.as<ZbSegment>();
+        if (dst_sizes) d_dst_sizes = ctx->dst_sizes.as<u64>();
+    } else if (flags & ZB200_SRC_DEVICE) {
         d_src = (const u8*)src_base; d_segs = (const ZbSegment*)segs; d_dst_sizes = dst_sizes;
     } else {
         // host input: one contiguous copy of the referenced span (the data a BufferWithSegments holds)
@@ -639,7 +648,13 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     std::vector<zb200_segment> hsegs;
     const u8* d_src; const ZbSegment* d_segs;
     const u8* up_src = nullptr; u64 up_bytes = 0;          // host input to upload while the kernel runs
-    if (flags & ZB200_SRC_DEVICE) {
+    if ((flags & ZB200_SRC_DEVICE) && (flags & ZB200_SEGS_HOST)) {
+        hsegs.assign(segs, segs + n);
+        CK(ctx->segs.ensure(n * sizeof(ZbSegment)));
+        CK(cudaMemcpyAsync(ctx->segs.p, segs, n * sizeof(ZbSegment), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));          // (the caller's table may go away)
+        d_src = (const u8*)src_base; d_segs = ctx->segs.as<ZbSegment>();
+    } else if (flags & ZB200_SRC_DEVICE) {
         hsegs.resize(n);
         CK(cudaMemcpyAsync(hsegs.data(), segs, n * sizeof(ZbSegment), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
