@@ -167,7 +167,7 @@ _bytes_data.argtypes = [C.py_object]
 
 def bytes_from_address(addr, n):
     """bytes(n) filled from host memory at addr; large results are copied on several threads (zb200_host_copy)."""
-    if n < (8 << 20):
+    if n < (2 << 20):
         return C.string_at(addr, n) if n else b""
     b = _bytes_new(None, n)
     lib().zb200_host_copy(_bytes_data(b), addr, n)

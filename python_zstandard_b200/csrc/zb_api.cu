@@ -304,9 +304,9 @@ int zb200_memcpy_d2h(zb200_ctx* ctx, void* dst, const void* src, size_t bytes)
 
 void zb200_host_copy(void* dst, const void* src, size_t bytes)
 {
-    size_t const piece = 4u << 20;
+    size_t const piece = 1u << 20;
     unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 4;
-    size_t nt = bytes / (8u << 20); if (nt > 16) nt = 16; if (nt > hw) nt = hw;
+    size_t nt = bytes / piece; if (nt > 16) nt = 16; if (nt > hw) nt = hw;
     if (nt < 2) { memcpy(dst, src, bytes); return; }
     size_t const n_pieces = (bytes + piece - 1) / piece;
     std::vector<std::thread> th;
