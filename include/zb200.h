@@ -173,6 +173,9 @@ const char* zb200_kernel_name(int k);
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx);
 /* pointer-doubling rounds of the last decompress call that took the pointer-jumping execute stage (0: it did not) */
 int      zb200_last_chase_rounds(const zb200_ctx* ctx);
+/* the block kernel the last compress call ran: "zb_compress_smem", "zb_compress_recs" or "zb_compress_blocks" (they share the
+   profile slot named zb_compress_blocks) */
+const char* zb200_last_compress_kernel(const zb200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,7 @@ def lib():
             "zb200_kernel_name": (C.c_char_p, [i]),
             "zb200_last_scratch_bytes": (u64, [vp]),
             "zb200_last_chase_rounds": (i, [vp]),
+            "zb200_last_compress_kernel": (C.c_char_p, [vp]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(L, name, None)

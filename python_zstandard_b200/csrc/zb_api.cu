@@ -109,6 +109,7 @@ struct zb200_ctx {
     DevBuf biglist;                           // frames whose scans are a warp's work (zb_scan_frames_big)
     DevBuf chase;                             // its pointer-jumping execute stage: a source pointer per output byte
     int last_chase_rounds = 0;
+    const char* last_compress_kernel = "";    // which of the three block kernels the last compress call ran (profile slot zb_compress_blocks)
     u32 entropy_warps = 0;
     // pinned pool
     std::mutex mu;
@@ -719,6 +720,7 @@ static int compress_common(zb200_ctx* ctx, const void* src_base, const zb200_seg
     bool const overlap_upload = up_bytes != 0 && nj != 0 && ctx->h_progress != nullptr;
     if (up_bytes && !overlap_upload) CK(cudaMemcpyAsync(ctx->src.p, up_src, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (overlap_upload) { CK(cudaEventRecord(ctx->chunk_ev[0], ctx->stream)); CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0)); }
+    ctx->last_compress_kernel = recs_kernel ? "zb_compress_recs" : (smem_kernel ? "zb_compress_smem" : "zb_compress_blocks");
     if (recs_kernel) { KSpan s(ctx, ZB200_K_COMPRESS);
       zb_launch_compress_recs(d_src, ctx->jobs.p, (u32)nj, ctas, ctx->slots.as<u8>(), slot_bytes, ctx->bouts.p, d_counter,
                               dict->c_tail, dict->c_D, dict->d_ctable, (const void*)dict->d_digest, dict->d_cct,
@@ -868,5 +870,6 @@ const char* zb200_kernel_name(int k)
 }
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }
 int zb200_last_chase_rounds(const zb200_ctx* ctx) { return ctx->last_chase_rounds; }
+const char* zb200_last_compress_kernel(const zb200_ctx* ctx) { return ctx->last_compress_kernel; }
 
 }  // extern "C"
