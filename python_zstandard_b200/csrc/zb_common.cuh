@@ -45,9 +45,10 @@ struct ZbSegment { u64 offset, length; };       // == BufferSegment, c-ext/pytho
 // result of the frame scan (one per frame)
 struct ZbFrameInfo {
     u64 content_size;     // from the header, ZB_CONTENT_UNKNOWN if absent
+    u64 n_seq_rec;        // sequence records needed: sum(nbSeq + 1) over compressed blocks
+    u64 n_lit;            // literal bytes that must be regenerated into scratch (Huffman coded); 64-bit: an 8 GiB frame can
+                          //   hold more than 4 GiB of them
     u32 n_blocks;
-    u32 n_seq_rec;        // sequence records needed: sum(nbSeq + 1) over compressed blocks
-    u32 n_lit;            // literal bytes that must be regenerated into scratch (Huffman coded)
     u32 status;
     u32 dict_id;
     u32 flags;            // bit0: checksum present

@@ -189,8 +189,8 @@ zb_scan_frames_big(const u8* __restrict__ src, const ZbSegment* __restrict__ seg
         }
         #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { n_lit += __shfl_xor_sync(0xFFFFFFFFu, n_lit, d); n_seq_rec += __shfl_xor_sync(0xFFFFFFFFu, n_seq_rec, d); }
-        if (!err && (n_lit > 0xFFFFFFFFull || n_seq_rec > 0xFFFFFFFFull || n_blocks > 0xFFFFFFFFull)) err = ZB_E_MEMORY;
-        fi.status = err; fi.n_lit = (u32)n_lit; fi.n_seq_rec = (u32)n_seq_rec; fi.n_blocks = (u32)n_blocks;
+        if (!err && n_blocks > 0xFFFFFFFFull) err = ZB_E_MEMORY;
+        fi.status = err; fi.n_lit = n_lit; fi.n_seq_rec = n_seq_rec; fi.n_blocks = (u32)n_blocks;
         if (lane == 0) info[f] = fi;
     }
 }
@@ -201,7 +201,7 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const u8* s = src + segs[f].offset; u64 n = segs[f].length;
-    u64 n_lit = 0, n_seq_rec = 0, n_blocks = 0;         // 64-bit while counting: a frame of >= 4 GiB of literals must fail, not wrap
+    u64 n_lit = 0, n_seq_rec = 0, n_blocks = 0;
     ZbFrameInfo fi; fi.content_size = ZB_CONTENT_UNKNOWN; fi.n_blocks = 0; fi.n_seq_rec = 0; fi.n_lit = 0;
     fi.status = ZB_OK; fi.dict_id = 0; fi.flags = 0;
     if (!zb_skip_skippable(s, n)) { fi.status = ZB_E_SRCSIZE_WRONG; info[f] = fi; return; }
@@ -229,8 +229,8 @@ __global__ void zb_scan_frames(const u8* __restrict__ src, const ZbSegment* __re
         pos += bsize;
         if (bh & 1) break;
     }
-    if (fi.status == ZB_OK && (n_lit > 0xFFFFFFFFull || n_seq_rec > 0xFFFFFFFFull || n_blocks > 0xFFFFFFFFull)) fi.status = ZB_E_MEMORY;
-    fi.n_lit = (u32)n_lit; fi.n_seq_rec = (u32)n_seq_rec; fi.n_blocks = (u32)n_blocks;
+    if (fi.status == ZB_OK && n_blocks > 0xFFFFFFFFull) fi.status = ZB_E_MEMORY;
+    fi.n_lit = n_lit; fi.n_seq_rec = n_seq_rec; fi.n_blocks = (u32)n_blocks;
     info[f] = fi;
 }
 
