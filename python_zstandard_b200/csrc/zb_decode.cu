@@ -1448,6 +1448,13 @@ __device__ static u64 zb_xxh64(const u8* p, u64 len)
     return h;
 }
 
+// Frames of ZB_XXH_BIG bytes and more are not hashed by a single lane (byte loads from global memory, one frame = one chain):
+// zb_verify_checksums_big gives each a CTA.
+#ifndef ZB_XXH_BIG
+#define ZB_XXH_BIG (256u << 10)
+#endif
+#define ZB_XXH_TILE 16384u               // bytes per shared-memory tile (two tiles)
+
 __global__ void zb_verify_checksums(const u8* __restrict__ dst, const ZbFramePlace* __restrict__ place, const u64* __restrict__ out_sizes,
                                     const ZbFrameInfo* __restrict__ info, const u32* __restrict__ ck_expect, u32 first, u32 n_frames,
                                     u32* __restrict__ status)
@@ -1455,8 +1462,73 @@ __global__ void zb_verify_checksums(const u8* __restrict__ dst, const ZbFramePla
     u32 const f = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     if (status[f] != ZB_OK || !(info[f].flags & 1)) return;
+    if (out_sizes[f] >= ZB_XXH_BIG) return;                            // zb_verify_checksums_big's
     u64 const h = zb_xxh64(dst + place[f].dst_off, out_sizes[f]);
     if ((u32)h != ck_expect[f]) status[f] = ZB_E_CHECKSUM_WRONG;
+}
+
+// XXH64 of one large frame per CTA (zstd/zstd.c:44260-44277 over XXH64_update's stripe loop).  The four accumulators are
+// four serial chains (rotate-multiply per 32-byte stripe: no way around ~25 cycles per stripe, 2.4 GB/s per frame), so the
+// kernel only makes sure nothing else is on them: warps 1-3 stage the next 16 KiB tile in shared memory with 128-bit loads
+// while lanes 0-3 of warp 0 consume the current one with aligned 64-bit shared-memory reads.
+__global__ void __launch_bounds__(128)
+zb_verify_checksums_big(const u8* __restrict__ dst, const ZbFramePlace* __restrict__ place, const u64* __restrict__ out_sizes,
+                        const ZbFrameInfo* __restrict__ info, const u32* __restrict__ ck_expect, u32 first, u32 n_frames,
+                        u32* __restrict__ status)
+{
+    __shared__ __align__(16) u8 s_tile[2][ZB_XXH_TILE + 16];
+    u64 const P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull;
+    u32 const tid = threadIdx.x;
+    for (u32 f = first + blockIdx.x; f < n_frames; f += gridDim.x) {
+        if (status[f] != ZB_OK || !(info[f].flags & 1)) continue;
+        u64 const len = out_sizes[f];
+        if (len < ZB_XXH_BIG) continue;
+        const u8* const p0 = dst + place[f].dst_off;
+        u64 const n_stripes = len >> 5;
+        u32 const mis = (u32)((uintptr_t)p0 & 15);                     // tiles are staged from 16-byte aligned addresses
+        const u8* const a0 = p0 - mis;
+        u64 const n_tiles = (n_stripes * 32 + ZB_XXH_TILE - 1) / ZB_XXH_TILE;
+        u64 v = tid == 0 ? P1 + P2 : (tid == 1 ? P2 : (tid == 2 ? 0ull : 0ull - P1));
+        __syncthreads();                                               // (the tiles are free)
+        for (u64 t = 0; t <= n_tiles; t++) {
+            if (tid >= 32 && t < n_tiles) {                            // stage tile t
+                u64 const off = t * ZB_XXH_TILE;
+                u64 const bytes = min((u64)ZB_XXH_TILE + 16, (n_stripes * 32 + mis + 15 - off) & ~15ull);
+                const uint4* g = (const uint4*)(a0 + off); uint4* d = (uint4*)s_tile[t & 1];
+                for (u32 i = tid - 32; i < bytes / 16; i += 96) d[i] = __ldcg(g + i);
+            }
+            if (tid < 4 && t > 0) {                                    // consume tile t - 1
+                u64 const off = (t - 1) * ZB_XXH_TILE;
+                u64 const left = n_stripes * 32 - off;
+                u32 const ns = (u32)(left < ZB_XXH_TILE ? left : ZB_XXH_TILE) >> 5;
+                const u8* const base = s_tile[(t - 1) & 1] + mis + tid * 8;
+                u32 const sh = (u32)((uintptr_t)base & 7) * 8;
+                const u64* q = (const u64*)(base - (sh >> 3));
+                if (sh == 0) for (u32 k = 0; k < ns; k++) { u64 const x = q[k * 4]; v = ((v + x * P2) << 31 | (v + x * P2) >> 33) * P1; }
+                else for (u32 k = 0; k < ns; k++) { u64 const x = (q[k * 4] >> sh) | (q[k * 4 + 1] << (64 - sh)); v = ((v + x * P2) << 31 | (v + x * P2) >> 33) * P1; }
+            }
+            __syncthreads();
+        }
+        // the four accumulators -> lane 0; the tail (< 32 bytes) and the avalanche as in zb_xxh64
+        __shared__ u64 s_v[4];
+        if (tid < 4) s_v[tid] = v;
+        __syncthreads();
+        if (tid == 0) {
+            auto rotl = [](u64 x, int r) { return (x << r) | (x >> (64 - r)); };
+            auto round = [&](u64 acc, u64 in) { return rotl(acc + in * P2, 31) * P1; };
+            u64 const P5 = 0x27D4EB2F165667C5ull;
+            u64 h = rotl(s_v[0], 1) + rotl(s_v[1], 7) + rotl(s_v[2], 12) + rotl(s_v[3], 18);
+            h = (h ^ round(0, s_v[0])) * P1 + P4; h = (h ^ round(0, s_v[1])) * P1 + P4; h = (h ^ round(0, s_v[2])) * P1 + P4; h = (h ^ round(0, s_v[3])) * P1 + P4;
+            h += len;
+            const u8* p = p0 + n_stripes * 32; const u8* const end = p0 + len;
+            while (p + 8 <= end) { h ^= round(0, zb_rd64(p)); h = rotl(h, 27) * P1 + P4; p += 8; }
+            if (p + 4 <= end) { h ^= (u64)zb_rd32(p) * P1; h = rotl(h, 23) * P2 + P3; p += 4; }
+            while (p < end) { h ^= (*p++) * P5; h = rotl(h, 11) * P1; }
+            h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+            if ((u32)h != ck_expect[f]) status[f] = ZB_E_CHECKSUM_WRONG;
+        }
+        __syncthreads();
+    }
 }
 
 // ===========================================================================
@@ -1667,6 +1739,7 @@ void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_s
 {
     u32 const n = end - first;
     zb_verify_checksums<<<(n + 127) / 128, 128, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
+    zb_verify_checksums_big<<<n < 592 ? n : 592, 128, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
 }
 
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,

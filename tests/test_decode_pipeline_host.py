@@ -203,3 +203,18 @@ def test_damaged_multi_block_frames_follow_the_reference(sim, ref):
         elif st[i] == 0:
             assert outs[i] == want, i
     assert rejected >= 3
+
+
+def test_content_checksum_of_large_frames(sim, ref):
+    """Frames above ZB_XXH_BIG (50 KB in this build, 256 KiB on the device) are hashed by a CTA each (zb_verify_checksums_big):
+    every alignment of the frame's start in the output, a length that is not a multiple of 32, and a wrong checksum."""
+    text = corpus.text_corpus(1 << 20)
+    segs = [bytes(text[100:100 + 3 + 7 * i]) for i in range(5)] + [bytes(text[5000 * i:5000 * i + 60000 + 13 * i]) for i in range(1, 18)]
+    frames = [ref.compress(s, level=3, checksum=True) for s in segs]
+    bad = bytearray(frames[9]); bad[-2] ^= 0x40; frames[9] = bytes(bad)
+    outs, st = decompress(sim, frames, [len(s) for s in segs], n_ctas=2, warps=7, take=3, exact_sizes=True)
+    for i, s in enumerate(segs):
+        if i == 9:
+            assert st[i] != 0
+        else:
+            assert st[i] == 0 and outs[i] == s, i

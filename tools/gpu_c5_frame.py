@@ -11,7 +11,7 @@ mb = int(os.environ.get("MB", "256"))
 t = corpus.text_corpus(8 << 20)
 data = np.tile(t, (mb << 20) // len(t) + 1)[:mb << 20].tobytes()
 ref = RefZstd()
-t0 = time.perf_counter(); frame = ref.compress(data, level=3, checksum=False); tc = time.perf_counter() - t0
+t0 = time.perf_counter(); frame = ref.compress(data, level=3, checksum=os.environ.get("CK", "0") == "1"); tc = time.perf_counter() - t0
 t0 = time.perf_counter(); back = ref.decompress(frame, len(data)); td = time.perf_counter() - t0
 assert back == data
 print("frame: %d MiB -> %.1f MiB, %d blocks; reference (1 thread): compress %.2f GB/s, decompress %.2f GB/s" % (
