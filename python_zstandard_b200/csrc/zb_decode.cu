@@ -1493,7 +1493,8 @@ zb_verify_checksums_big(const u8* __restrict__ dst, const ZbFramePlace* __restri
         for (u64 t = 0; t <= n_tiles; t++) {
             if (tid >= 32 && t < n_tiles) {                            // stage tile t
                 u64 const off = t * ZB_XXH_TILE;
-                u64 const bytes = min((u64)ZB_XXH_TILE + 16, (n_stripes * 32 + mis + 15 - off) & ~15ull);
+                u64 const rest = (n_stripes * 32 + mis + 15 - off) & ~15ull;
+                u64 const bytes = rest < (u64)ZB_XXH_TILE + 16 ? rest : (u64)ZB_XXH_TILE + 16;
                 const uint4* g = (const uint4*)(a0 + off); uint4* d = (uint4*)s_tile[t & 1];
                 for (u32 i = tid - 32; i < bytes / 16; i += 96) d[i] = __ldcg(g + i);
             }
