@@ -34,3 +34,13 @@ with d.stream_reader(io.BytesIO(frame)) as r:
 dt = time.perf_counter() - t0
 assert n == len(data)
 print("stream_reader: %.3f s = %.2f GB/s" % (dt, len(data) / dt / 1e9), flush=True)
+# one-shot compress() of the same large buffer: one frame of independent 128 KiB blocks
+c = zstd.ZstdCompressor(level=3)
+for it in range(2):
+    t0 = time.perf_counter(); ours = c.compress(data); dt = time.perf_counter() - t0
+print("compress(): %.3f s = %.2f GB/s, %.1f MiB (reference level 3: %.1f MiB, %+.2f %%)" % (
+    dt, len(data) / dt / 1e9, len(ours) / 2**20, len(frame) / 2**20, 100.0 * (len(ours) / len(frame) - 1)), flush=True)
+assert ref.decompress(ours, len(data)) == data
+t0 = time.perf_counter(); back = d.decompress(ours); dt = time.perf_counter() - t0
+assert back == data
+print("decompress() of our own frame: %.3f s = %.2f GB/s" % (dt, len(data) / dt / 1e9), flush=True)
