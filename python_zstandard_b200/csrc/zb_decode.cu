@@ -1468,50 +1468,62 @@ __global__ void zb_verify_checksums(const u8* __restrict__ dst, const ZbFramePla
 }
 
 // XXH64 of one large frame per CTA (zstd/zstd.c:44260-44277 over XXH64_update's stripe loop).  The four accumulators are
-// four serial chains (rotate-multiply per 32-byte stripe: no way around ~25 cycles per stripe, 2.4 GB/s per frame), so the
-// kernel only makes sure nothing else is on them: warps 1-3 stage the next 16 KiB tile in shared memory with 128-bit loads
-// while lanes 0-3 of warp 0 consume the current one with aligned 64-bit shared-memory reads.
-__global__ void __launch_bounds__(128)
+// four serial chains -- 64-bit add, rotate, 64-bit multiply per 32-byte stripe, ~27 cycles of dependent latency, no algebra
+// gets around the rotate -- so a frame hashes at ~2 GB/s however many threads there are; the kernel only makes sure NOTHING
+// ELSE sits on those chains: threads 32-255 stage the next 16 KiB tile in shared memory, realigned to the frame's start
+// (two 32-bit loads and a funnel shift per word), while lanes 0-3 of warp 0 consume the current one with one aligned
+// 64-bit read per stripe, the products in * P2 of the next four stripes computed in the shadow of the current four rounds.
+__global__ void __launch_bounds__(256)
 zb_verify_checksums_big(const u8* __restrict__ dst, const ZbFramePlace* __restrict__ place, const u64* __restrict__ out_sizes,
                         const ZbFrameInfo* __restrict__ info, const u32* __restrict__ ck_expect, u32 first, u32 n_frames,
                         u32* __restrict__ status)
 {
-    __shared__ __align__(16) u8 s_tile[2][ZB_XXH_TILE + 16];
+    __shared__ __align__(16) u32 s_tile[2][ZB_XXH_TILE / 4];
+    __shared__ u64 s_v[4];
     u64 const P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull;
     u32 const tid = threadIdx.x;
+    #define ZB_XXH_ROUND(v, c) do { u64 const s_ = (v) + (c); (v) = ((s_ << 31) | (s_ >> 33)) * P1; } while (0)
     for (u32 f = first + blockIdx.x; f < n_frames; f += gridDim.x) {
         if (status[f] != ZB_OK || !(info[f].flags & 1)) continue;
         u64 const len = out_sizes[f];
         if (len < ZB_XXH_BIG) continue;
         const u8* const p0 = dst + place[f].dst_off;
-        u64 const n_stripes = len >> 5;
-        u32 const mis = (u32)((uintptr_t)p0 & 15);                     // tiles are staged from 16-byte aligned addresses
-        const u8* const a0 = p0 - mis;
-        u64 const n_tiles = (n_stripes * 32 + ZB_XXH_TILE - 1) / ZB_XXH_TILE;
+        u64 const n_words = (len >> 5) * 8;                            // 32-bit words inside whole stripes
+        u32 const sh = (u32)((uintptr_t)p0 & 3) * 8;
+        const u32* const g32 = (const u32*)(p0 - (sh >> 3));           // aligned words; word j of the frame = funnel(g32[j], g32[j + 1])
+        u64 const n_tiles = (n_words + ZB_XXH_TILE / 4 - 1) / (ZB_XXH_TILE / 4);
         u64 v = tid == 0 ? P1 + P2 : (tid == 1 ? P2 : (tid == 2 ? 0ull : 0ull - P1));
         __syncthreads();                                               // (the tiles are free)
         for (u64 t = 0; t <= n_tiles; t++) {
             if (tid >= 32 && t < n_tiles) {                            // stage tile t
-                u64 const off = t * ZB_XXH_TILE;
-                u64 const rest = (n_stripes * 32 + mis + 15 - off) & ~15ull;
-                u64 const bytes = rest < (u64)ZB_XXH_TILE + 16 ? rest : (u64)ZB_XXH_TILE + 16;
-                const uint4* g = (const uint4*)(a0 + off); uint4* d = (uint4*)s_tile[t & 1];
-                for (u32 i = tid - 32; i < bytes / 16; i += 96) d[i] = __ldcg(g + i);
+                u64 const w0 = t * (ZB_XXH_TILE / 4);
+                u32 const nw = (u32)(n_words - w0 < ZB_XXH_TILE / 4 ? n_words - w0 : ZB_XXH_TILE / 4);
+                u32* const d = s_tile[t & 1];
+                if (sh == 0) for (u32 i = tid - 32; i < nw; i += 224) d[i] = __ldcg(g32 + w0 + i);
+                else for (u32 i = tid - 32; i < nw; i += 224) d[i] = __funnelshift_r(__ldcg(g32 + w0 + i), __ldcg(g32 + w0 + i + 1), sh);
             }
-            if (tid < 4 && t > 0) {                                    // consume tile t - 1
-                u64 const off = (t - 1) * ZB_XXH_TILE;
-                u64 const left = n_stripes * 32 - off;
-                u32 const ns = (u32)(left < ZB_XXH_TILE ? left : ZB_XXH_TILE) >> 5;
-                const u8* const base = s_tile[(t - 1) & 1] + mis + tid * 8;
-                u32 const sh = (u32)((uintptr_t)base & 7) * 8;
-                const u64* q = (const u64*)(base - (sh >> 3));
-                if (sh == 0) for (u32 k = 0; k < ns; k++) { u64 const x = q[k * 4]; v = ((v + x * P2) << 31 | (v + x * P2) >> 33) * P1; }
-                else for (u32 k = 0; k < ns; k++) { u64 const x = (q[k * 4] >> sh) | (q[k * 4 + 1] << (64 - sh)); v = ((v + x * P2) << 31 | (v + x * P2) >> 33) * P1; }
+            if (tid < 4 && t > 0) {                                    // consume tile t - 1: stripe k of my accumulator = q[4 k]
+                u64 const w0 = (t - 1) * (ZB_XXH_TILE / 4);
+                u32 const ns = (u32)(n_words - w0 < ZB_XXH_TILE / 4 ? n_words - w0 : ZB_XXH_TILE / 4) >> 3;
+                const u64* const q = (const u64*)s_tile[(t - 1) & 1] + tid;
+                u32 k = 0;
+                if (ns >= 4) {
+                    u64 c0 = q[0] * P2, c1 = q[4] * P2, c2 = q[8] * P2, c3 = q[12] * P2;
+                    for (; k + 8 <= ns; k += 4) {
+                        u64 const n0 = q[(k + 4) * 4] * P2, n1 = q[(k + 5) * 4] * P2, n2 = q[(k + 6) * 4] * P2, n3 = q[(k + 7) * 4] * P2;
+                        ZB_XXH_ROUND(v, c0); ZB_XXH_ROUND(v, c1); ZB_XXH_ROUND(v, c2); ZB_XXH_ROUND(v, c3);
+                        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                    }
+                    ZB_XXH_ROUND(v, c0); ZB_XXH_ROUND(v, c1); ZB_XXH_ROUND(v, c2); ZB_XXH_ROUND(v, c3);
+                    k += 4;
+                }
+                for (; k < ns; k++) { u64 const c = q[k * 4] * P2; ZB_XXH_ROUND(v, c); }
             }
             __syncthreads();
         }
+        #undef ZB_XXH_ROUND
+        u64 const n_stripes = len >> 5;
         // the four accumulators -> lane 0; the tail (< 32 bytes) and the avalanche as in zb_xxh64
-        __shared__ u64 s_v[4];
         if (tid < 4) s_v[tid] = v;
         __syncthreads();
         if (tid == 0) {
@@ -1740,7 +1752,7 @@ void zb_launch_verify(const u8* dst, const ZbFramePlace* place, const u64* out_s
 {
     u32 const n = end - first;
     zb_verify_checksums<<<(n + 127) / 128, 128, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
-    zb_verify_checksums_big<<<n < 592 ? n : 592, 128, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
+    zb_verify_checksums_big<<<n < 592 ? n : 592, 256, 0, st>>>(dst, place, out_sizes, info, ck_expect, first, end, status);
 }
 
 void zb_launch_finish(const ZbFramePlace* place, const u64* out_sizes, const u32* status, u32 n, ZbSegment* out_segs,

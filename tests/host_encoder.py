@@ -348,7 +348,7 @@ extern "C" long long t_decompress_batch(const u8* src, const u64* seg_off, const
     }
     else simt::launch((n + 7) / 8, 256, [&] { zb_execute(src, place.data(), status.data(), blocks.data(), seqs.data(), lits.data(), out, 0, n, dict, (u64)ZB_TILE_CAP + 1); });
     if (totals[4]) simt::launch((n + 127) / 128, 128, [&] { zb_verify_checksums(out, place.data(), out_sizes.data(), info.data(), ck.data(), 0, n, status.data()); });
-    if (totals[4]) simt::launch(n < 8 ? n : 8, 128, [&] { zb_verify_checksums_big(out, place.data(), out_sizes.data(), info.data(), ck.data(), 0, n, status.data()); });
+    if (totals[4]) simt::launch(n < 8 ? n : 8, 256, [&] { zb_verify_checksums_big(out, place.data(), out_sizes.data(), info.data(), ck.data(), 0, n, status.data()); });
     std::vector<ZbSegment> out_segs(n); u32 first_error = 0xFFFFFFFFu;
     simt::launch((n + 255) / 256, 256, [&] { zb_finish(place.data(), out_sizes.data(), status.data(), n, out_segs.data(), &first_error); });
     for (u32 i = 0; i < n; i++) { out_off[i] = out_segs[i].offset; out_len[i] = out_segs[i].length; status_out[i] = status[i]; }
