@@ -117,6 +117,20 @@ int zb200_decompress_batch_ptrs_ex(zb200_ctx* ctx, const void* const* srcs, cons
                                    const uint64_t* dst_sizes, const zb200_ddict* dict, const zb200_dparams* params,
                                    uint32_t flags, zb200_result** out);
 
+/* ---- one batch over several devices: the `threads` argument of the reference's batch calls as a C entry point.
+ * The items are cut into contiguous ranges balanced by input bytes -- the reference's static worker partition
+ * (c-ext/compressor.c:1127,1183-1200; c-ext/decompressor.c:1237,1290-1305) --, range k runs on devices[k] in its own context
+ * (created on first use and kept by the library; a device may be named more than once and then gets a context per mention),
+ * all ranges concurrently, and comes back as results[k]: what the reference returns per worker, in item order.
+ * results[k] is NULL and first_item[k] = n where the partition has fewer than n_devices ranges.  Host buffers only
+ * (no ZB200_SRC_DEVICE / ZB200_DST_DEVICE).  dict / dict_size: the raw dictionary or NULL; digested per device.
+ * Returns 0, or the first failing range's code with its text in zb200_multi_last_error() (per-item codec errors are in
+ * the results, as always). */
+int zb200_decompress_batch_multi(const int* devices, int n_devices, const void* src_base, const zb200_segment* segs, size_t n,
+                                 const uint64_t* dst_sizes, const void* dict, size_t dict_size, const zb200_dparams* params,
+                                 uint32_t flags, zb200_result** results, size_t* first_item);
+const char* zb200_multi_last_error(void);
+
 /* ---- batch compression.
  * src_base + segs[i].offset .. +length is the i-th input (DataSource, c-ext/compressor.c:805-808).
  * Every input becomes one zstd frame (RFC 8878) of independent <=128 KiB blocks. */
@@ -133,6 +147,10 @@ typedef struct {
  * content as history before every frame, ZSTD_CCtx_refCDict / loadDictionary_byReference, c-ext/compressor.c:1146-1168) */
 int zb200_compress_batch(zb200_ctx* ctx, const void* src_base, const zb200_segment* segs, size_t n,
                          const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out);
+/* one batch over several devices, as zb200_decompress_batch_multi */
+int zb200_compress_batch_multi(const int* devices, int n_devices, const void* src_base, const zb200_segment* segs, size_t n,
+                               const zb200_cparams* params, const void* dict, size_t dict_size, uint32_t flags,
+                               zb200_result** results, size_t* first_item);
 /* same, from an array of independent host buffers (list input, c-ext/compressor.c:1434-1466) */
 int zb200_compress_batch_ptrs(zb200_ctx* ctx, const void* const* srcs, const size_t* sizes, size_t n,
                               const zb200_cparams* params, const zb200_ddict* dict, uint32_t flags, zb200_result** out);

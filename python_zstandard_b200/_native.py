@@ -91,6 +91,9 @@ def lib():
             "zb200_kernel_name": (C.c_char_p, [i]),
             "zb200_last_scratch_bytes": (u64, [vp]),
             "zb200_last_chase_rounds": (i, [vp]),
+            "zb200_decompress_batch_multi": (i, [vp, i, vp, vp, sz, vp, vp, sz, vp, u32, vp, vp]),
+            "zb200_compress_batch_multi": (i, [vp, i, vp, vp, sz, vp, vp, sz, u32, vp, vp]),
+            "zb200_multi_last_error": (C.c_char_p, []),
             "zb200_last_compress_kernel": (C.c_char_p, [vp]),
         }
         for name, (res, args) in sigs.items():

@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <map>
+#include <algorithm>
 
 extern "C" {
 void zb_launch_default_tables(cudaStream_t st);
@@ -868,6 +870,100 @@ const char* zb200_kernel_name(int k)
                                                 "zb_compress_blocks", "zb_frame_layout", "zb_write_frames", "zb_verify_checksums"};
     return (k >= 0 && k < ZB200_K_COUNT && names[k]) ? names[k] : "";
 }
+// ---------------------------------------------------------------- one batch over several devices
+}  // extern "C"
+namespace {
+struct MultiSlot { zb200_ctx* ctx = nullptr; std::mutex mu; };
+std::mutex g_multi_mu;
+std::map<std::pair<int, int>, MultiSlot*> g_multi;      // (device, k-th mention of it in a call) -> its context, kept for the process
+thread_local std::string g_multi_err;
+
+MultiSlot* multi_slot(int device, int rep)
+{
+    std::lock_guard<std::mutex> g(g_multi_mu);
+    auto& s = g_multi[std::make_pair(device, rep)];
+    if (!s) s = new MultiSlot();
+    return s;
+}
+
+// contiguous, non-empty ranges balanced by input bytes (the rule of python_zstandard_b200/sharding.py::split_ranges, which
+// restates the reference's worker partition, c-ext/compressor.c:1183-1200)
+std::vector<size_t> multi_cuts(const zb200_segment* segs, size_t n, size_t parts)
+{
+    std::vector<size_t> cuts{0};
+    if (parts > n) parts = n;
+    if (parts > 1 && n >= 2) {
+        std::vector<u64> cum(n); u64 acc = 0;
+        for (size_t i = 0; i < n; i++) { acc += segs[i].length; cum[i] = acc; }
+        for (size_t p = 1; p < parts; p++) {
+            u64 const target = (u64)((unsigned __int128)acc * p / parts);
+            size_t k = (size_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()) + 1;
+            if (k < cuts.back() + 1) k = cuts.back() + 1;
+            if (k > n - (parts - p)) k = n - (parts - p);
+            cuts.push_back(k);
+        }
+    }
+    cuts.push_back(n);
+    return cuts;
+}
+
+template <class Call>
+int multi_run(const int* devices, int n_devices, const zb200_segment* segs, size_t n, const void* dict, size_t dict_size,
+              zb200_result** results, size_t* first_item, Call call)
+{
+    g_multi_err.clear();
+    if (!devices || n_devices <= 0 || !segs || n == 0 || !results) { g_multi_err = "bad arguments"; return -3; }
+    for (int k = 0; k < n_devices; k++) { results[k] = nullptr; if (first_item) first_item[k] = n; }
+    std::vector<size_t> const cuts = multi_cuts(segs, n, (size_t)n_devices);
+    size_t const nr = cuts.size() - 1;
+    std::vector<int> rc(nr, 0); std::vector<std::string> msg(nr);
+    std::vector<std::thread> th;
+    std::map<int, int> seen;
+    for (size_t k = 0; k < nr; k++) {
+        MultiSlot* const slot = multi_slot(devices[k], seen[devices[k]]++);
+        size_t const lo = cuts[k], hi = cuts[k + 1];
+        if (first_item) first_item[k] = lo;
+        th.emplace_back([=, &rc, &msg] {
+            std::lock_guard<std::mutex> g(slot->mu);
+            if (!slot->ctx && zb200_ctx_create(devices[k], &slot->ctx) != 0) { rc[k] = -2; msg[k] = "cannot create a context on device " + std::to_string(devices[k]); return; }
+            zb200_ddict* dd = nullptr;
+            if (dict && dict_size && zb200_ddict_create(slot->ctx, dict, dict_size, &dd) != 0) { rc[k] = -1; msg[k] = zb200_ctx_last_error(slot->ctx); return; }
+            rc[k] = call(slot->ctx, lo, hi, dd, &results[k]);
+            if (rc[k]) msg[k] = zb200_ctx_last_error(slot->ctx);
+            if (dd) zb200_ddict_free(dd);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < nr; k++) if (rc[k]) { g_multi_err = "range " + std::to_string(k) + " (device " + std::to_string(devices[k]) + "): " + msg[k]; return rc[k]; }
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+const char* zb200_multi_last_error(void) { return g_multi_err.c_str(); }
+
+int zb200_decompress_batch_multi(const int* devices, int n_devices, const void* src_base, const zb200_segment* segs, size_t n,
+                                 const uint64_t* dst_sizes, const void* dict, size_t dict_size, const zb200_dparams* params,
+                                 uint32_t flags, zb200_result** results, size_t* first_item)
+{
+    if (flags & (ZB200_SRC_DEVICE | ZB200_DST_DEVICE | ZB200_SEGS_HOST)) { g_multi_err = "host buffers only"; return -3; }
+    return multi_run(devices, n_devices, segs, n, dict, dict_size, results, first_item,
+                     [=](zb200_ctx* ctx, size_t lo, size_t hi, zb200_ddict* dd, zb200_result** out) {
+                         return zb200_decompress_batch_ex(ctx, src_base, segs + lo, hi - lo, dst_sizes ? dst_sizes + lo : nullptr, dd, params, flags, out);
+                     });
+}
+
+int zb200_compress_batch_multi(const int* devices, int n_devices, const void* src_base, const zb200_segment* segs, size_t n,
+                               const zb200_cparams* params, const void* dict, size_t dict_size, uint32_t flags,
+                               zb200_result** results, size_t* first_item)
+{
+    if (flags & (ZB200_SRC_DEVICE | ZB200_DST_DEVICE | ZB200_SEGS_HOST)) { g_multi_err = "host buffers only"; return -3; }
+    return multi_run(devices, n_devices, segs, n, dict, dict_size, results, first_item,
+                     [=](zb200_ctx* ctx, size_t lo, size_t hi, zb200_ddict* dd, zb200_result** out) {
+                         return zb200_compress_batch(ctx, src_base, segs + lo, hi - lo, params, dd, flags, out);
+                     });
+}
+
 uint64_t zb200_last_scratch_bytes(const zb200_ctx* ctx) { return ctx->last_scratch; }
 int zb200_last_chase_rounds(const zb200_ctx* ctx) { return ctx->last_chase_rounds; }
 const char* zb200_last_compress_kernel(const zb200_ctx* ctx) { return ctx->last_compress_kernel; }

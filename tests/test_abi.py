@@ -71,3 +71,34 @@ def test_compress_bound_equals_the_reference():
         want = expect(n) if expect else n + (n >> 8) + (((128 << 10) - n) >> 11 if n < (128 << 10) else 0)
         assert lib.zb200_compress_bound(n) == want, n
     assert lib.zb200_compress_bound(131072) == 131584 and lib.zb200_compress_bound(4096) == 4174
+
+
+def test_multi_device_partition_equals_the_python_rule():
+    """zb200_*_batch_multi cuts a batch exactly like sharding.split_ranges (the reference's worker partition).  Without a
+    device the call fails when it creates its first context -- after the partition has been written to first_item[]."""
+    import ctypes as C
+    import numpy as np
+    from python_zstandard_b200 import _native
+    from python_zstandard_b200.sharding import split_ranges
+    L = _native.lib()
+    rng = np.random.default_rng(3)
+    for n, parts in ((1, 4), (2, 2), (5, 8), (100, 3), (1000, 7), (4096, 8), (77, 1)):
+        lens = rng.integers(0, 5000, n).astype(np.uint64)
+        if n > 3:
+            lens[n // 2] = 1 << 20                       # one dominant item
+        segs = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64), lens], axis=1).astype(np.uint64)
+        devs = (C.c_int * parts)(*([0] * parts))
+        results = (C.c_void_p * parts)()
+        first = (C.c_size_t * parts)()
+        src = np.zeros(max(1, int(lens.sum())), dtype=np.uint8)
+        rc = L.zb200_decompress_batch_multi(devs, parts, src.ctypes.data, segs.ctypes.data, n, None, None, 0, None, 0, results, first)
+        want = split_ranges(lens, parts)
+        got = [first[k] for k in range(parts)]
+        assert got[:len(want)] == [lo for lo, _ in want], (n, parts)
+        assert all(g == n for g in got[len(want):])
+        if rc != 0:                                     # no GPU here: a clean failure with a message, nothing returned
+            assert all(not results[k] for k in range(parts)) and L.zb200_multi_last_error()
+        else:
+            for k in range(parts):
+                if results[k]:
+                    L.zb200_result_free(results[k])

@@ -261,3 +261,66 @@ def test_device_resident_results_survive_the_next_call(ref):
         ctx.check(L.zb200_memcpy_d2h(ctx.h, out.ctypes.data, L.zb200_result_data(r), len(want)), "d2h")
         assert out.tobytes() == want
         L.zb200_result_free(r)
+
+
+def test_c_abi_one_batch_over_several_contexts(ref):
+    """zb200_decompress_batch_multi / zb200_compress_batch_multi: the reference's `threads` partition inside the C ABI.
+    Three contexts on device 0 stand in for three devices (bench.py --gpus N and tools run the real thing): the ranges
+    come back in item order, every item as the single-context call returns it; a dictionary is digested per context;
+    a damaged item is reported inside its range's result."""
+    import ctypes as C
+    from python_zstandard_b200 import _native
+    L = _native.lib()
+    rng = np.random.default_rng(11)
+    text = corpus.text_corpus(1 << 20)
+    items = [text[o:o + int(s)].tobytes() for o, s in zip(rng.integers(0, (1 << 20) - 70000, 90), rng.integers(1, 60000, 90))]
+    samples = [text[i * 997:i * 997 + 600].tobytes() for i in range(400)]
+    dict_raw = ref.train_dictionary(16384, samples)
+    for use_dict in (False, True):
+        frames = [ref.compress(s, level=3, dict_data=dict_raw if use_dict else b"") for s in items]
+        blob = np.frombuffer(b"".join(frames), dtype=np.uint8)
+        lens = np.array([len(f) for f in frames], dtype=np.uint64)
+        segs = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64), lens], axis=1).astype(np.uint64)
+        devs = (C.c_int * 3)(0, 0, 0); results = (C.c_void_p * 3)(); first = (C.c_size_t * 3)()
+        rc = L.zb200_decompress_batch_multi(devs, 3, blob.ctypes.data, segs.ctypes.data, len(items), None,
+                                            dict_raw if use_dict else None, len(dict_raw) if use_dict else 0, None, 0, results, first)
+        assert rc == 0, L.zb200_multi_last_error()
+        assert first[0] == 0 and 0 < first[1] < first[2] < len(items)
+        got = []
+        for k in range(3):
+            assert not L.zb200_result_first_error(results[k], None, None, None, None)
+            n_k = L.zb200_result_count(results[k]); base = L.zb200_result_data(results[k])
+            st = np.ctypeslib.as_array(C.cast(L.zb200_result_segments(results[k]), C.POINTER(C.c_uint64)), shape=(n_k, 2))
+            got += [C.string_at(base + int(o), int(l)) for o, l in st]
+            L.zb200_result_free(results[k])
+        assert got == items
+    # compression over the same three contexts: every frame regenerated by the reference, in item order
+    blob = np.frombuffer(b"".join(items), dtype=np.uint8)
+    lens = np.array([len(s) for s in items], dtype=np.uint64)
+    segs = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64), lens], axis=1).astype(np.uint64)
+    results = (C.c_void_p * 3)(); first = (C.c_size_t * 3)()
+    rc = L.zb200_compress_batch_multi((C.c_int * 3)(0, 0, 0), 3, blob.ctypes.data, segs.ctypes.data, len(items), None, None, 0, 0, results, first)
+    assert rc == 0, L.zb200_multi_last_error()
+    back = []
+    for k in range(3):
+        n_k = L.zb200_result_count(results[k]); base = L.zb200_result_data(results[k])
+        st = np.ctypeslib.as_array(C.cast(L.zb200_result_segments(results[k]), C.POINTER(C.c_uint64)), shape=(n_k, 2))
+        back += [ref.decompress(C.string_at(base + int(o), int(l)), 70000) for o, l in st]
+        L.zb200_result_free(results[k])
+    assert back == items
+    # a damaged item: the call succeeds, the item's error sits in its range's result
+    frames = [ref.compress(s, level=3) for s in items]
+    bad = bytearray(frames[80]); bad[len(bad) // 2] ^= 0x55; frames[80] = bytes(bad[:len(bad) - 3])
+    blob = np.frombuffer(b"".join(frames), dtype=np.uint8)
+    lens = np.array([len(f) for f in frames], dtype=np.uint64)
+    segs = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64), lens], axis=1).astype(np.uint64)
+    rc = L.zb200_decompress_batch_multi((C.c_int * 3)(0, 0, 0), 3, blob.ctypes.data, segs.ctypes.data, len(items), None, None, 0, None, 0, results, first)
+    assert rc == 0
+    item = C.c_size_t()
+    flags = [bool(L.zb200_result_first_error(results[k], C.byref(item), None, None, None)) for k in range(3)]
+    k80 = max(k for k in range(3) if first[k] <= 80)
+    assert flags == [k == k80 for k in range(3)]
+    L.zb200_result_first_error(results[k80], C.byref(item), None, None, None)
+    assert first[k80] + item.value == 80
+    for k in range(3):
+        L.zb200_result_free(results[k])
