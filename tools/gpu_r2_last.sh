@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 2
-(MB=256 CK=1 timeout 600 python tools/gpu_c5_frame.py) 2>&1 | tail -n 7
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_last.log 2>&1; tail -n 25 gpurun_out/pytest_gpu_last.log | cut -c1-220
