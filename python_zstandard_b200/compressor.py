@@ -58,8 +58,38 @@ class ZstdCompressionParameters:
                 raise ZstdError("compression parameter %s is not supported by the B200 backend" % k)
             setattr(self, k, 0)
 
+    # window_log of ZSTD_getCParams(level, source_size, dict_size): the W column of the four level tables
+    # (zstd/zstd.c:30650-30756: any size / <= 256 KB / <= 128 KB / <= 16 KB; row 0 = negative levels, rows 1..22 = levels)
+    _LEVEL_WINDOW_LOG = (
+        (19, 19, 20, 21, 21, 21, 21, 21, 21, 22, 22, 22, 22, 22, 22, 22, 22, 23, 23, 23, 25, 26, 27),
+        (18,) * 23, (17,) * 23, (14,) * 23)
+
+    @classmethod
+    def _level_window_log(cls, level, source_size, dict_size):
+        """ZSTD_getCParams(...).windowLog: table row by size class (ZSTD_getCParamRowSize / ZSTD_getCParams_internal,
+        zstd/zstd.c:30823-30871), then the downsizing of ZSTD_adjustCParams_internal (:24498-24524).  source_size 0 means
+        unknown, as in the reference's from_level (c-ext/compressionparams.c:497-560 -> ZSTD_getCParams :30876)."""
+        unknown = source_size == 0
+        if unknown:
+            rsize = (1 << 64) - 1 if dict_size == 0 else dict_size + 499        # (UNKNOWN + dictSize + 500 wraps in the reference)
+        else:
+            rsize = source_size + dict_size
+        table = (rsize <= 256 << 10) + (rsize <= 128 << 10) + (rsize <= 16 << 10)
+        row = 3 if level == 0 else (0 if level < 0 else min(level, 22))
+        wlog = cls._LEVEL_WINDOW_LOG[table][row]
+        if not unknown and source_size <= (1 << 30) and dict_size <= (1 << 30):
+            tsize = (source_size + dict_size) & 0xFFFFFFFF
+            src_log = 6 if tsize < 64 else (tsize - 1).bit_length()
+            wlog = min(wlog, src_log)
+        return max(wlog, 10)
+
     @classmethod
     def from_level(cls, level, source_size=0, dict_size=0, **kwargs):
+        """ZstdCompressionParameters.from_level (c-ext/compressionparams.c:497-560): the parameters ZSTD_getCParams picks for
+        (level, source_size, dict_size), unless given.  window_log is the one that reaches this backend (frame header, block
+        size); the match-finder columns of the level tables describe CPU strategies this backend does not have."""
+        if kwargs.get("window_log") in (None, 0, -1):
+            kwargs["window_log"] = cls._level_window_log(level, source_size, dict_size)
         return cls(compression_level=level, **kwargs)
 
 

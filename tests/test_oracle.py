@@ -101,3 +101,33 @@ def test_mutated_frames_vs_live_reference(oracle):
             assert got == exp
             both += 1
     assert both > 50
+
+
+def test_from_level_window_log_equals_getcparams():
+    """ZstdCompressionParameters.from_level(level, source_size, dict_size).window_log == ZSTD_getCParams(...).windowLog of the
+    unmodified reference for every level and a sweep of source / dictionary sizes (the other columns of the level tables
+    configure CPU match finders and do not reach this backend)."""
+    import ctypes as C
+    import python_zstandard_b200 as zstd
+
+    class CP(C.Structure):
+        _fields_ = [(k, C.c_uint) for k in ("windowLog", "chainLog", "hashLog", "searchLog", "minMatch", "targetLength", "strategy")]
+    from oracle import RefZstd, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    Z = RefZstd().Z
+    Z.ZSTD_getCParams.restype = CP
+    Z.ZSTD_getCParams.argtypes = [C.c_int, C.c_ulonglong, C.c_size_t]
+    sizes = [0, 1, 63, 64, 65, 1000, 16 << 10, (16 << 10) + 1, 100000, 128 << 10, (128 << 10) + 1, 256 << 10, (256 << 10) + 1,
+             1 << 20, 5 << 20, 1 << 27, 1 << 30, (1 << 30) + 1, 1 << 33]
+    dicts = [0, 1, 500, 16000, 112640, 130000, 300000, 1 << 22]
+    checked = 0
+    for level in list(range(-7, 23)) + [30]:
+        for s in sizes:
+            for d in dicts:
+                want = Z.ZSTD_getCParams(level, s, d).windowLog
+                got = zstd.ZstdCompressionParameters.from_level(level, source_size=s, dict_size=d).window_log
+                assert got == want, (level, s, d, got, want)
+                checked += 1
+    assert checked > 4000
+    assert zstd.ZstdCompressionParameters.from_level(3, source_size=1000, window_log=15).window_log == 15
