@@ -125,3 +125,28 @@ def test_reader_and_decompressobj_logic_over_several_frames():
         o.decompress(b"x")
     o = streams.ZstdDecompressionObj(_HostDctx(ref), read_across_frames=True)
     assert b"".join(o.decompress(blob[i:i + 7777]) for i in range(0, len(blob), 7777)) == whole
+
+
+def test_compressobj_logic():
+    ref = RefZstd()
+
+    class Cctx:
+        def compress(self, data):
+            return ref.compress(data, level=3)
+    text = corpus.text_corpus(1 << 20)[:200000].tobytes()
+    o = streams.ZstdCompressionObj(Cctx())
+    assert [o.compress(text[i:i + 30000]) for i in range(0, len(text), 30000)] == [b""] * 7
+    frame = o.flush()
+    assert ref.decompress(frame, len(text)) == text
+    with pytest.raises(ZstdError, match="cannot call compress\\(\\) after compressor finished"):
+        o.compress(b"more")
+    with pytest.raises(ZstdError, match="compressor object already finished"):
+        o.flush()
+    o = streams.ZstdCompressionObj(Cctx(), size=10)
+    o.compress(b"12345")
+    with pytest.raises(ZstdError, match="Src size is incorrect"):
+        o.flush()
+    with pytest.raises(ValueError, match="flush mode not recognized"):
+        streams.ZstdCompressionObj(Cctx()).flush(flush_mode=7)
+    with pytest.raises(NotImplementedError):
+        streams.ZstdCompressionObj(Cctx()).flush(flush_mode=streams.COMPRESSOBJ_FLUSH_BLOCK)
