@@ -63,3 +63,30 @@ def test_collection():
     with pytest.raises(IndexError, match="offset must be less than 3"):
         c[3]
     assert [c[i].tobytes() for i in range(3)] == [b"foo", b"bar", b"baz"]
+
+
+def test_device_buffer_argument_checks_without_a_device():
+    """DeviceBufferWithSegments validates like BufferWithSegments before it ever touches the GPU."""
+    import struct
+    import pytest
+    import python_zstandard_b200 as zstd
+
+    class Fake:                      # something that claims to be a 1-D device array of 100 bytes (at a host address)
+        def __init__(self, shape=(100,), typestr="|u1", strides=None):
+            import ctypes
+            self._b = ctypes.create_string_buffer(128)
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ctypes.addressof(self._b), False),
+                                             "strides": strides, "version": 3}
+    with pytest.raises(TypeError, match="__cuda_array_interface__"):
+        zstd.DeviceBufferWithSegments(b"host bytes", struct.pack("=QQ", 0, 3))
+    with pytest.raises(TypeError, match="contiguous 1-D"):
+        zstd.DeviceBufferWithSegments(Fake(shape=(10, 10)), struct.pack("=QQ", 0, 3))
+    with pytest.raises(TypeError, match="contiguous 1-D"):
+        zstd.DeviceBufferWithSegments(Fake(strides=(2,)), struct.pack("=QQ", 0, 3))
+    with pytest.raises(ValueError, match="segments array size is not a multiple of 16"):
+        zstd.DeviceBufferWithSegments(Fake(), b"\x00" * 17)
+    with pytest.raises(ValueError, match="references memory outside buffer"):
+        zstd.DeviceBufferWithSegments(Fake(), struct.pack("=QQ", 90, 11))
+    with pytest.raises(TypeError, match="does not live in device memory"):
+        zstd.DeviceBufferWithSegments(Fake(), struct.pack("=QQ", 0, 100))      # a host address (or no device at all)
+    assert "device_buffers" in zstd.backend_features
