@@ -15,6 +15,12 @@
  *   zb200_ddict_create / _free  ensure_ddict / ZSTD_createDDict_advanced   c-ext/compressiondict.c:148-162
  *   zb200_frame_info            ZSTD_getFrameHeader_advanced   zstd/zstd.c:43668 (c-ext/frameparams.c)
  *   zb200_error_string          ZSTD_getErrorName              zstd/zstd.c (error_private.c)
+ *   zb200_*_batch_multi         the worker partition and pool of both functions above: `threads` workers over contiguous
+ *                               ranges balanced by bytes   c-ext/compressor.c:1127,1183-1200; c-ext/decompressor.c:1237,1290-1305
+ *   zb200_dparams               ZstdDecompressor(max_window_size=) -> ZSTD_DCtx_setMaxWindowSize   c-ext/decompressor.c:17-60
+ *   zb200_cparams.window_log    ZSTD_c_windowLog of ZstdCompressionParameters   c-ext/compressionparams.c:46
+ *   zb200_host_copy             the write into the result PyBytes   c-ext/decompressor.c:283-352
+ *   ZB200_SRC/DST_DEVICE, ZB200_SEGS_HOST, zb200_pointer_device: no counterpart (device-resident callers)
  *
  * Plain pointers and sizes only; no torch / Python types.  All functions return 0 on
  * success or a negative value for an infrastructure failure (CUDA, allocation, bad
