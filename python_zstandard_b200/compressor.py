@@ -58,17 +58,30 @@ class ZstdCompressionParameters:
                 raise ZstdError("compression parameter %s is not supported by the B200 backend" % k)
             setattr(self, k, 0)
 
-    # window_log of ZSTD_getCParams(level, source_size, dict_size): the W column of the four level tables
-    # (zstd/zstd.c:30650-30756: any size / <= 256 KB / <= 128 KB / <= 16 KB; row 0 = negative levels, rows 1..22 = levels)
-    _LEVEL_WINDOW_LOG = (
-        (19, 19, 20, 21, 21, 21, 21, 21, 21, 22, 22, 22, 22, 22, 22, 22, 22, 23, 23, 23, 25, 26, 27),
-        (18,) * 23, (17,) * 23, (14,) * 23)
+    # The level tables of the reference (zstd/zstd.c:30650-30756): four size classes (any / <= 256 KB / <= 128 KB / <= 16 KB),
+    # row 0 = base of the negative levels, rows 1..22 = levels; columns: window_log, chain_log, hash_log, search_log, min_match,
+    # target_length, strategy (1 fast .. 9 btultra2).  Data, restated; only window_log reaches this backend.
+    _LEVEL_TABLES = (
+        ((19, 12, 13, 1, 6, 1, 1), (19, 13, 14, 1, 7, 0, 1), (20, 15, 16, 1, 6, 0, 1), (21, 16, 17, 1, 5, 0, 2), (21, 18, 18, 1, 5, 0, 2), (21, 18, 19, 3, 5, 2, 3), (21, 18, 19, 3, 5, 4, 4), (21, 19, 20, 4, 5, 8, 4),
+         (21, 19, 20, 4, 5, 16, 5), (22, 20, 21, 4, 5, 16, 5), (22, 21, 22, 5, 5, 16, 5), (22, 21, 22, 6, 5, 16, 5), (22, 22, 23, 6, 5, 32, 5), (22, 22, 22, 4, 5, 32, 6), (22, 22, 23, 5, 5, 32, 6), (22, 23, 23, 6, 5, 32, 6),
+         (22, 22, 22, 5, 5, 48, 7), (23, 23, 22, 5, 4, 64, 7), (23, 23, 22, 6, 3, 64, 8), (23, 24, 22, 7, 3, 256, 9), (25, 25, 23, 7, 3, 256, 9), (26, 26, 24, 7, 3, 512, 9), (27, 27, 25, 9, 3, 999, 9)),
+        ((18, 12, 13, 1, 5, 1, 1), (18, 13, 14, 1, 6, 0, 1), (18, 14, 14, 1, 5, 0, 2), (18, 16, 16, 1, 4, 0, 2), (18, 16, 17, 3, 5, 2, 3), (18, 17, 18, 5, 5, 2, 3), (18, 18, 19, 3, 5, 4, 4), (18, 18, 19, 4, 4, 4, 4),
+         (18, 18, 19, 4, 4, 8, 5), (18, 18, 19, 5, 4, 8, 5), (18, 18, 19, 6, 4, 8, 5), (18, 18, 19, 5, 4, 12, 6), (18, 19, 19, 7, 4, 12, 6), (18, 18, 19, 4, 4, 16, 7), (18, 18, 19, 4, 3, 32, 7), (18, 18, 19, 6, 3, 128, 7),
+         (18, 19, 19, 6, 3, 128, 8), (18, 19, 19, 8, 3, 256, 8), (18, 19, 19, 6, 3, 128, 9), (18, 19, 19, 8, 3, 256, 9), (18, 19, 19, 10, 3, 512, 9), (18, 19, 19, 12, 3, 512, 9), (18, 19, 19, 13, 3, 999, 9)),
+        ((17, 12, 12, 1, 5, 1, 1), (17, 12, 13, 1, 6, 0, 1), (17, 13, 15, 1, 5, 0, 1), (17, 15, 16, 2, 5, 0, 2), (17, 17, 17, 2, 4, 0, 2), (17, 16, 17, 3, 4, 2, 3), (17, 16, 17, 3, 4, 4, 4), (17, 16, 17, 3, 4, 8, 5),
+         (17, 16, 17, 4, 4, 8, 5), (17, 16, 17, 5, 4, 8, 5), (17, 16, 17, 6, 4, 8, 5), (17, 17, 17, 5, 4, 8, 6), (17, 18, 17, 7, 4, 12, 6), (17, 18, 17, 3, 4, 12, 7), (17, 18, 17, 4, 3, 32, 7), (17, 18, 17, 6, 3, 256, 7),
+         (17, 18, 17, 6, 3, 128, 8), (17, 18, 17, 8, 3, 256, 8), (17, 18, 17, 10, 3, 512, 8), (17, 18, 17, 5, 3, 256, 9), (17, 18, 17, 7, 3, 512, 9), (17, 18, 17, 9, 3, 512, 9), (17, 18, 17, 11, 3, 999, 9)),
+        ((14, 12, 13, 1, 5, 1, 1), (14, 14, 15, 1, 5, 0, 1), (14, 14, 15, 1, 4, 0, 1), (14, 14, 15, 2, 4, 0, 2), (14, 14, 14, 4, 4, 2, 3), (14, 14, 14, 3, 4, 4, 4), (14, 14, 14, 4, 4, 8, 5), (14, 14, 14, 6, 4, 8, 5),
+         (14, 14, 14, 8, 4, 8, 5), (14, 15, 14, 5, 4, 8, 6), (14, 15, 14, 9, 4, 8, 6), (14, 15, 14, 3, 4, 12, 7), (14, 15, 14, 4, 3, 24, 7), (14, 15, 14, 5, 3, 32, 8), (14, 15, 15, 6, 3, 64, 8), (14, 15, 15, 7, 3, 256, 8),
+         (14, 15, 15, 5, 3, 48, 9), (14, 15, 15, 6, 3, 128, 9), (14, 15, 15, 7, 3, 256, 9), (14, 15, 15, 8, 3, 256, 9), (14, 15, 15, 8, 3, 512, 9), (14, 15, 15, 9, 3, 512, 9), (14, 15, 15, 10, 3, 999, 9)),
+    )
 
     @classmethod
-    def _level_window_log(cls, level, source_size, dict_size):
-        """ZSTD_getCParams(...).windowLog: table row by size class (ZSTD_getCParamRowSize / ZSTD_getCParams_internal,
-        zstd/zstd.c:30823-30871), then the downsizing of ZSTD_adjustCParams_internal (:24498-24524).  source_size 0 means
-        unknown, as in the reference's from_level (c-ext/compressionparams.c:497-560 -> ZSTD_getCParams :30876)."""
+    def _cparams_for(cls, level, source_size, dict_size):
+        """ZSTD_getCParams(level, source_size, dict_size) restated: the row by size class (ZSTD_getCParamRowSize and
+        ZSTD_getCParams_internal, zstd/zstd.c:30823-30871), then ZSTD_adjustCParams_internal in its "unknown" mode
+        (:24427-24563: window downsized to the input, hash / chain logs to the window, the row-hash cap).  source_size 0 means
+        unknown, as in c-ext/compressionparams.c:234-279."""
         unknown = source_size == 0
         if unknown:
             rsize = (1 << 64) - 1 if dict_size == 0 else dict_size + 499        # (UNKNOWN + dictSize + 500 wraps in the reference)
@@ -76,21 +89,43 @@ class ZstdCompressionParameters:
             rsize = source_size + dict_size
         table = (rsize <= 256 << 10) + (rsize <= 128 << 10) + (rsize <= 16 << 10)
         row = 3 if level == 0 else (0 if level < 0 else min(level, 22))
-        wlog = cls._LEVEL_WINDOW_LOG[table][row]
+        wlog, clog, hlog, slog, mml, tlen, strat = cls._LEVEL_TABLES[table][row]
+        if level < 0:
+            tlen = -max(level, -(1 << 17))                                      # acceleration: ZSTD_minCLevel() = -ZSTD_TARGETLENGTH_MAX
         if not unknown and source_size <= (1 << 30) and dict_size <= (1 << 30):
             tsize = (source_size + dict_size) & 0xFFFFFFFF
-            src_log = 6 if tsize < 64 else (tsize - 1).bit_length()
-            wlog = min(wlog, src_log)
-        return max(wlog, 10)
+            wlog = min(wlog, 6 if tsize < 64 else (tsize - 1).bit_length())
+        if not unknown:
+            # ZSTD_dictAndWindowLog: a window log that also reaches the dictionary
+            dw = wlog
+            if dict_size:
+                wsize = 1 << wlog
+                if wsize < dict_size + source_size:
+                    dw = 31 if dict_size + wsize >= (1 << 31) else (dict_size + wsize - 1).bit_length()
+            hlog = min(hlog, dw + 1)
+            cycle = clog - (1 if strat >= 6 else 0)                            # ZSTD_cycleLog: binary-tree strategies count double
+            if cycle > dw:
+                clog -= cycle - dw
+        wlog = max(wlog, 10)                                                    # ZSTD_WINDOWLOG_ABSOLUTEMIN
+        if 3 <= strat <= 5:                                                     # the row-based match finder hashes at most 32 bits
+            hlog = min(hlog, 24 + min(max(slog, 4), 6))
+        return {"window_log": wlog, "chain_log": clog, "hash_log": hlog, "search_log": slog, "min_match": mml,
+                "target_length": tlen, "strategy": strat}
 
     @classmethod
     def from_level(cls, level, source_size=0, dict_size=0, **kwargs):
-        """ZstdCompressionParameters.from_level (c-ext/compressionparams.c:497-560): the parameters ZSTD_getCParams picks for
-        (level, source_size, dict_size), unless given.  window_log is the one that reaches this backend (frame header, block
-        size); the match-finder columns of the level tables describe CPU strategies this backend does not have."""
+        """ZstdCompressionParameters.from_level (c-ext/compressionparams.c:234-380): the parameters ZSTD_getCParams picks for
+        (level, source_size, dict_size), each unless given.  window_log is the one that reaches this backend (frame header,
+        block size); the match-finder columns are reported as attributes, like the reference's, and describe CPU strategies
+        this backend replaces by its own parse of that level's class -- asking for DIFFERENT ones is still refused."""
+        derived = cls._cparams_for(level, source_size, dict_size)
         if kwargs.get("window_log") in (None, 0, -1):
-            kwargs["window_log"] = cls._level_window_log(level, source_size, dict_size)
-        return cls(compression_level=level, **kwargs)
+            kwargs["window_log"] = derived["window_log"]
+        self = cls(compression_level=level, **kwargs)
+        for k, v in derived.items():
+            if k != "window_log" and kwargs.get(k) in (None, 0, -1):
+                setattr(self, k, v)
+        return self
 
 
 class ZstdCompressor:

@@ -103,10 +103,10 @@ def test_mutated_frames_vs_live_reference(oracle):
     assert both > 50
 
 
-def test_from_level_window_log_equals_getcparams():
-    """ZstdCompressionParameters.from_level(level, source_size, dict_size).window_log == ZSTD_getCParams(...).windowLog of the
-    unmodified reference for every level and a sweep of source / dictionary sizes (the other columns of the level tables
-    configure CPU match finders and do not reach this backend)."""
+def test_from_level_equals_getcparams():
+    """ZstdCompressionParameters.from_level(level, source_size, dict_size) carries what ZSTD_getCParams(...) of the unmodified
+    reference returns -- all seven fields, every level (negative ones, 0, beyond 22) and a sweep of source / dictionary sizes
+    across the table and downsizing thresholds.  window_log is the field that reaches this backend."""
     import ctypes as C
     import python_zstandard_b200 as zstd
 
@@ -120,14 +120,19 @@ def test_from_level_window_log_equals_getcparams():
     Z.ZSTD_getCParams.argtypes = [C.c_int, C.c_ulonglong, C.c_size_t]
     sizes = [0, 1, 63, 64, 65, 1000, 16 << 10, (16 << 10) + 1, 100000, 128 << 10, (128 << 10) + 1, 256 << 10, (256 << 10) + 1,
              1 << 20, 5 << 20, 1 << 27, 1 << 30, (1 << 30) + 1, 1 << 33]
-    dicts = [0, 1, 500, 16000, 112640, 130000, 300000, 1 << 22]
+    dicts = [0, 1, 500, 16000, 112640, 130000, 300000, 1 << 22, 1 << 29, (1 << 30) + 5, 1 << 31]
+    names = ("window_log", "chain_log", "hash_log", "search_log", "min_match", "target_length", "strategy")
     checked = 0
-    for level in list(range(-7, 23)) + [30]:
+    for level in list(range(-7, 23)) + [30, -200000]:
         for s in sizes:
             for d in dicts:
-                want = Z.ZSTD_getCParams(level, s, d).windowLog
-                got = zstd.ZstdCompressionParameters.from_level(level, source_size=s, dict_size=d).window_log
-                assert got == want, (level, s, d, got, want)
+                w = Z.ZSTD_getCParams(level, s, d)
+                want = (w.windowLog, w.chainLog, w.hashLog, w.searchLog, w.minMatch, w.targetLength, w.strategy)
+                p = zstd.ZstdCompressionParameters.from_level(level, source_size=s, dict_size=d)
+                assert tuple(getattr(p, k) for k in names) == want, (level, s, d)
                 checked += 1
-    assert checked > 4000
-    assert zstd.ZstdCompressionParameters.from_level(3, source_size=1000, window_log=15).window_log == 15
+    assert checked > 6000
+    p = zstd.ZstdCompressionParameters.from_level(3, source_size=1000, window_log=15)
+    assert p.window_log == 15 and p.hash_log == Z.ZSTD_getCParams(3, 1000, 0).hashLog
+    with pytest.raises(zstd.ZstdError, match="not supported by the B200 backend"):
+        zstd.ZstdCompressionParameters.from_level(3, hash_log=20)            # asking for a different match finder is still refused
